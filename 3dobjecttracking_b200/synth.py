@@ -1,0 +1,306 @@
+"""Seeded synthetic workloads for the M3T pose-optimisation hot path.
+
+ctypes wrapper around synth/libm3t_synth.so (analytic sparse-viewpoint models of the reference's
+triangle prism, synthetic 640x480 BGR8 / U16 frames, ground-truth + perturbed start poses) plus the
+BASELINE.json workload presets C1..C4. Pure data tooling: no CUDA, no oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "synth", "libm3t_synth.so")
+_lib = None
+
+REGION_POINT_FLOATS = 38  # 152 B, RegionModel::DataPoint (region_model.h:89-95)
+DEPTH_POINT_FLOATS = 36   # 144 B, DepthModel::DataPoint (depth_model.h:67-71)
+
+
+class Intrinsics(C.Structure):
+    """m3t::Intrinsics (common.h:25-29); layout shared by m3tb_intrinsics / orc_intrinsics."""
+    _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("ppu", C.c_float), ("ppv", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+    def copy(self):
+        return Intrinsics(self.fu, self.fv, self.ppu, self.ppv, self.width, self.height)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            from . import _build
+            _build.build_synth()
+        L = C.CDLL(_LIB_PATH)
+        fp = C.POINTER(C.c_float)
+        L.m3ts_n_views.restype = C.c_int
+        L.m3ts_n_views.argtypes = [C.c_int]
+        for name in ("m3ts_generate_region_model", "m3ts_generate_depth_model"):
+            f = getattr(L, name)
+            f.restype = C.c_int
+            f.argtypes = [C.c_int, C.c_int, C.c_float, C.c_uint64, fp, fp, C.c_void_p]
+        L.m3ts_ground_truth_pose.restype = None
+        L.m3ts_ground_truth_pose.argtypes = [C.c_uint64, C.c_int, C.POINTER(Intrinsics), C.c_float, C.c_float,
+                                             C.c_float, fp]
+        L.m3ts_perturb_pose.restype = None
+        L.m3ts_perturb_pose.argtypes = [C.c_uint64, C.c_int, C.c_float, C.c_float, fp, fp]
+        L.m3ts_render_color.restype = None
+        L.m3ts_render_color.argtypes = [C.POINTER(Intrinsics), fp, C.c_uint64, C.POINTER(C.c_uint8),
+                                        C.POINTER(C.c_uint8), C.c_float, C.c_void_p, C.c_size_t]
+        L.m3ts_render_depth.restype = None
+        L.m3ts_render_depth.argtypes = [C.POINTER(Intrinsics), fp, C.c_uint64, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+@dataclass
+class Model:
+    """Sparse viewpoint model in the reference's layout (views x points x DataPoint)."""
+    kind: str                    # "region" | "depth"
+    orientations: np.ndarray     # [nv,3] f32
+    view_scalars: np.ndarray     # [nv] f32: contour_length / surface_area
+    points: np.ndarray           # [nv,np,38|36] f32
+    stride_depth_offset: float = 0.002   # model.h:161-167
+    max_radius_depth_offset: float = 0.05
+
+    @property
+    def n_views(self):
+        return self.points.shape[0]
+
+    @property
+    def n_points(self):
+        return self.points.shape[1]
+
+
+def generate_region_model(n_divides=4, n_points=200, sphere_radius=0.8, seed=0) -> Model:
+    nv = lib().m3ts_n_views(n_divides)
+    ori = np.zeros((nv, 3), np.float32)
+    cl = np.zeros(nv, np.float32)
+    pts = np.zeros((nv, n_points, REGION_POINT_FLOATS), np.float32)
+    r = lib().m3ts_generate_region_model(n_divides, n_points, sphere_radius, seed, _fp(ori), _fp(cl),
+                                         pts.ctypes.data_as(C.c_void_p))
+    assert r == nv, r
+    return Model("region", ori, cl, pts)
+
+
+def generate_depth_model(n_divides=4, n_points=200, sphere_radius=0.8, seed=0) -> Model:
+    nv = lib().m3ts_n_views(n_divides)
+    ori = np.zeros((nv, 3), np.float32)
+    sa = np.zeros(nv, np.float32)
+    pts = np.zeros((nv, n_points, DEPTH_POINT_FLOATS), np.float32)
+    r = lib().m3ts_generate_depth_model(n_divides, n_points, sphere_radius, seed, _fp(ori), _fp(sa),
+                                        pts.ctypes.data_as(C.c_void_p))
+    assert r == nv, r
+    return Model("depth", ori, sa, pts)
+
+
+def pose_mul(a, b):
+    """[R|t] x [R|t] for float32 [3,4] arrays (float64 internally; data prep only)."""
+    A = np.eye(4); A[:3] = a
+    B = np.eye(4); B[:3] = b
+    return (A @ B)[:3].astype(np.float32)
+
+
+def pose_inv(a):
+    A = np.eye(4); A[:3] = a
+    return np.linalg.inv(A)[:3].astype(np.float32)
+
+
+def ground_truth_pose(seed, index, intr, margin_px, z_min, z_max):
+    out = np.zeros(12, np.float32)
+    lib().m3ts_ground_truth_pose(seed, index, C.byref(intr), margin_px, z_min, z_max, _fp(out))
+    return out.reshape(3, 4)
+
+
+def perturb_pose(seed, index, rot_deg, trans_m, pose):
+    src = np.ascontiguousarray(pose, np.float32).reshape(12)
+    out = np.zeros(12, np.float32)
+    lib().m3ts_perturb_pose(seed, index, rot_deg, trans_m, _fp(src), _fp(out))
+    return out.reshape(3, 4)
+
+
+def render_color(intr, body2camera, seed, fg_mean=(40, 80, 200), bg_mean=(120, 120, 120), sigma=10.0, out=None):
+    """BGR8 frame [H, pitch] with pitch = 3*W rounded up to 16 B (cv::Mat-style row pitch)."""
+    pitch = (3 * intr.width + 15) // 16 * 16
+    if out is None:
+        out = np.zeros((intr.height, pitch), np.uint8)
+    fg = (C.c_uint8 * 3)(*fg_mean)
+    bg = (C.c_uint8 * 3)(*bg_mean)
+    b2c = np.ascontiguousarray(body2camera, np.float32).reshape(12)
+    lib().m3ts_render_color(C.byref(intr), _fp(b2c), seed, fg, bg, sigma, out.ctypes.data_as(C.c_void_p), out.strides[0])
+    return out
+
+
+def render_depth(intr, body2camera, seed, background_z=1.0, noise_sigma=0.001, invalid_fraction=0.01,
+                 depth_scale=0.001, out=None):
+    if out is None:
+        out = np.zeros((intr.height, intr.width), np.uint16)
+    b2c = np.ascontiguousarray(body2camera, np.float32).reshape(12)
+    lib().m3ts_render_depth(C.byref(intr), _fp(b2c), seed, background_z, noise_sigma, invalid_fraction, depth_scale,
+                            out.ctypes.data_as(C.c_void_p), out.strides[0])
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# Workload presets (BASELINE.json configs; parameters from SURVEY.md §8d)
+# --------------------------------------------------------------------------------------------------
+@dataclass
+class RegionSettings:
+    n_lines_max: int = 200
+    min_continuous_distance: float = 3.0
+    function_amplitude: float = 0.43
+    function_slope: float = 0.5
+    learning_rate: float = 1.3
+    n_global_iterations: int = 1
+    scales: tuple = (6, 4, 2, 1)
+    standard_deviations: tuple = (15.0, 5.0, 3.5, 1.5)
+    n_histogram_bins: int = 16
+    learning_rate_f: float = 0.2
+    learning_rate_b: float = 0.2
+    unconsidered_line_length: float = 0.5
+    max_considered_line_length: float = 20.0
+
+
+@dataclass
+class DepthSettings:
+    n_points_max: int = 200
+    stride_length: float = 0.005
+    considered_distances: tuple = (0.05, 0.02, 0.01)
+    standard_deviations: tuple = (0.05, 0.03, 0.02)
+
+
+@dataclass
+class Workload:
+    name: str
+    n_bodies: int
+    region: RegionSettings | None
+    depth: DepthSettings | None
+    tikhonov_rotation: float
+    tikhonov_translation: float
+    n_corr_iterations: int
+    n_update_iterations: int
+    color_intrinsics: Intrinsics
+    depth_intrinsics: Intrinsics
+    color_world2camera: np.ndarray          # [3,4]
+    depth_world2camera: np.ndarray          # [3,4]
+    depth_scale: float
+    region_model: Model | None
+    depth_model: Model | None
+    color_frames: np.ndarray | None         # [nb,H,pitch] u8 (one frame per body)
+    depth_frames: np.ndarray | None         # [nb,H,W] u16
+    gt_body2world: np.ndarray               # [nb,3,4]
+    start_body2world: np.ndarray            # [nb,3,4]
+    seed: int = 0
+    notes: dict = field(default_factory=dict)
+
+    @property
+    def lines_per_body(self):
+        return self.region.n_lines_max if self.region else 0
+
+    @property
+    def points_per_body(self):
+        return self.depth.n_points_max if self.depth else 0
+
+
+PRESETS = {
+    # name: (n_bodies, n_lines, n_points, rbot_shape)
+    "c1": dict(n_bodies=1, n_lines=200, n_points=0, rbot=False),
+    "c2": dict(n_bodies=1, n_lines=200, n_points=200, rbot=False),
+    "c3": dict(n_bodies=64, n_lines=300, n_points=0, rbot=True),
+    "c4": dict(n_bodies=128, n_lines=512, n_points=512, rbot=False),  # per-GPU shard of 1024 bodies / 8 GPUs
+}
+
+
+def default_color_intrinsics(rbot=False):
+    if rbot:  # rbot_evaluator.h:40-41 re-centred to a 640x480 frame
+        return Intrinsics(650.048, 647.183, 319.5, 239.5, 640, 480)
+    return Intrinsics(614.0, 614.5, 321.3, 238.9, 640, 480)
+
+
+def default_depth_intrinsics():
+    return Intrinsics(385.7, 385.9, 322.1, 241.6, 640, 480)
+
+
+def _rot(axis, deg):
+    a = np.deg2rad(deg)
+    x, y, z = np.asarray(axis, float) / np.linalg.norm(axis)
+    c, s, Cc = np.cos(a), np.sin(a), 1 - np.cos(a)
+    return np.array([[c + x * x * Cc, x * y * Cc - z * s, x * z * Cc + y * s],
+                     [y * x * Cc + z * s, c + y * y * Cc, y * z * Cc - x * s],
+                     [z * x * Cc - y * s, z * y * Cc + x * s, c + z * z * Cc]])
+
+
+def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divides=4, seed=0, rot_deg=3.0,
+                  trans_m=0.005, rbot=None, model_points=None, frames=True, color_sigma=10.0) -> Workload:
+    """Build one of the BASELINE.json workloads (optionally resized) from (seed, body index)."""
+    preset = dict(PRESETS[name])
+    if n_bodies is not None:
+        preset["n_bodies"] = n_bodies
+    if n_lines is not None:
+        preset["n_lines"] = n_lines
+    if n_points is not None:
+        preset["n_points"] = n_points
+    if rbot is not None:
+        preset["rbot"] = rbot
+    nb = preset["n_bodies"]
+    rb = preset["rbot"]
+    region = depth = None
+    if preset["n_lines"] > 0:
+        region = RegionSettings(n_lines_max=preset["n_lines"])
+        if rb:  # evaluate_rbot_dataset.cpp:25-44,76-83
+            region.scales = (5, 2, 2, 1)
+            region.standard_deviations = (20.0, 7.0, 3.0, 1.5)
+            region.function_amplitude = 0.36
+            region.function_slope = 0.0
+            region.n_histogram_bins = 32
+    if preset["n_points"] > 0:
+        depth = DepthSettings(n_points_max=preset["n_points"])
+    ci = default_color_intrinsics(rb)
+    di = default_depth_intrinsics()
+    # non-identity camera poses (the reference's fixture has a non-identity depth camera2world as well)
+    c_w2c = np.zeros((3, 4), np.float32)
+    c_w2c[:, :3] = _rot((0.2, 1.0, 0.1), 4.0)
+    c_w2c[:, 3] = (0.01, -0.02, 0.03)
+    d_rel = np.zeros((3, 4), np.float32)      # colour-camera -> depth-camera
+    d_rel[:, :3] = _rot((1.0, 0.3, -0.2), 0.6)
+    d_rel[:, 3] = (-0.015, 0.001, 0.002)
+    d_w2c = pose_mul(d_rel, c_w2c)
+    c_c2w = pose_inv(c_w2c)
+
+    mp_r = model_points or max(preset["n_lines"], 1)
+    mp_d = model_points or max(preset["n_points"], 1)
+    region_model = generate_region_model(n_divides, mp_r, 0.8, seed) if region else None
+    depth_model = generate_depth_model(n_divides, mp_d, 0.8, seed) if depth else None
+
+    max_scale = max(region.scales) if region else 0
+    margin = 19 * max_scale / 2 + 75.0  # longest line half-length + body radius in px (+ slack for the depth camera)
+    gt = np.zeros((nb, 3, 4), np.float32)
+    start = np.zeros((nb, 3, 4), np.float32)
+    pitch = (3 * ci.width + 15) // 16 * 16
+    color = np.zeros((nb, ci.height, pitch), np.uint8) if (region and frames) else None
+    dframes = np.zeros((nb, di.height, di.width), np.uint16) if (depth and frames) else None
+    for b in range(nb):
+        b2c = ground_truth_pose(seed, b, ci, margin, 0.5, 0.7)
+        b2w = pose_mul(c_c2w, b2c)
+        gt[b] = b2w
+        start[b] = perturb_pose(seed, b, rot_deg, trans_m, b2w)
+        if color is not None:
+            render_color(ci, pose_mul(c_w2c, b2w), seed * 1000003 + b, sigma=color_sigma, out=color[b])
+        if dframes is not None:
+            render_depth(di, pose_mul(d_w2c, b2w), seed * 1000003 + b, depth_scale=0.001, out=dframes[b])
+    lam = (1000.0, 30000.0)  # optimizer.h:52-53
+    return Workload(name=name, n_bodies=nb, region=region, depth=depth, tikhonov_rotation=lam[0],
+                    tikhonov_translation=lam[1], n_corr_iterations=7, n_update_iterations=2,
+                    color_intrinsics=ci, depth_intrinsics=di, color_world2camera=c_w2c, depth_world2camera=d_w2c,
+                    depth_scale=0.001, region_model=region_model, depth_model=depth_model, color_frames=color,
+                    depth_frames=dframes, gt_body2world=gt, start_body2world=start, seed=seed,
+                    notes=dict(n_divides=n_divides, rot_deg=rot_deg, trans_m=trans_m, rbot=rb, color_sigma=color_sigma))

@@ -1,0 +1,242 @@
+/* m3t_b200.h — C ABI of libm3t_b200: the B200-native (sm_100a) implementation of M3T's
+ * per-frame pose-optimisation hot path (RegionModality correspondence lines + DepthModality
+ * point-to-plane -> per-body 6x6 Hessian / 6-gradient -> Tikhonov Gauss-Newton solve -> SE(3) update).
+ *
+ * The reference (DLR-RM/3DObjectTracking, M3T/) has no FFI: its extension surface is C++ subclassing
+ * of m3t::Modality (M3T/include/m3t/modality.h:56-155). This header is the boundary a maintainer binds
+ * instead; every entry point names the reference method(s) it replaces. The header-only C++ adapters in
+ * 3dobjecttracking_b200/host/ (m3t_b200::RegionModality, DepthModality, Optimizer, Tracker ...) keep the
+ * reference's class / method names on top of these calls. See INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, opaque context handle, no torch / Eigen / OpenCV types in any signature;
+ *  - every function returns an int status: 0 = ok, negative = m3tb_status error; never throws;
+ *    m3tb_last_error() returns a human-readable message for the last failure on that context
+ *    (the reference prints to std::cerr and returns false, e.g. region_modality.cpp:1813-1819);
+ *  - poses are float[12], row-major 3x4 [R | t] (the top three rows of m3t::Transform3fA);
+ *  - the 6-vector parameter order is [rot_x, rot_y, rot_z, trans_x, trans_y, trans_z], variation in
+ *    the body frame, right-multiplied (link.cpp:222-238);
+ *  - gradients are float[6]; Hessians float[36] (symmetric, so row/column-major is moot);
+ *  - all work is enqueued on the context's CUDA stream (m3tb_set_stream); calls that return data
+ *    to host memory synchronise that stream before returning;
+ *  - one host thread per context (the reference's Calculate* methods are single-threaded as well,
+ *    tracker.cpp:251-255). Contexts are independent.
+ *  - there is NO CPU fallback: every compute entry point fails with M3TB_ERR_CUDA when no
+ *    sm_100-class device is usable.
+ */
+#ifndef M3T_B200_H_
+#define M3T_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M3TB_MAX_SCHEDULE 8      /* max entries in scales / standard_deviations / considered_distances */
+#define M3TB_N_DEPTH_OFFSETS 30  /* kMaxNDepthOffsets, M3T/include/m3t/model.h:58 */
+#define M3TB_FUNCTION_LENGTH 8   /* region_modality.h:415 (compiled-in; other values are rejected) */
+#define M3TB_DISTRIBUTION_LENGTH 12 /* region_modality.h:416 (compiled-in) */
+#define M3TB_REGION_POINT_BYTES 152 /* RegionModel::DataPoint as stored in .bin, region_model.h:89-95 */
+#define M3TB_DEPTH_POINT_BYTES 144  /* DepthModel::DataPoint as stored in .bin, depth_model.h:67-71 */
+
+typedef enum m3tb_status {
+  M3TB_OK = 0,
+  M3TB_ERR_INVALID = -1,   /* bad argument / id out of range / object not set up */
+  M3TB_ERR_CUDA = -2,      /* CUDA runtime failure or no usable device */
+  M3TB_ERR_UNSUPPORTED = -3, /* option of the reference that this build does not implement */
+  M3TB_ERR_NOT_SET_UP = -4 /* mirrors "Set up ... first" (IsSetup() == false) */
+} m3tb_status;
+
+typedef struct m3tb_ctx m3tb_ctx;
+
+/* m3t::Intrinsics, M3T/include/m3t/common.h:25-29 */
+typedef struct m3tb_intrinsics {
+  float fu, fv, ppu, ppv;
+  int32_t width, height;
+} m3tb_intrinsics;
+
+/* Parameters of m3t::RegionModality, defaults region_modality.h:411-443 */
+typedef struct m3tb_region_params {
+  int32_t n_lines_max;             /* 200 */
+  int32_t use_adaptive_coverage;   /* 0 */
+  float reference_contour_length;  /* 0 */
+  float min_continuous_distance;   /* 3 */
+  int32_t function_length;         /* 8  (must equal M3TB_FUNCTION_LENGTH) */
+  int32_t distribution_length;     /* 12 (must equal M3TB_DISTRIBUTION_LENGTH) */
+  float function_amplitude;        /* 0.43 */
+  float function_slope;            /* 0.5 */
+  float learning_rate;             /* 1.3 */
+  int32_t n_global_iterations;     /* 1 */
+  int32_t n_scales;                /* 4 */
+  int32_t scales[M3TB_MAX_SCHEDULE];           /* {6,4,2,1} */
+  int32_t n_standard_deviations;   /* 4 */
+  float standard_deviations[M3TB_MAX_SCHEDULE]; /* {15,5,3.5,1.5} */
+  int32_t n_histogram_bins;        /* 16 */
+  float learning_rate_f;           /* 0.2 */
+  float learning_rate_b;           /* 0.2 */
+  float unconsidered_line_length;  /* 0.5 */
+  float max_considered_line_length; /* 20 */
+  int32_t measure_occlusions;      /* 0 */
+  float measured_depth_offset_radius; /* 0.01 */
+  float measured_occlusion_radius;    /* 0.01 */
+  float measured_occlusion_threshold; /* 0.03 */
+  int32_t n_unoccluded_iterations; /* 10 */
+  int32_t min_n_unoccluded_lines;  /* 0 */
+} m3tb_region_params;
+
+/* Parameters of m3t::DepthModality, defaults depth_modality.h:302-321 */
+typedef struct m3tb_depth_params {
+  int32_t n_points_max;            /* 200 */
+  int32_t use_adaptive_coverage;   /* 0 */
+  int32_t use_depth_scaling;       /* 0 */
+  float reference_surface_area;    /* 0 */
+  float stride_length;             /* 0.005 */
+  int32_t n_considered_distances;  /* 3 */
+  float considered_distances[M3TB_MAX_SCHEDULE]; /* {0.05,0.02,0.01} */
+  int32_t n_standard_deviations;   /* 3 */
+  float standard_deviations[M3TB_MAX_SCHEDULE];  /* {0.05,0.03,0.02} */
+  int32_t measure_occlusions;      /* 0 */
+  float measured_depth_offset_radius; /* 0.01 */
+  float measured_occlusion_radius;    /* 0.01 */
+  float measured_occlusion_threshold; /* 0.03 */
+  int32_t n_unoccluded_iterations; /* 10 */
+  int32_t min_n_unoccluded_points; /* 0 */
+} m3tb_depth_params;
+
+/* Parameters of m3t::Optimizer, defaults optimizer.h:52-53 */
+typedef struct m3tb_optimizer_params {
+  float tikhonov_parameter_rotation;    /* 1000 */
+  float tikhonov_parameter_translation; /* 30000 */
+} m3tb_optimizer_params;
+
+/* Per-line state kept between CalculateCorrespondences and CalculateGradientAndHessian
+ * (RegionModality::DataLine, region_modality.h:150-165) - debug / parity read-back only. */
+typedef struct m3tb_region_line {
+  int32_t model_index;      /* index of the model point inside the closest view */
+  int32_t valid;            /* 1 if the line survived IsLineValid + CalculateSegmentProbabilities */
+  float center_f_body[3];
+  float center_u, center_v;
+  float normal_u, normal_v;
+  float delta_r;
+  float normal_component_to_scale;
+  float distribution[M3TB_DISTRIBUTION_LENGTH];
+  float mean;
+  float measured_variance;
+} m3tb_region_line;
+
+/* DepthModality::DataPoint (depth_modality.h:139-150) - debug / parity read-back only. */
+typedef struct m3tb_depth_point {
+  int32_t model_index;
+  int32_t valid;
+  float center_f_body[3];
+  float normal_f_body[3];
+  float correspondence_center_f_camera[3];
+} m3tb_depth_point;
+
+/* ---- defaults (the reference's in-class member initialisers) ------------------------------- */
+void m3tb_region_params_default(m3tb_region_params* p);       /* region_modality.h:411-443 */
+void m3tb_depth_params_default(m3tb_depth_params* p);         /* depth_modality.h:302-321 */
+void m3tb_optimizer_params_default(m3tb_optimizer_params* p); /* optimizer.h:52-53 */
+
+/* ---- context -------------------------------------------------------------------------------- */
+/* Creates a context on CUDA device `device`. Capacities are fixed at creation (the reference
+ * allocates per object; here all bodies live in one batch). */
+int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3tb_ctx** out);
+int m3tb_destroy(m3tb_ctx* ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream) for all work; NULL = default stream. */
+int m3tb_set_stream(m3tb_ctx* ctx, void* cuda_stream);
+int m3tb_synchronize(m3tb_ctx* ctx);
+const char* m3tb_last_error(const m3tb_ctx* ctx);
+/* Number of kernels this context has launched since creation (bench.py's gpu_launches). */
+int64_t m3tb_launch_count(const m3tb_ctx* ctx);
+
+/* ---- sparse viewpoint models (inputs of RegionModel/DepthModel::GetClosestView) --------------- */
+/* Replaces RegionModel::views_ (region_model.h:97-110) as filled by RegionModel::LoadModel
+ * (region_model.cpp:259-307). `points` is n_views*n_points RegionModel::DataPoint records exactly
+ * as stored in the .bin (152 B AoS); `orientations` n_views*3; `contour_lengths` n_views. */
+int m3tb_set_region_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points,
+                          const float* orientations, const float* contour_lengths,
+                          const void* points, float stride_depth_offset,
+                          float max_radius_depth_offset);
+/* Replaces DepthModel::views_ (depth_model.h:73-86); `points` are 144-B DepthModel::DataPoint. */
+int m3tb_set_depth_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points,
+                         const float* orientations, const float* surface_areas,
+                         const void* points, float stride_depth_offset,
+                         float max_radius_depth_offset);
+
+/* ---- cameras (Camera::intrinsics(), world2camera_pose(), image(); camera.h / camera.cpp:39) --- */
+int m3tb_set_color_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics,
+                          const float world2camera[12]);
+int m3tb_set_depth_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics,
+                          const float world2camera[12], float depth_scale);
+/* Camera::UpdateImage: copy a host cv::Mat-style frame (CV_8UC3 BGR / CV_16UC1) to the device.
+ * `pitch` is the host row pitch in bytes. Host memory stays caller-owned; pinned memory makes the
+ * copy asynchronous on the context stream. */
+int m3tb_upload_color(m3tb_ctx* ctx, int cam, const uint8_t* bgr, size_t pitch);
+int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitch);
+/* Same, for frames that already live in device memory (device-resident pipelines, bench `value`). */
+int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch);
+int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch);
+
+/* ---- bodies: one rigid body = Body + RegionModality and/or DepthModality + root Link + Optimizer.
+ * region == NULL / depth == NULL leaves that modality out (model / camera id then ignored).
+ * Equivalent of constructing the objects and calling their SetUp() (region_modality.cpp:37-77,
+ * depth_modality.cpp:34-60, optimizer.cpp:22-40). ------------------------------------------- */
+int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region,
+                  const m3tb_depth_params* depth, const m3tb_optimizer_params* optimizer,
+                  int region_model, int depth_model, int color_camera, int depth_camera);
+int m3tb_n_bodies(const m3tb_ctx* ctx);
+
+/* Body::set_body2world_pose / body2world_pose (body.cpp:85-90) for bodies [first, first+count). */
+int m3tb_set_poses(m3tb_ctx* ctx, int first, int count, const float* body2world);
+int m3tb_get_poses(m3tb_ctx* ctx, int first, int count, float* body2world);
+
+/* ColorHistograms::histogram_f_/histogram_b_ (color_histograms.h:96-97), n_bins^3 floats each. */
+int m3tb_set_histograms(m3tb_ctx* ctx, int body, const float* histogram_f, const float* histogram_b);
+int m3tb_get_histograms(m3tb_ctx* ctx, int body, float* histogram_f, float* histogram_b);
+
+/* ---- the hot path, fused: Tracker::ExecuteTrackingStep without CalculateResults (tracker.cpp:344-361)
+ * for every body of the context: for corr in [0,n_corr): CalculateCorrespondences; for upd in
+ * [0,n_update): CalculateGradientAndHessian + Optimizer::CalculateOptimization. One kernel launch. */
+int m3tb_tracking_step(m3tb_ctx* ctx, int iteration, int n_corr_iterations, int n_update_iterations);
+/* One correspondence iteration (the unit of BASELINE.json's metric): CalculateCorrespondences +
+ * n_update x (CalculateGradientAndHessian + CalculateOptimization). */
+int m3tb_corr_iteration(m3tb_ctx* ctx, int iteration, int corr_iteration, int n_update_iterations);
+
+/* Tracker::StartModalities -> RegionModality::StartModality (region_modality.cpp:375-388):
+ * first_iteration_ = iteration; histogram initialisation from the current pose and frame. */
+int m3tb_start_modalities(m3tb_ctx* ctx, int iteration);
+/* Tracker::CalculateResults -> RegionModality::CalculateResults (region_modality.cpp:572-583):
+ * online histogram update with learning_rate_f/b. */
+int m3tb_calculate_results(m3tb_ctx* ctx, int iteration);
+
+/* ---- the hot path, fine-grained: mirrors the Modality / Optimizer methods 1:1 (parity, debugging,
+ * and the B200 Modality adapters driven by an unmodified m3t::Tracker). g/H may be NULL. ------- */
+/* RegionModality::CalculateCorrespondences (region_modality.cpp:390-465), all bodies. */
+int m3tb_region_correspondences(m3tb_ctx* ctx, int iteration, int corr_iteration);
+/* RegionModality::CalculateGradientAndHessian (region_modality.cpp:485-558): g[n_bodies][6], H[n_bodies][36]. */
+int m3tb_region_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration,
+                                 float* gradients, float* hessians);
+/* DepthModality::CalculateCorrespondences (depth_modality.cpp:252-315). */
+int m3tb_depth_correspondences(m3tb_ctx* ctx, int iteration, int corr_iteration);
+/* DepthModality::CalculateGradientAndHessian (depth_modality.cpp:333-381). */
+int m3tb_depth_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration,
+                                float* gradients, float* hessians);
+/* Optimizer::CalculateOptimization (optimizer.cpp:144-167) for every body, using the gradients /
+ * Hessians left on the device by the two calls above (Link::CalculateGradientAndHessian sums them,
+ * link.cpp:184-193), then Link::UpdatePoses (link.cpp:205-241). */
+int m3tb_calculate_optimization(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration);
+
+/* ---- parity read-back of the per-line / per-point state (data_lines_, data_points_) ----------- */
+/* `lines` must hold n_lines_max records; *n_out receives how many model points were processed. */
+int m3tb_get_region_lines(m3tb_ctx* ctx, int body, m3tb_region_line* lines, int capacity, int* n_out);
+int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int capacity, int* n_out);
+/* Index of the closest view chosen by the last *correspondences call (GetClosestView). */
+int m3tb_get_closest_views(m3tb_ctx* ctx, int body, int* region_view, int* depth_view);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M3T_B200_H_ */

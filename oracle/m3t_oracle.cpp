@@ -1,0 +1,1109 @@
+// m3t_oracle.cpp — CPU oracle (TEST INFRASTRUCTURE ONLY, see m3t_oracle.h).
+//
+// Scalar float32 restatement of the reference's pose-optimisation hot path. Every function cites the
+// reference file:line (relative to /root/reference/M3T/) it follows. Compile with
+// -ffp-contract=off so that each float operation rounds once, in the order written here; the CUDA
+// path is compiled with -fmad=false for the same reason, which makes the per-line state comparable
+// bit for bit (ORC_ROTATION_LINEAR / ORC_EXP_RODRIGUES modes).
+#include "m3t_oracle.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// Small fixed-size helpers (stand-ins for Eigen::Transform<float,3,Affine> / Matrix3f / Vector3f)
+// Pose layout: float[12] row-major 3x4, p[4*i+j]; p[4*i+3] = translation.
+// ---------------------------------------------------------------------------------------------
+inline float R_(const float* p, int i, int j) { return p[4 * i + j]; }
+inline float T_(const float* p, int i) { return p[4 * i + 3]; }
+
+// Transform3fA * Transform3fA (Affine x Affine): res.affine() = lhs.affine() * rhs.matrix()
+void PoseMul(const float* a, const float* b, float* out) {
+  float r[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j)
+      r[4 * i + j] = R_(a, i, 0) * R_(b, 0, j) + R_(a, i, 1) * R_(b, 1, j) + R_(a, i, 2) * R_(b, 2, j);
+    r[4 * i + 3] = R_(a, i, 0) * T_(b, 0) + R_(a, i, 1) * T_(b, 1) + R_(a, i, 2) * T_(b, 2) + T_(a, i);
+  }
+  std::memcpy(out, r, sizeof(r));
+}
+
+// Transform3fA * Vector3f : linear * v + translation
+inline void PoseApply(const float* p, const float* v, float* out) {
+  float x = R_(p, 0, 0) * v[0] + R_(p, 0, 1) * v[1] + R_(p, 0, 2) * v[2] + T_(p, 0);
+  float y = R_(p, 1, 0) * v[0] + R_(p, 1, 1) * v[1] + R_(p, 1, 2) * v[2] + T_(p, 1);
+  float z = R_(p, 2, 0) * v[0] + R_(p, 2, 1) * v[1] + R_(p, 2, 2) * v[2] + T_(p, 2);
+  out[0] = x; out[1] = y; out[2] = z;
+}
+
+// Eigen 3x3 inverse (compute_inverse_size3_helper): cofactors, det from first column, * (1/det).
+// m, out: row-major 3x3.
+void Inverse3(const float* m, float* out) {
+  auto M = [&](int i, int j) { return m[3 * i + j]; };
+  auto cof = [&](int i, int j) {
+    int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+    return M(i1, j1) * M(i2, j2) - M(i1, j2) * M(i2, j1);
+  };
+  float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+  float det = c00 * M(0, 0) + c10 * M(1, 0) + c20 * M(2, 0);
+  float invdet = 1.0f / det;
+  out[0] = c00 * invdet; out[1] = c10 * invdet; out[2] = c20 * invdet;
+  out[3] = cof(0, 1) * invdet; out[4] = cof(1, 1) * invdet; out[5] = cof(2, 1) * invdet;
+  out[6] = cof(0, 2) * invdet; out[7] = cof(1, 2) * invdet; out[8] = cof(2, 2) * invdet;
+}
+
+// Transform3fA::inverse() for Affine mode: linear().inverse(), translation = -inv * t.
+void PoseInverse(const float* p, float* out) {
+  float m[9], inv[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) m[3 * i + j] = R_(p, i, j);
+  Inverse3(m, inv);
+  float r[12];
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) r[4 * i + j] = inv[3 * i + j];
+    // res.translation() = -res.linear() * translation()
+    r[4 * i + 3] = (-inv[3 * i + 0]) * T_(p, 0) + (-inv[3 * i + 1]) * T_(p, 1) + (-inv[3 * i + 2]) * T_(p, 2);
+  }
+  std::memcpy(out, r, sizeof(r));
+}
+
+// Transform3fA::rotation(): for an Affine transform Eigen computes the rotation factor of the
+// linear block via JacobiSVD (R = U V^T, computeRotationScaling). Restated as the polar factor,
+// evaluated in double with Newton's iteration X <- (X + X^-T)/2 and rounded once to float.
+void PoseRotation(const float* p, int rotation_mode, float* r /*row-major 3x3*/) {
+  if (rotation_mode == ORC_ROTATION_LINEAR) {
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r[3 * i + j] = R_(p, i, j);
+    return;
+  }
+  double x[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) x[3 * i + j] = double(R_(p, i, j));
+  for (int it = 0; it < 12; ++it) {
+    auto X = [&](int i, int j) { return x[3 * i + j]; };
+    double c[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        c[3 * i + j] = X(i1, j1) * X(i2, j2) - X(i1, j2) * X(i2, j1);
+      }
+    double det = c[0] * x[0] + c[1] * x[1] + c[2] * x[2];
+    double delta = 0.0;
+    for (int k = 0; k < 9; ++k) {
+      double nx = 0.5 * (x[k] + c[k] / det);  // X^-T = cofactor matrix / det
+      delta = std::max(delta, std::fabs(nx - x[k]));
+      x[k] = nx;
+    }
+    if (delta < 1e-15) break;
+  }
+  for (int k = 0; k < 9; ++k) r[k] = float(x[k]);
+}
+
+// Eigen's Vector::normalized(): v / sqrt(squaredNorm) if squaredNorm > 0.
+inline void Normalize3(float* v) {
+  float z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+  if (z > 0.0f) {
+    float n = std::sqrt(z);
+    v[0] /= n; v[1] /= n; v[2] /= n;
+  }
+}
+inline void Normalize2(float* v) {
+  float z = v[0] * v[0] + v[1] * v[1];
+  if (z > 0.0f) {
+    float n = std::sqrt(z);
+    v[0] /= n; v[1] /= n;
+  }
+}
+
+// common.h:170-176
+template <typename T>
+inline T LastValidValue(const T* values, int n, int idx) {
+  return idx < n ? values[idx] : values[n - 1];
+}
+
+// common.h:48-56
+inline float sgnf(float v) { return v < 0.0f ? -1.0f : (v > 0.0f ? 1.0f : 0.0f); }
+
+inline int Bitshift(int n_bins) {  // color_histograms.cpp:131-159
+  switch (n_bins) {
+    case 2: return 7;
+    case 4: return 6;
+    case 8: return 5;
+    case 16: return 4;
+    case 32: return 3;
+    case 64: return 2;
+    default: return -1;
+  }
+}
+
+inline int HistIndex(int n_bins, int bitshift, const uint8_t* px) {  // color_histograms.cpp:97-99
+  return (px[0] >> bitshift) * n_bins * n_bins + (px[1] >> bitshift) * n_bins + (px[2] >> bitshift);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Region modality precalculated variables
+// ---------------------------------------------------------------------------------------------
+struct RegionVars {
+  // PrecalculateFunctionLookup / PrecalculateDistributionVariables (region_modality.cpp:910-936)
+  float lookup_f[8], lookup_b[8];
+  int line_length_in_segments;
+  float dl_minus_1_half, dl_plus_1_half;
+  float min_expected_variance;
+  // PrecalculateCameraVariables (:945-966)
+  float fu, fv, ppu, ppv;
+  int w_m1, h_m1, w_m2, h_m2;
+  // PrecalculatePoseVariables (:1000-1009)
+  float body2camera[12];
+  float rot[9];  // body2camera_rotation_
+  // PrecalculateIterationDependentVariables (:1011-1023)
+  int scale;
+  float fscale;
+  int line_length, line_length_minus_1;
+  float line_length_minus_1_half, line_length_half_minus_1;
+  float variance;
+  int n_bins, bitshift;
+};
+
+void FunctionLookup(const orc_region_params* p, float* lf, float* lb, float* min_expected_variance) {
+  // region_modality.cpp:910-923
+  for (int i = 0; i < p->function_length; ++i) {
+    float x = float(i) - float(p->function_length - 1) / 2.0f;
+    if (p->function_slope == 0.0f)
+      lf[i] = 0.5f - p->function_amplitude * float((0.0f < x) - (x < 0.0f));
+    else
+      lf[i] = 0.5f - p->function_amplitude * std::tanh(x / (2.0f * p->function_slope));
+    lb[i] = 1.0f - lf[i];
+  }
+  // region_modality.cpp:925-936
+  float laplace = 1.0f / (2.0f * powf(atanhf(2.0f * p->function_amplitude), 2.0f));
+  float gaussian = p->function_slope;
+  *min_expected_variance = std::max(laplace, gaussian);
+}
+
+void RegionPrecalc(const orc_region_params* p, const orc_color_frame* c, const float* body2world,
+                   int corr_iteration, int rotation_mode, RegionVars* v) {
+  FunctionLookup(p, v->lookup_f, v->lookup_b, &v->min_expected_variance);
+  v->line_length_in_segments = p->function_length + p->distribution_length - 1;
+  v->dl_minus_1_half = (float(p->distribution_length) - 1.0f) / 2.0f;
+  v->dl_plus_1_half = (float(p->distribution_length) + 1.0f) / 2.0f;
+  v->fu = c->intrinsics.fu; v->fv = c->intrinsics.fv;
+  v->ppu = c->intrinsics.ppu; v->ppv = c->intrinsics.ppv;
+  v->w_m1 = c->intrinsics.width - 1; v->h_m1 = c->intrinsics.height - 1;
+  v->w_m2 = c->intrinsics.width - 2; v->h_m2 = c->intrinsics.height - 2;
+  PoseMul(c->world2camera, body2world, v->body2camera);
+  PoseRotation(v->body2camera, rotation_mode, v->rot);
+  v->scale = LastValidValue(p->scales, p->n_scales, corr_iteration);
+  v->fscale = float(v->scale);
+  v->line_length = v->line_length_in_segments * v->scale;
+  v->line_length_minus_1 = v->line_length - 1;
+  v->line_length_minus_1_half = float(v->line_length - 1) * 0.5f;
+  v->line_length_half_minus_1 = float(v->line_length) * 0.5f - 1.0f;
+  float sd = LastValidValue(p->standard_deviations, p->n_standard_deviations, corr_iteration);
+  v->variance = sd * sd;  // powf(sd, 2.0f)
+  v->n_bins = p->n_histogram_bins;
+  v->bitshift = Bitshift(p->n_histogram_bins);
+}
+
+// RegionModel::GetClosestView (region_model.cpp:105-130) / DepthModel::GetClosestView (depth_model.cpp:81-106)
+int ClosestView(const orc_model* m, const float* body2camera, int rotation_mode) {
+  float t[3] = {T_(body2camera, 0), T_(body2camera, 1), T_(body2camera, 2)};
+  float norm = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+  if (norm == 0.0f) return 0;
+  Normalize3(t);
+  float o[3];
+  if (rotation_mode == ORC_ROTATION_POLAR) {
+    float r[9], inv[9];
+    PoseRotation(body2camera, rotation_mode, r);
+    Inverse3(r, inv);  // rotation().inverse()
+    for (int i = 0; i < 3; ++i) o[i] = inv[3 * i + 0] * t[0] + inv[3 * i + 1] * t[1] + inv[3 * i + 2] * t[2];
+  } else {
+    for (int j = 0; j < 3; ++j) o[j] = R_(body2camera, 0, j) * t[0] + R_(body2camera, 1, j) * t[1] + R_(body2camera, 2, j) * t[2];
+  }
+  float closest_dot = -1.0f;
+  int best = 0;  // reference leaves the pointer untouched if no dot > -1; views_[0] is our stand-in
+  for (int v = 0; v < m->n_views; ++v) {
+    const float* vo = m->orientations + 3 * v;
+    float dot = o[0] * vo[0] + o[1] * vo[1] + o[2] * vo[2];
+    if (dot > closest_dot) {
+      best = v;
+      closest_dot = dot;
+    }
+  }
+  return best;
+}
+
+// n_lines / n_points selection (region_modality.cpp:414-430, depth_modality.cpp:281-293)
+int AdaptiveCount(int n_max, int use_adaptive, float reference, float view_scalar, float max_scalar, int n_model) {
+  int n = n_max;
+  if (use_adaptive) {
+    if (reference > 0.0f)
+      n = int(float(n_max) * std::min(1.0f, view_scalar / reference));
+    else
+      n = int(float(n_max) * view_scalar / max_scalar);
+  }
+  if (n > n_model) n = n_model;
+  return n;
+}
+
+// MultiplyPixelColorProbability (region_modality.cpp:1575-1598) + GetProbabilities (color_histograms.cpp:94-102)
+inline void MultiplyPixel(const RegionVars& v, const float* hist_f, const float* hist_b, const uint8_t* px,
+                          float* pf_acc, float* pb_acc) {
+  int idx = HistIndex(v.n_bins, v.bitshift, px);
+  float pf = hist_f[idx];
+  float pb = hist_b[idx];
+  if (pf || pb) {
+    float sum = pf;
+    sum += pb;
+    pf /= sum;
+    pb /= sum;
+  } else {
+    pf = 0.5f;
+    pb = 0.5f;
+  }
+  *pf_acc *= pf;
+  *pb_acc *= pb;
+}
+
+// CalculateSegmentProbabilities (region_modality.cpp:1433-1573)
+bool SegmentProbabilities(const RegionVars& v, const orc_color_frame* c, const float* hist_f, const float* hist_b,
+                          float center_u, float center_v, float normal_u, float normal_v, float* sf, float* sb,
+                          float* normal_component_to_scale, float* delta_r) {
+  const int n_seg = v.line_length_in_segments;
+  const uint8_t* img = c->bgr;
+  const size_t pitch = c->pitch;
+  if (std::fabs(normal_v) < std::fabs(normal_u)) {
+    float v_step = normal_v / normal_u;
+    int u = int(center_u - v.line_length_half_minus_1);
+    int u_end = u + v.line_length_minus_1;
+    float v_f = center_v + v_step * (float(u) - center_u) + 0.5f;
+    float v_f_end = v_f + v_step * float(v.line_length_minus_1);
+    if (u < 0 || u_end > v.w_m1 || int(v_f) < 0 || int(v_f) > v.h_m1 || int(v_f_end) < 1 || int(v_f_end) > v.h_m2)
+      return false;
+    int seg = normal_u > 0 ? 0 : n_seg - 1;
+    int dir = normal_u > 0 ? 1 : -1;
+    sf[seg] = 1.0f; sb[seg] = 1.0f;
+    int segment_idx = 0;
+    for (; u <= u_end; ++u, v_f += v_step, ++segment_idx) {
+      if (segment_idx == v.scale) {
+        seg += dir;
+        sf[seg] = 1.0f; sb[seg] = 1.0f;
+        segment_idx = 0;
+      }
+      MultiplyPixel(v, hist_f, hist_b, img + size_t(int(v_f)) * pitch + 3 * size_t(u), &sf[seg], &sb[seg]);
+    }
+    *normal_component_to_scale = std::fabs(normal_u) / v.fscale;
+    *delta_r = (std::round(center_u - v.line_length_minus_1_half) + v.line_length_minus_1_half - center_u) / normal_u;
+  } else {
+    float u_step = normal_u / normal_v;
+    int vv = int(center_v - v.line_length_half_minus_1);
+    int v_end = vv + v.line_length_minus_1;
+    float u_f = center_u + u_step * (float(vv) - center_v) + 0.5f;
+    float u_f_end = u_f + u_step * float(v.line_length_minus_1);
+    if (vv < 0 || v_end > v.h_m1 || int(u_f) < 0 || int(u_f) > v.w_m1 || int(u_f_end) < 1 || int(u_f_end) > v.w_m2)
+      return false;
+    int seg = normal_v > 0 ? 0 : n_seg - 1;
+    int dir = normal_v > 0 ? 1 : -1;
+    sf[seg] = 1.0f; sb[seg] = 1.0f;
+    int segment_idx = 0;
+    for (; vv <= v_end; ++vv, u_f += u_step, ++segment_idx) {
+      if (segment_idx == v.scale) {
+        seg += dir;
+        sf[seg] = 1.0f; sb[seg] = 1.0f;
+        segment_idx = 0;
+      }
+      MultiplyPixel(v, hist_f, hist_b, img + size_t(vv) * pitch + 3 * size_t(int(u_f)), &sf[seg], &sb[seg]);
+    }
+    *normal_component_to_scale = std::fabs(normal_v) / v.fscale;
+    *delta_r = (std::round(center_v - v.line_length_minus_1_half) + v.line_length_minus_1_half - center_v) / normal_v;
+  }
+  // Normalize segment probabilities (:1555-1571)
+  if (v.scale > 1) {
+    for (int i = 0; i < n_seg; ++i) {
+      if (sf[i] || sb[i]) {
+        float sum = sf[i];
+        sum += sb[i];
+        sf[i] /= sum;
+        sb[i] /= sum;
+      } else {
+        sf[i] = 0.5f;
+        sb[i] = 0.5f;
+      }
+    }
+  }
+  return true;
+}
+
+// CalculateDistribution (region_modality.cpp:1600-1637)
+void Distribution(const RegionVars& v, int function_length, int distribution_length, const float* sf,
+                  const float* sb, float* dist) {
+  float area = 0.0f;
+  for (int d = 0; d < distribution_length; ++d) {
+    float val = 1.0f;
+    for (int k = 0; k < function_length; ++k) val *= sf[d + k] * v.lookup_f[k] + sb[d + k] * v.lookup_b[k];
+    dist[d] = val;
+    area += val;
+  }
+  for (int d = 0; d < distribution_length; ++d) dist[d] /= area;
+}
+
+// CalculateDistributionMoments (region_modality.cpp:1639-1658)
+void Moments(const RegionVars& v, int distribution_length, const float* dist, float* mean, float* variance) {
+  float mean_from_begin = 0.0f;
+  for (int i = 0; i < distribution_length; ++i) mean_from_begin += float(i) * dist[i];
+  float var = 0.0f;
+  for (int i = 0; i < distribution_length; ++i) {
+    float d = float(i) - mean_from_begin;
+    var += (d * d) * dist[i];  // powf(x, 2.0f) * dist[i]
+  }
+  *mean = mean_from_begin - v.dl_minus_1_half;
+  *variance = std::max(var, v.min_expected_variance);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depth modality precalculated variables (depth_modality.cpp:618-654)
+// ---------------------------------------------------------------------------------------------
+struct DepthVars {
+  float fu, fv, ppu, ppv, depth_scale;
+  int w_m1, h_m1;
+  float body2camera[12], camera2body[12];
+  float considered_distance;
+  int max_n_strides;
+  float standard_deviation;
+};
+
+void DepthPrecalc(const orc_depth_params* p, const orc_depth_frame* f, const float* body2world, int corr_iteration,
+                  DepthVars* v) {
+  v->fu = f->intrinsics.fu; v->fv = f->intrinsics.fv;
+  v->ppu = f->intrinsics.ppu; v->ppv = f->intrinsics.ppv;
+  v->depth_scale = f->depth_scale;
+  v->w_m1 = f->intrinsics.width - 1; v->h_m1 = f->intrinsics.height - 1;
+  PoseMul(f->world2camera, body2world, v->body2camera);  // :642-643
+  PoseInverse(v->body2camera, v->camera2body);            // :644
+  v->considered_distance = LastValidValue(p->considered_distances, p->n_considered_distances, corr_iteration);
+  v->max_n_strides = int(v->considered_distance / p->stride_length + 0.5f);  // :651
+  v->standard_deviation = LastValidValue(p->standard_deviations, p->n_standard_deviations, corr_iteration);
+}
+
+// DepthModality::FindCorrespondence (depth_modality.cpp:826-884)
+bool FindCorrespondence(const orc_depth_params* p, const DepthVars& v, const orc_depth_frame* f,
+                        const float* center_f_camera, float center_u, float center_v, float depth_pt,
+                        float* correspondence) {
+  float considered_distance = v.considered_distance;
+  if (p->use_depth_scaling) considered_distance *= depth_pt;
+  float meter_to_pixel = v.fu / depth_pt;
+  float diameter = 2.0f * considered_distance * meter_to_pixel;
+  int stride = int(diameter / float(v.max_n_strides) + 1.0f);
+  int n_strides = int(diameter / float(stride) + 0.5f);
+  int rounded_diameter = n_strides * stride;
+  float rounded_radius = 0.5f * float(rounded_diameter);
+  int u_min = int(center_u - rounded_radius + 0.5f);
+  int v_min = int(center_v - rounded_radius + 0.5f);
+  int u_max = u_min + rounded_diameter;
+  int v_max = v_min + rounded_diameter;
+  u_min = std::max(u_min, 0);
+  v_min = std::max(v_min, 0);
+  u_max = std::min(u_max, v.w_m1);
+  v_max = std::min(v_max, v.h_m1);
+  // NB: the reference really uses std::min(0.0f, ...) here (:851-852), i.e. the lower bound is <= 0.
+  float min_depth_value = std::min(0.0f, (depth_pt - considered_distance) / v.depth_scale);
+  float max_depth_value = (depth_pt + considered_distance) / v.depth_scale;
+  float min_considered_distance_square = considered_distance * considered_distance;
+  float min_measured_distance_square = min_considered_distance_square;
+  for (int vv = v_min; vv <= v_max; vv += stride) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(f->depth) + size_t(vv) * f->pitch);
+    for (int uu = u_min; uu <= u_max; uu += stride) {
+      float depth = float(row[uu]);
+      if (depth > min_depth_value && depth < max_depth_value) {
+        depth *= v.depth_scale;
+        float tx = (float(uu) - v.ppu) * depth / v.fu;
+        float ty = (float(vv) - v.ppv) * depth / v.fv;
+        float tz = depth;
+        float dx = tx - center_f_camera[0], dy = ty - center_f_camera[1], dz = tz - center_f_camera[2];
+        float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < min_measured_distance_square) {
+          correspondence[0] = tx; correspondence[1] = ty; correspondence[2] = tz;
+          min_measured_distance_square = d2;
+        }
+      }
+    }
+  }
+  return min_measured_distance_square != min_considered_distance_square;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eigen::LDLT<MatrixXf, Lower> restated (Eigen/src/Cholesky/LDLT.h: ldlt_inplace<Lower>::unblocked,
+// LDLT::_solve_impl). a: n x n, only the lower triangle is read. Returns false if n is too large.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxN = 128;
+bool LdltSolve(int n, const float* a_in, const float* b, float* x) {
+  if (n > kMaxN || n < 1) return false;
+  std::vector<float> mat(size_t(n) * n, 0.0f);
+  auto A = [&](int i, int j) -> float& { return mat[size_t(i) * n + j]; };
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) A(i, j) = a_in[size_t(i) * n + j];
+  std::vector<int> trans(n);
+  std::vector<float> temp(n);
+  bool zero_matrix = false;
+  if (n == 1) {
+    trans[0] = 0;
+  } else {
+    for (int k = 0; k < n; ++k) {
+      // Find largest diagonal element (first maximum wins)
+      int biggest = k;
+      float big = std::fabs(A(k, k));
+      for (int i = k + 1; i < n; ++i) {
+        float val = std::fabs(A(i, i));
+        if (val > big) { big = val; biggest = i; }
+      }
+      trans[k] = biggest;
+      if (k != biggest) {
+        int s = n - biggest - 1;
+        for (int j = 0; j < k; ++j) std::swap(A(k, j), A(biggest, j));
+        for (int i = 0; i < s; ++i) std::swap(A(biggest + 1 + i, k), A(biggest + 1 + i, biggest));
+        std::swap(A(k, k), A(biggest, biggest));
+        for (int i = k + 1; i < biggest; ++i) {
+          float tmp = A(i, k);
+          A(i, k) = A(biggest, i);
+          A(biggest, i) = tmp;
+        }
+      }
+      int rs = n - k - 1;
+      if (k > 0) {
+        for (int j = 0; j < k; ++j) temp[j] = A(j, j) * A(k, j);
+        float dot = 0.0f;
+        for (int j = 0; j < k; ++j) dot += A(k, j) * temp[j];
+        A(k, k) -= dot;
+        for (int i = k + 1; i < n; ++i) {
+          float acc = 0.0f;
+          for (int j = 0; j < k; ++j) acc += A(i, j) * temp[j];
+          A(i, k) -= acc;
+        }
+      }
+      float akk = A(k, k);
+      bool pivot_is_valid = std::fabs(akk) > 0.0f;
+      if (k == 0 && !pivot_is_valid) {
+        // The entire diagonal is zero, there is nothing more to do except filling the transpositions
+        for (int j = 0; j < n; ++j) trans[j] = j;
+        zero_matrix = true;
+        break;
+      }
+      if (rs > 0 && pivot_is_valid)
+        for (int i = k + 1; i < n; ++i) A(i, k) /= akk;
+    }
+  }
+  (void)zero_matrix;
+  // _solve_impl: dst = P b
+  std::vector<float> dst(b, b + n);
+  for (int k = 0; k < n; ++k) std::swap(dst[k], dst[trans[k]]);
+  // dst = L^-1 (P b): unit lower, column oriented
+  for (int j = 0; j < n; ++j)
+    for (int i = j + 1; i < n; ++i) dst[i] -= A(i, j) * dst[j];
+  // dst = D^-1 (L^-1 P b) with Eigen's tolerance 1 / highest()
+  const float tolerance = 1.0f / std::numeric_limits<float>::max();
+  for (int i = 0; i < n; ++i) {
+    if (std::fabs(A(i, i)) > tolerance)
+      dst[i] /= A(i, i);
+    else
+      dst[i] = 0.0f;
+  }
+  // dst = L^-T (...): unit upper, column oriented backwards
+  for (int j = n - 1; j >= 0; --j)
+    for (int i = 0; i < j; ++i) dst[i] -= A(j, i) * dst[j];
+  // dst = P^T dst
+  for (int k = n - 1; k >= 0; --k) std::swap(dst[k], dst[trans[k]]);
+  for (int i = 0; i < n; ++i) x[i] = dst[i];
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Vector2Skewsymmetric(w).exp()  (common.h:64-70, link.cpp:224; Eigen unsupported MatrixFunctions,
+// MatrixExponential.h: matrix_exp_computeUV<_, float> + matrix_exp_compute).
+// ---------------------------------------------------------------------------------------------
+struct M3 {
+  float m[9];
+  float& operator()(int i, int j) { return m[3 * i + j]; }
+  float operator()(int i, int j) const { return m[3 * i + j]; }
+};
+M3 Mul(const M3& a, const M3& b) {
+  M3 r;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r(i, j) = a(i, 0) * b(0, j) + a(i, 1) * b(1, j) + a(i, 2) * b(2, j);
+  return r;
+}
+M3 Lin(float ca, const M3& a, float cb, const M3& b) {  // ca*a + cb*b
+  M3 r;
+  for (int k = 0; k < 9; ++k) r.m[k] = ca * a.m[k] + cb * b.m[k];
+  return r;
+}
+M3 Identity3() { return M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+
+// denom.partialPivLu().solve(numer) for 3x3
+M3 LuSolve(M3 a, M3 b) {
+  int perm[3] = {0, 1, 2};
+  for (int k = 0; k < 3; ++k) {
+    int piv = k;
+    float big = std::fabs(a(k, k));
+    for (int i = k + 1; i < 3; ++i)
+      if (std::fabs(a(i, k)) > big) { big = std::fabs(a(i, k)); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < 3; ++j) { std::swap(a(k, j), a(piv, j)); std::swap(b(k, j), b(piv, j)); }
+      std::swap(perm[k], perm[piv]);
+    }
+    for (int i = k + 1; i < 3; ++i) {
+      a(i, k) /= a(k, k);
+      for (int j = k + 1; j < 3; ++j) a(i, j) -= a(i, k) * a(k, j);
+    }
+  }
+  // forward (unit lower)
+  for (int c = 0; c < 3; ++c) {
+    for (int i = 1; i < 3; ++i)
+      for (int j = 0; j < i; ++j) b(i, c) -= a(i, j) * b(j, c);
+    for (int i = 2; i >= 0; --i) {
+      for (int j = i + 1; j < 3; ++j) b(i, c) -= a(i, j) * b(j, c);
+      b(i, c) /= a(i, i);
+    }
+  }
+  return b;
+}
+
+void ExpSkew(const float* w, int exp_mode, float* out) {
+  M3 A{{0.0f, -w[2], w[1], w[2], 0.0f, -w[0], -w[1], w[0], 0.0f}};  // common.h:64-70
+  if (exp_mode == ORC_EXP_RODRIGUES) {
+    // closed form, same expression as the CUDA path (csrc/m3t_b200_math.cuh ExpSkew)
+    float t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+    float a, b;
+    if (t2 < 1e-8f) {
+      a = 1.0f - t2 / 6.0f;
+      b = 0.5f - t2 / 24.0f;
+    } else {
+      float t = std::sqrt(t2);
+      float sh = std::sin(0.5f * t);
+      a = std::sin(t) / t;
+      b = 2.0f * sh * sh / t2;
+    }
+    M3 A2 = Mul(A, A);
+    M3 I = Identity3();
+    for (int k = 0; k < 9; ++k) out[k] = I.m[k] + a * A.m[k] + b * A2.m[k];
+    return;
+  }
+  float l1norm = 0.0f;
+  for (int j = 0; j < 3; ++j) {
+    float s = std::fabs(A(0, j)) + std::fabs(A(1, j)) + std::fabs(A(2, j));
+    l1norm = std::max(l1norm, s);
+  }
+  int squarings = 0;
+  M3 U, V;
+  const M3 I = Identity3();
+  if (l1norm < 4.258730016922831e-001f) {
+    const float b[] = {120.0f, 60.0f, 12.0f, 1.0f};
+    M3 A2 = Mul(A, A);
+    M3 tmp = Lin(b[3], A2, b[1], I);
+    U = Mul(A, tmp);
+    V = Lin(b[2], A2, b[0], I);
+  } else if (l1norm < 1.880152677804762e+000f) {
+    const float b[] = {30240.0f, 15120.0f, 3360.0f, 420.0f, 30.0f, 1.0f};
+    M3 A2 = Mul(A, A);
+    M3 A4 = Mul(A2, A2);
+    M3 tmp;
+    for (int k = 0; k < 9; ++k) tmp.m[k] = b[5] * A4.m[k] + b[3] * A2.m[k] + b[1] * I.m[k];
+    U = Mul(A, tmp);
+    for (int k = 0; k < 9; ++k) V.m[k] = b[4] * A4.m[k] + b[2] * A2.m[k] + b[0] * I.m[k];
+  } else {
+    const float maxnorm = 3.925724783138660f;
+    std::frexp(l1norm / maxnorm, &squarings);
+    if (squarings < 0) squarings = 0;
+    M3 As = A;
+    for (int k = 0; k < 9; ++k) As.m[k] = std::ldexp(A.m[k], -squarings);
+    const float b[] = {17297280.0f, 8648640.0f, 1995840.0f, 277200.0f, 25200.0f, 1512.0f, 56.0f, 1.0f};
+    M3 A2 = Mul(As, As);
+    M3 A4 = Mul(A2, A2);
+    M3 A6 = Mul(A4, A2);
+    M3 tmp;
+    for (int k = 0; k < 9; ++k) tmp.m[k] = b[7] * A6.m[k] + b[5] * A4.m[k] + b[3] * A2.m[k] + b[1] * I.m[k];
+    U = Mul(As, tmp);
+    for (int k = 0; k < 9; ++k) V.m[k] = b[6] * A6.m[k] + b[4] * A4.m[k] + b[2] * A2.m[k] + b[0] * I.m[k];
+  }
+  M3 numer = Lin(1.0f, U, 1.0f, V);
+  M3 denom = Lin(-1.0f, U, 1.0f, V);
+  M3 result = LuSolve(denom, numer);
+  for (int i = 0; i < squarings; ++i) result = Mul(result, result);
+  for (int k = 0; k < 9; ++k) out[k] = result.m[k];
+}
+
+inline double Now() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+// =============================================================================================
+// extern "C" surface
+// =============================================================================================
+extern "C" {
+
+void orc_region_params_default(orc_region_params* p) {  // region_modality.h:411-443
+  std::memset(p, 0, sizeof(*p));
+  p->n_lines_max = 200;
+  p->use_adaptive_coverage = 0;
+  p->reference_contour_length = 0.0f;
+  p->min_continuous_distance = 3.0f;
+  p->function_length = 8;
+  p->distribution_length = 12;
+  p->function_amplitude = 0.43f;
+  p->function_slope = 0.5f;
+  p->learning_rate = 1.3f;
+  p->n_global_iterations = 1;
+  p->n_scales = 4;
+  const int s[] = {6, 4, 2, 1};
+  const float sd[] = {15.0f, 5.0f, 3.5f, 1.5f};
+  for (int i = 0; i < 4; ++i) { p->scales[i] = s[i]; p->standard_deviations[i] = sd[i]; }
+  p->n_standard_deviations = 4;
+  p->n_histogram_bins = 16;
+  p->learning_rate_f = 0.2f;
+  p->learning_rate_b = 0.2f;
+  p->unconsidered_line_length = 0.5f;
+  p->max_considered_line_length = 20.0f;
+  p->measure_occlusions = 0;
+  p->measured_depth_offset_radius = 0.01f;
+  p->measured_occlusion_radius = 0.01f;
+  p->measured_occlusion_threshold = 0.03f;
+  p->n_unoccluded_iterations = 10;
+  p->min_n_unoccluded_lines = 0;
+}
+
+void orc_depth_params_default(orc_depth_params* p) {  // depth_modality.h:302-321
+  std::memset(p, 0, sizeof(*p));
+  p->n_points_max = 200;
+  p->stride_length = 0.005f;
+  p->n_considered_distances = 3;
+  const float cd[] = {0.05f, 0.02f, 0.01f};
+  const float sd[] = {0.05f, 0.03f, 0.02f};
+  for (int i = 0; i < 3; ++i) { p->considered_distances[i] = cd[i]; p->standard_deviations[i] = sd[i]; }
+  p->n_standard_deviations = 3;
+  p->measured_depth_offset_radius = 0.01f;
+  p->measured_occlusion_radius = 0.01f;
+  p->measured_occlusion_threshold = 0.03f;
+  p->n_unoccluded_iterations = 10;
+  p->min_n_unoccluded_points = 0;
+}
+
+void orc_pose_multiply(const float a[12], const float b[12], float out[12]) { PoseMul(a, b, out); }
+void orc_pose_inverse(const float a[12], float out[12]) { PoseInverse(a, out); }
+void orc_pose_rotation(const float a[12], int rotation_mode, float r[9]) { PoseRotation(a, rotation_mode, r); }
+void orc_exp_skew(const float w[3], int exp_mode, float r[9]) { ExpSkew(w, exp_mode, r); }
+int orc_ldlt_solve(int n, const float* a, const float* b, float* x) { return LdltSolve(n, a, b, x) ? 1 : 0; }
+void orc_function_lookup(const orc_region_params* p, float lookup_f[8], float lookup_b[8], float* mev) {
+  FunctionLookup(p, lookup_f, lookup_b, mev);
+}
+
+// ---- ColorHistograms ------------------------------------------------------------------------
+void orc_hist_clear(int n_bins, float* memory_f, float* memory_b) {  // color_histograms.cpp:49-58
+  size_t n = size_t(n_bins) * n_bins * n_bins;
+  std::fill(memory_f, memory_f + n, 0.0f);
+  std::fill(memory_b, memory_b + n, 0.0f);
+}
+void orc_hist_add(int n_bins, float* memory, const uint8_t bgr[3]) {  // :60-70
+  memory[HistIndex(n_bins, Bitshift(n_bins), bgr)] += 1.0f;
+}
+void orc_hist_calculate(int n_bins, float learning_rate, const float* memory, float* histogram) {  // :174-214
+  int n = n_bins * n_bins * n_bins;
+  float sum = 0.0f;
+  for (int i = 0; i < n; ++i) sum += memory[i];
+  if (!sum) {
+    if (learning_rate == 1.0f) {
+      float uniform_value = 1.0f / float(n);
+      std::fill(histogram, histogram + n, uniform_value);
+    }
+    return;
+  }
+  float complement_learning_rate = 1.0f - learning_rate;
+  float learning_rate_divide_sum = learning_rate / sum;
+  if (complement_learning_rate == 0.0f) {
+    for (int i = 0; i < n; ++i) histogram[i] = memory[i] * learning_rate_divide_sum;
+  } else {
+    for (int i = 0; i < n; ++i) {
+      histogram[i] *= complement_learning_rate;
+      histogram[i] += memory[i] * learning_rate_divide_sum;
+    }
+  }
+}
+void orc_hist_get(int n_bins, const float* hist_f, const float* hist_b, const uint8_t bgr[3], float* pf, float* pb) {
+  int idx = HistIndex(n_bins, Bitshift(n_bins), bgr);
+  *pf = hist_f[idx];
+  *pb = hist_b[idx];
+}
+
+int orc_closest_view(const orc_model* model, const float body2camera[12], int rotation_mode) {
+  return ClosestView(model, body2camera, rotation_mode);
+}
+
+// ---- RegionModality::AddLinePixelColorsToTempHistograms (region_modality.cpp:1025-1155) -------
+void orc_region_add_line_pixels(const orc_region_params* p, const orc_model* model, const orc_color_frame* c,
+                                const float body2world[12], int rotation_mode, float* memory_f, float* memory_b) {
+  RegionVars v;
+  RegionPrecalc(p, c, body2world, 0, rotation_mode, &v);
+  int view = ClosestView(model, v.body2camera, rotation_mode);
+  int n_lines = AdaptiveCount(p->n_lines_max, p->use_adaptive_coverage, p->reference_contour_length,
+                              model->view_scalars ? model->view_scalars[view] : 0.0f, model->max_view_scalar,
+                              model->n_points);
+  const float* pts = model->points + size_t(view) * model->n_points * ORC_REGION_POINT_FLOATS;
+  for (int i = 0; i < n_lines; ++i) {
+    const float* dp = pts + size_t(i) * ORC_REGION_POINT_FLOATS;
+    const float* center_f_body = dp;
+    const float* normal_f_body = dp + 3;
+    float foreground_distance = dp[6], background_distance = dp[7];
+    float cc[3];
+    PoseApply(v.body2camera, center_f_body, cc);
+    if (cc[2] <= 0.0f) continue;
+    float center_u = cc[0] * v.fu / cc[2] + v.ppu;
+    float center_v = cc[1] * v.fv / cc[2] + v.ppv;
+    int i_center_u = int(center_u + 0.5f);
+    int i_center_v = int(center_v + 0.5f);
+    if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+    float length_f = p->max_considered_line_length;
+    float length_b = p->max_considered_line_length;
+    float l_f = foreground_distance * v.fu / cc[2];
+    float l_b = background_distance * v.fu / cc[2];
+    length_f = std::fmin(length_f, l_f - 2.0f * p->unconsidered_line_length);
+    length_b = std::fmin(length_b, l_b - 2.0f * p->unconsidered_line_length);
+    float normal[2] = {v.rot[0] * normal_f_body[0] + v.rot[1] * normal_f_body[1] + v.rot[2] * normal_f_body[2],
+                       v.rot[3] * normal_f_body[0] + v.rot[4] * normal_f_body[1] + v.rot[5] * normal_f_body[2]};
+    Normalize2(normal);
+    float u_step, v_step;
+    int projected_length_f, projected_length_b;
+    float abs_normal_u = std::fabs(normal[0]);
+    float abs_normal_v = std::fabs(normal[1]);
+    if (abs_normal_u > abs_normal_v) {
+      u_step = sgnf(normal[0]);
+      v_step = normal[1] / abs_normal_u;
+      projected_length_f = int(length_f * abs_normal_u + 0.5f);
+      projected_length_b = int(length_b * abs_normal_u + 0.5f);
+    } else {
+      u_step = normal[0] / abs_normal_v;
+      v_step = sgnf(normal[1]);
+      projected_length_f = int(length_f * abs_normal_v + 0.5f);
+      projected_length_b = int(length_b * abs_normal_v + 0.5f);
+    }
+    float u = center_u - normal[0] * p->unconsidered_line_length + 0.5f;
+    float vv = center_v - normal[1] * p->unconsidered_line_length + 0.5f;
+    for (int k = 0; k < projected_length_f; ++k) {
+      int i_u = int(u), i_v = int(vv);
+      if (i_u < 0 || i_u > v.w_m1 || i_v < 0 || i_v > v.h_m1) break;
+      orc_hist_add(p->n_histogram_bins, memory_f, c->bgr + size_t(i_v) * c->pitch + 3 * size_t(i_u));
+      u -= u_step;
+      vv -= v_step;
+    }
+    u = center_u + normal[0] * p->unconsidered_line_length + 0.5f;
+    vv = center_v + normal[1] * p->unconsidered_line_length + 0.5f;
+    for (int k = 0; k < projected_length_b; ++k) {
+      int i_u = int(u), i_v = int(vv);
+      if (i_u < 0 || i_u > v.w_m1 || i_v < 0 || i_v > v.h_m1) break;
+      orc_hist_add(p->n_histogram_bins, memory_b, c->bgr + size_t(i_v) * c->pitch + 3 * size_t(i_u));
+      u += u_step;
+      vv += v_step;
+    }
+  }
+}
+
+// ---- RegionModality::CalculateCorrespondences (region_modality.cpp:390-465) -------------------
+int orc_region_correspondences(const orc_region_params* p, const orc_model* model, const orc_color_frame* c,
+                               const orc_depth_frame* occlusion_depth, const float* hist_f, const float* hist_b,
+                               const float body2world[12], int iteration, int first_iteration, int corr_iteration,
+                               int rotation_mode, orc_region_line* lines, int* view_index) {
+  (void)occlusion_depth; (void)iteration; (void)first_iteration;  // occlusion handling: not configured
+  RegionVars v;
+  RegionPrecalc(p, c, body2world, corr_iteration, rotation_mode, &v);
+  int view = ClosestView(model, v.body2camera, rotation_mode);
+  if (view_index) *view_index = view;
+  int n_lines = AdaptiveCount(p->n_lines_max, p->use_adaptive_coverage, p->reference_contour_length,
+                              model->view_scalars ? model->view_scalars[view] : 0.0f, model->max_view_scalar,
+                              model->n_points);
+  const float* pts = model->points + size_t(view) * model->n_points * ORC_REGION_POINT_FLOATS;
+  float sf[32], sb[32];
+  // Without occlusion handling pass j == 0 always suffices (:435-463).
+  for (int i = 0; i < n_lines; ++i) {
+    const float* dp = pts + size_t(i) * ORC_REGION_POINT_FLOATS;
+    orc_region_line& L = lines[i];
+    std::memset(&L, 0, sizeof(L));
+    L.model_index = i;
+    // CalculateBasicLineData (:1231-1250)
+    float cc[3];
+    PoseApply(v.body2camera, dp, cc);
+    float n2[2] = {v.rot[0] * dp[3] + v.rot[1] * dp[4] + v.rot[2] * dp[5],
+                   v.rot[3] * dp[3] + v.rot[4] * dp[4] + v.rot[5] * dp[5]};
+    Normalize2(n2);
+    L.center_f_body[0] = dp[0]; L.center_f_body[1] = dp[1]; L.center_f_body[2] = dp[2];
+    L.center_u = cc[0] * v.fu / cc[2] + v.ppu;
+    L.center_v = cc[1] * v.fv / cc[2] + v.ppv;
+    L.normal_u = n2[0];
+    L.normal_v = n2[1];
+    float continuous_distance = std::min(dp[7], dp[6]) * v.fu / (cc[2] * v.fscale);
+    // IsLineValid (:1252-1291)
+    if (continuous_distance < p->min_continuous_distance) continue;
+    if (cc[2] <= 0.0f) continue;
+    int i_center_u = int(L.center_u + 0.5f);
+    int i_center_v = int(L.center_v + 0.5f);
+    if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+    if (!SegmentProbabilities(v, c, hist_f, hist_b, L.center_u, L.center_v, L.normal_u, L.normal_v, sf, sb,
+                              &L.normal_component_to_scale, &L.delta_r))
+      continue;
+    Distribution(v, p->function_length, p->distribution_length, sf, sb, L.distribution);
+    Moments(v, p->distribution_length, L.distribution, &L.mean, &L.measured_variance);
+    L.valid = 1;
+  }
+  return n_lines;
+}
+
+// ---- RegionModality::CalculateGradientAndHessian (region_modality.cpp:485-558) ----------------
+void orc_region_gradient_hessian(const orc_region_params* p, const orc_color_frame* c, const float body2world[12],
+                                 const orc_region_line* lines, int n_lines, int corr_iteration, int opt_iteration,
+                                 int rotation_mode, float g[6], float H[36]) {
+  RegionVars v;
+  RegionPrecalc(p, c, body2world, corr_iteration, rotation_mode, &v);
+  for (int i = 0; i < 6; ++i) g[i] = 0.0f;
+  for (int i = 0; i < 36; ++i) H[i] = 0.0f;
+  for (int li = 0; li < n_lines; ++li) {
+    const orc_region_line& L = lines[li];
+    if (!L.valid) continue;
+    float cc[3];
+    PoseApply(v.body2camera, L.center_f_body, cc);
+    float x = cc[0], y = cc[1], z = cc[2];
+    float fu_z = v.fu / z;
+    float fv_z = v.fv / z;
+    float xfu_z = x * fu_z;
+    float yfv_z = y * fv_z;
+    float delta_cs = (L.normal_u * (xfu_z + v.ppu - L.center_u) + L.normal_v * (yfv_z + v.ppv - L.center_v) - L.delta_r) *
+                     L.normal_component_to_scale;
+    float dloglikelihood_ddelta_cs;
+    if (opt_iteration < p->n_global_iterations) {
+      dloglikelihood_ddelta_cs = (L.mean - delta_cs) / L.measured_variance;
+    } else {
+      int dist_idx_upper = int(delta_cs + v.dl_plus_1_half);
+      int dist_idx_lower = dist_idx_upper - 1;
+      if (dist_idx_upper <= 0 || dist_idx_upper >= p->distribution_length) continue;
+      dloglikelihood_ddelta_cs = (std::log(L.distribution[dist_idx_upper]) - std::log(L.distribution[dist_idx_lower])) *
+                                 p->learning_rate / L.measured_variance;
+    }
+    float ncts = L.normal_component_to_scale;
+    float dc[3] = {ncts * L.normal_u * fu_z, ncts * L.normal_v * fv_z,
+                   ncts * (-L.normal_u * xfu_z - L.normal_v * yfv_z) / z};
+    float dt[3];
+    for (int j = 0; j < 3; ++j) dt[j] = dc[0] * v.rot[0 + j] + dc[1] * v.rot[3 + j] + dc[2] * v.rot[6 + j];
+    const float* cb = L.center_f_body;
+    float J[6] = {cb[1] * dt[2] - cb[2] * dt[1], cb[2] * dt[0] - cb[0] * dt[2], cb[0] * dt[1] - cb[1] * dt[0],
+                  dt[0], dt[1], dt[2]};
+    float weight = v.min_expected_variance / (ncts * ncts * v.variance);
+    float wg = weight * dloglikelihood_ddelta_cs;
+    float wh = weight / L.measured_variance;
+    for (int i = 0; i < 6; ++i) g[i] += wg * J[i];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j <= i; ++j) H[6 * i + j] -= (wh * J[i]) * J[j];
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = i + 1; j < 6; ++j) H[6 * i + j] = H[6 * j + i];  // selfadjointView<Lower>
+}
+
+// ---- DepthModality::CalculateCorrespondences (depth_modality.cpp:252-315) ---------------------
+int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model, const orc_depth_frame* f,
+                              const float body2world[12], int iteration, int first_iteration, int corr_iteration,
+                              int rotation_mode, orc_depth_point* points, int* view_index) {
+  (void)iteration; (void)first_iteration;
+  DepthVars v;
+  DepthPrecalc(p, f, body2world, corr_iteration, &v);
+  int view = ClosestView(model, v.body2camera, rotation_mode);
+  if (view_index) *view_index = view;
+  int n_points = AdaptiveCount(p->n_points_max, p->use_adaptive_coverage, p->reference_surface_area,
+                               model->view_scalars ? model->view_scalars[view] : 0.0f, model->max_view_scalar,
+                               model->n_points);
+  const float* pts = model->points + size_t(view) * model->n_points * ORC_DEPTH_POINT_FLOATS;
+  for (int i = 0; i < n_points; ++i) {
+    const float* dp = pts + size_t(i) * ORC_DEPTH_POINT_FLOATS;
+    orc_depth_point& P = points[i];
+    std::memset(&P, 0, sizeof(P));
+    P.model_index = i;
+    // CalculateBasicPointData (:656-695)
+    float cc[3];
+    PoseApply(v.body2camera, dp, cc);
+    for (int k = 0; k < 3; ++k) { P.center_f_body[k] = dp[k]; P.normal_f_body[k] = dp[3 + k]; }
+    float center_u = cc[0] * v.fu / cc[2] + v.ppu;
+    float center_v = cc[1] * v.fv / cc[2] + v.ppv;
+    float depth = cc[2];
+    // IsPointValid (:697-726)
+    if (depth <= 0.0f) continue;
+    int i_center_u = int(center_u + 0.5f);
+    int i_center_v = int(center_v + 0.5f);
+    if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+    if (!FindCorrespondence(p, v, f, cc, center_u, center_v, depth, P.correspondence_center_f_camera)) continue;
+    P.valid = 1;
+  }
+  return n_points;
+}
+
+// ---- DepthModality::CalculateGradientAndHessian (depth_modality.cpp:333-381) ------------------
+void orc_depth_gradient_hessian(const orc_depth_params* p, const orc_depth_frame* f, const float body2world[12],
+                                const orc_depth_point* points, int n_points, int corr_iteration, float g[6],
+                                float H[36]) {
+  DepthVars v;
+  DepthPrecalc(p, f, body2world, corr_iteration, &v);
+  for (int i = 0; i < 6; ++i) g[i] = 0.0f;
+  for (int i = 0; i < 36; ++i) H[i] = 0.0f;
+  for (int pi = 0; pi < n_points; ++pi) {
+    const orc_depth_point& P = points[pi];
+    if (!P.valid) continue;
+    float yb[3];
+    PoseApply(v.camera2body, P.correspondence_center_f_camera, yb);
+    const float* n = P.normal_f_body;
+    const float* xb = P.center_f_body;
+    float epsilon = n[0] * (xb[0] - yb[0]) + n[1] * (xb[1] - yb[1]) + n[2] * (xb[2] - yb[2]);
+    float cx[3] = {yb[1] * n[2] - yb[2] * n[1], yb[2] * n[0] - yb[0] * n[2], yb[0] * n[1] - yb[1] * n[0]};
+    float correspondence_depth = P.correspondence_center_f_camera[2];
+    float weight = 1.0f / (v.standard_deviation * correspondence_depth);
+    float squared_weight = weight * weight;
+    float wc[3] = {weight * cx[0], weight * cx[1], weight * cx[2]};
+    float wn[3] = {weight * n[0], weight * n[1], weight * n[2]};
+    float se = squared_weight * epsilon;
+    for (int i = 0; i < 3; ++i) {
+      g[i] -= se * cx[i];
+      g[3 + i] -= se * n[i];
+    }
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) H[6 * i + j] -= wc[i] * wc[j];           // topLeft, Upper
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) H[6 * i + 3 + j] -= wc[i] * wn[j];       // topRight
+    for (int i = 0; i < 3; ++i)
+      for (int j = i; j < 3; ++j) H[6 * (3 + i) + 3 + j] -= wn[i] * wn[j]; // bottomRight, Upper
+  }
+  for (int i = 0; i < 6; ++i)
+    for (int j = 0; j < i; ++j) H[6 * i + j] = H[6 * j + i];  // selfadjointView<Upper>
+}
+
+// ---- Optimizer::CalculateOptimization for one rigid body (optimizer.cpp:144-167) --------------
+int orc_optimize_rigid(const float g[6], const float H[36], float tikhonov_rotation, float tikhonov_translation,
+                       int exp_mode, float body2world[12], float theta_out[6]) {
+  float a[36], b[6], theta[6];
+  // b += J^T g ; a(lower) -= J^T H J with J = I6 (root link, body2joint = I, all directions free)
+  for (int i = 0; i < 6; ++i) {
+    b[i] = 0.0f + g[i];
+    for (int j = 0; j < 6; ++j) a[6 * i + j] = (j <= i) ? 0.0f - H[6 * i + j] : 0.0f;
+  }
+  for (int i = 0; i < 6; ++i) a[6 * i + i] += (i < 3) ? tikhonov_rotation : tikhonov_translation;  // :159, :252-271
+  LdltSolve(6, a, b, theta);
+  if (theta_out) std::memcpy(theta_out, theta, sizeof(theta));
+  for (int i = 0; i < 6; ++i)
+    if (std::isnan(theta[i])) return 0;  // :165
+  // Link::UpdatePoses (link.cpp:205-241), root link: link2world * [exp(skew(theta_r)) | theta_t]
+  float e[9];
+  ExpSkew(theta, exp_mode, e);
+  float var[12] = {e[0], e[1], e[2], theta[3], e[3], e[4], e[5], theta[4], e[6], e[7], e[8], theta[5]};
+  float nb[12];
+  PoseMul(body2world, var, nb);
+  std::memcpy(body2world, nb, sizeof(nb));
+  return 1;
+}
+
+// ---- batch drivers ---------------------------------------------------------------------------
+int orc_max_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+static void StartOne(orc_body* b, int iteration, int rotation_mode) {
+  // RegionModality::StartModality (region_modality.cpp:375-388)
+  b->first_iteration = iteration;
+  if (!b->region) return;
+  int nb = b->region->n_histogram_bins;
+  size_t n = size_t(nb) * nb * nb;
+  std::vector<float> mf(n, 0.0f), mb(n, 0.0f);
+  orc_region_add_line_pixels(b->region, b->region_model, b->color, b->body2world, rotation_mode, mf.data(), mb.data());
+  orc_hist_calculate(nb, 1.0f, mf.data(), b->histogram_f);  // InitializeHistograms (color_histograms.cpp:72-81)
+  orc_hist_calculate(nb, 1.0f, mb.data(), b->histogram_b);
+}
+
+void orc_start_modalities(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads) {
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int i = 0; i < n_bodies; ++i) StartOne(&bodies[i], iteration, rotation_mode);
+}
+
+static void ResultsOne(orc_body* b, int rotation_mode) {
+  // RegionModality::CalculateResults (region_modality.cpp:572-583)
+  if (!b->region) return;
+  int nb = b->region->n_histogram_bins;
+  size_t n = size_t(nb) * nb * nb;
+  std::vector<float> mf(n, 0.0f), mb(n, 0.0f);
+  orc_region_add_line_pixels(b->region, b->region_model, b->color, b->body2world, rotation_mode, mf.data(), mb.data());
+  orc_hist_calculate(nb, b->region->learning_rate_f, mf.data(), b->histogram_f);  // UpdateHistograms (:83-92)
+  orc_hist_calculate(nb, b->region->learning_rate_b, mb.data(), b->histogram_b);
+}
+
+void orc_calculate_results(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads) {
+  (void)iteration;
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int i = 0; i < n_bodies; ++i) ResultsOne(&bodies[i], rotation_mode);
+}
+
+// Tracker::ExecuteTrackingStep (tracker.cpp:344-361) for one body (= one optimizer with a root link).
+static void StepOne(orc_body* b, int iteration, int n_corr, int n_update, int rotation_mode, int exp_mode,
+                    double* phase) {
+  for (int corr = 0; corr < n_corr; ++corr) {
+    double t0 = Now();
+    if (b->region)
+      b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, nullptr, b->histogram_f,
+                                              b->histogram_b, b->body2world, iteration, b->first_iteration, corr,
+                                              rotation_mode, b->lines, &b->region_view);
+    if (b->depth)
+      b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
+                                              b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);
+    double t1 = Now();
+    phase[0] += t1 - t0;
+    for (int upd = 0; upd < n_update; ++upd) {
+      double t2 = Now();
+      float g[6] = {0, 0, 0, 0, 0, 0}, H[36], gr[6], Hr[36], gd[6], Hd[36];
+      for (int i = 0; i < 36; ++i) H[i] = 0.0f;
+      // Link::CalculateGradientAndHessian (link.cpp:184-193): region first, then depth
+      if (b->region) {
+        orc_region_gradient_hessian(b->region, b->color, b->body2world, b->lines, b->n_lines, corr, upd,
+                                    rotation_mode, gr, Hr);
+        for (int i = 0; i < 6; ++i) g[i] += gr[i];
+        for (int i = 0; i < 36; ++i) H[i] += Hr[i];
+      }
+      if (b->depth) {
+        orc_depth_gradient_hessian(b->depth, b->depth_frame, b->body2world, b->points, b->n_points, corr, gd, Hd);
+        for (int i = 0; i < 6; ++i) g[i] += gd[i];
+        for (int i = 0; i < 36; ++i) H[i] += Hd[i];
+      }
+      double t3 = Now();
+      phase[1] += t3 - t2;
+      orc_optimize_rigid(g, H, b->tikhonov_rotation, b->tikhonov_translation, exp_mode, b->body2world, nullptr);
+      phase[2] += Now() - t3;
+    }
+  }
+}
+
+void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int n_corr, int n_update, int rotation_mode,
+                       int exp_mode, int n_threads, double* phase_seconds) {
+  double p0 = 0, p1 = 0, p2 = 0;
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1) reduction(+ : p0, p1, p2)
+  for (int i = 0; i < n_bodies; ++i) {
+    double phase[3] = {0, 0, 0};
+    StepOne(&bodies[i], iteration, n_corr, n_update, rotation_mode, exp_mode, phase);
+    p0 += phase[0]; p1 += phase[1]; p2 += phase[2];
+  }
+  if (phase_seconds) {
+    phase_seconds[0] += p0; phase_seconds[1] += p1; phase_seconds[2] += p2;
+  }
+}
+
+}  // extern "C"

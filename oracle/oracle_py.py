@@ -1,0 +1,331 @@
+"""ctypes binding of the CPU oracle (oracle/libm3t_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs. The product package never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+ROTATION_LINEAR, ROTATION_POLAR = 0, 1
+EXP_RODRIGUES, EXP_PADE = 0, 1
+MAX_SCHEDULE = 8
+
+fp = C.POINTER(C.c_float)
+
+
+class Intrinsics(C.Structure):
+    _fields_ = [("fu", C.c_float), ("fv", C.c_float), ("ppu", C.c_float), ("ppv", C.c_float),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class RegionParams(C.Structure):
+    _fields_ = [("n_lines_max", C.c_int32), ("use_adaptive_coverage", C.c_int32),
+                ("reference_contour_length", C.c_float), ("min_continuous_distance", C.c_float),
+                ("function_length", C.c_int32), ("distribution_length", C.c_int32),
+                ("function_amplitude", C.c_float), ("function_slope", C.c_float), ("learning_rate", C.c_float),
+                ("n_global_iterations", C.c_int32), ("n_scales", C.c_int32), ("scales", C.c_int32 * MAX_SCHEDULE),
+                ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
+                ("n_histogram_bins", C.c_int32), ("learning_rate_f", C.c_float), ("learning_rate_b", C.c_float),
+                ("unconsidered_line_length", C.c_float), ("max_considered_line_length", C.c_float),
+                ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
+                ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("n_points_max", C.c_int32), ("use_adaptive_coverage", C.c_int32), ("use_depth_scaling", C.c_int32),
+                ("reference_surface_area", C.c_float), ("stride_length", C.c_float),
+                ("n_considered_distances", C.c_int32), ("considered_distances", C.c_float * MAX_SCHEDULE),
+                ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
+                ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
+                ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32)]
+
+
+class RegionLine(C.Structure):
+    _fields_ = [("model_index", C.c_int32), ("valid", C.c_int32), ("center_f_body", C.c_float * 3),
+                ("center_u", C.c_float), ("center_v", C.c_float), ("normal_u", C.c_float), ("normal_v", C.c_float),
+                ("delta_r", C.c_float), ("normal_component_to_scale", C.c_float), ("distribution", C.c_float * 12),
+                ("mean", C.c_float), ("measured_variance", C.c_float)]
+
+
+class DepthPoint(C.Structure):
+    _fields_ = [("model_index", C.c_int32), ("valid", C.c_int32), ("center_f_body", C.c_float * 3),
+                ("normal_f_body", C.c_float * 3), ("correspondence_center_f_camera", C.c_float * 3)]
+
+
+REGION_LINE_DTYPE = np.dtype([("model_index", "<i4"), ("valid", "<i4"), ("center_f_body", "<f4", 3),
+                              ("center_u", "<f4"), ("center_v", "<f4"), ("normal_u", "<f4"), ("normal_v", "<f4"),
+                              ("delta_r", "<f4"), ("normal_component_to_scale", "<f4"), ("distribution", "<f4", 12),
+                              ("mean", "<f4"), ("measured_variance", "<f4")])
+DEPTH_POINT_DTYPE = np.dtype([("model_index", "<i4"), ("valid", "<i4"), ("center_f_body", "<f4", 3),
+                              ("normal_f_body", "<f4", 3), ("correspondence_center_f_camera", "<f4", 3)])
+assert REGION_LINE_DTYPE.itemsize == C.sizeof(RegionLine)
+assert DEPTH_POINT_DTYPE.itemsize == C.sizeof(DepthPoint)
+
+
+class Model(C.Structure):
+    _fields_ = [("n_views", C.c_int32), ("n_points", C.c_int32), ("orientations", fp), ("view_scalars", fp),
+                ("points", fp), ("stride_depth_offset", C.c_float), ("max_radius_depth_offset", C.c_float),
+                ("max_view_scalar", C.c_float)]
+
+
+class ColorFrame(C.Structure):
+    _fields_ = [("intrinsics", Intrinsics), ("world2camera", C.c_float * 12), ("bgr", C.c_void_p),
+                ("pitch", C.c_size_t)]
+
+
+class DepthFrame(C.Structure):
+    _fields_ = [("intrinsics", Intrinsics), ("world2camera", C.c_float * 12), ("depth", C.c_void_p),
+                ("pitch", C.c_size_t), ("depth_scale", C.c_float)]
+
+
+class Body(C.Structure):
+    _fields_ = [("body2world", C.c_float * 12), ("region", C.POINTER(RegionParams)), ("region_model", C.POINTER(Model)),
+                ("color", C.POINTER(ColorFrame)), ("depth", C.POINTER(DepthParams)), ("depth_model", C.POINTER(Model)),
+                ("depth_frame", C.POINTER(DepthFrame)), ("histogram_f", fp), ("histogram_b", fp),
+                ("tikhonov_rotation", C.c_float), ("tikhonov_translation", C.c_float), ("first_iteration", C.c_int32),
+                ("lines", C.POINTER(RegionLine)), ("points", C.POINTER(DepthPoint)), ("n_lines", C.c_int32),
+                ("n_points", C.c_int32), ("region_view", C.c_int32), ("depth_view", C.c_int32)]
+
+
+_libs = {}
+
+
+def build(native=False):
+    target = "native" if native else "all"
+    subprocess.run(["make", "-C", _HERE, target], check=True, capture_output=True)
+
+
+def lib(native=False):
+    """native=True: the -O3 -march=native build (timing only; built on the machine it runs on)."""
+    key = "native" if native else "strict"
+    if key in _libs:
+        return _libs[key]
+    name = "libm3t_oracle_native.so" if native else "libm3t_oracle.so"
+    path = os.path.join(_HERE, name)
+    if native or not os.path.exists(path):
+        build(native)
+    L = C.CDLL(path)
+    L.orc_region_params_default.argtypes = [C.POINTER(RegionParams)]
+    L.orc_depth_params_default.argtypes = [C.POINTER(DepthParams)]
+    L.orc_pose_multiply.argtypes = [fp, fp, fp]
+    L.orc_pose_inverse.argtypes = [fp, fp]
+    L.orc_pose_rotation.argtypes = [fp, C.c_int, fp]
+    L.orc_exp_skew.argtypes = [fp, C.c_int, fp]
+    L.orc_ldlt_solve.argtypes = [C.c_int, fp, fp, fp]
+    L.orc_ldlt_solve.restype = C.c_int
+    L.orc_function_lookup.argtypes = [C.POINTER(RegionParams), fp, fp, fp]
+    L.orc_hist_clear.argtypes = [C.c_int, fp, fp]
+    L.orc_hist_add.argtypes = [C.c_int, fp, C.POINTER(C.c_uint8)]
+    L.orc_hist_calculate.argtypes = [C.c_int, C.c_float, fp, fp]
+    L.orc_hist_get.argtypes = [C.c_int, fp, fp, C.POINTER(C.c_uint8), fp, fp]
+    L.orc_closest_view.argtypes = [C.POINTER(Model), fp, C.c_int]
+    L.orc_closest_view.restype = C.c_int
+    L.orc_region_add_line_pixels.argtypes = [C.POINTER(RegionParams), C.POINTER(Model), C.POINTER(ColorFrame), fp,
+                                             C.c_int, fp, fp]
+    L.orc_region_correspondences.argtypes = [C.POINTER(RegionParams), C.POINTER(Model), C.POINTER(ColorFrame),
+                                             C.POINTER(DepthFrame), fp, fp, fp, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.POINTER(RegionLine), C.POINTER(C.c_int)]
+    L.orc_region_correspondences.restype = C.c_int
+    L.orc_region_gradient_hessian.argtypes = [C.POINTER(RegionParams), C.POINTER(ColorFrame), fp,
+                                              C.POINTER(RegionLine), C.c_int, C.c_int, C.c_int, C.c_int, fp, fp]
+    L.orc_depth_correspondences.argtypes = [C.POINTER(DepthParams), C.POINTER(Model), C.POINTER(DepthFrame), fp,
+                                            C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(DepthPoint),
+                                            C.POINTER(C.c_int)]
+    L.orc_depth_correspondences.restype = C.c_int
+    L.orc_depth_gradient_hessian.argtypes = [C.POINTER(DepthParams), C.POINTER(DepthFrame), fp, C.POINTER(DepthPoint),
+                                             C.c_int, C.c_int, fp, fp]
+    L.orc_optimize_rigid.argtypes = [fp, fp, C.c_float, C.c_float, C.c_int, fp, fp]
+    L.orc_optimize_rigid.restype = C.c_int
+    L.orc_start_modalities.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_tracking_step.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(C.c_double)]
+    L.orc_calculate_results.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int]
+    L.orc_max_threads.restype = C.c_int
+    _libs[key] = L
+    return L
+
+
+def f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ptr(a):
+    return a.ctypes.data_as(fp)
+
+
+def region_params(settings) -> RegionParams:
+    p = RegionParams()
+    lib().orc_region_params_default(C.byref(p))
+    if settings is None:
+        return p
+    for k in ("n_lines_max", "min_continuous_distance", "function_amplitude", "function_slope", "learning_rate",
+              "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
+              "unconsidered_line_length", "max_considered_line_length"):
+        setattr(p, k, getattr(settings, k))
+    p.n_scales = len(settings.scales)
+    p.n_standard_deviations = len(settings.standard_deviations)
+    for i, s in enumerate(settings.scales):
+        p.scales[i] = int(s)
+    for i, s in enumerate(settings.standard_deviations):
+        p.standard_deviations[i] = float(s)
+    return p
+
+
+def depth_params(settings) -> DepthParams:
+    p = DepthParams()
+    lib().orc_depth_params_default(C.byref(p))
+    if settings is None:
+        return p
+    p.n_points_max = settings.n_points_max
+    p.stride_length = settings.stride_length
+    p.n_considered_distances = len(settings.considered_distances)
+    p.n_standard_deviations = len(settings.standard_deviations)
+    for i, s in enumerate(settings.considered_distances):
+        p.considered_distances[i] = float(s)
+    for i, s in enumerate(settings.standard_deviations):
+        p.standard_deviations[i] = float(s)
+    return p
+
+
+def make_model(m) -> Model:
+    """m: 3dobjecttracking_b200.synth.Model (or anything with the same attributes)."""
+    om = Model()
+    om.n_views, om.n_points = m.n_views, m.n_points
+    om.orientations = ptr(m.orientations)
+    om.view_scalars = ptr(m.view_scalars)
+    om.points = ptr(m.points)
+    om.stride_depth_offset = m.stride_depth_offset
+    om.max_radius_depth_offset = m.max_radius_depth_offset
+    om.max_view_scalar = float(m.view_scalars.max()) if m.view_scalars.size else 0.0
+    return om
+
+
+def _intr(i) -> Intrinsics:
+    return Intrinsics(i.fu, i.fv, i.ppu, i.ppv, i.width, i.height)
+
+
+class OracleTracker:
+    """Drives the oracle over a synth.Workload the way Tracker drives modalities + optimizers."""
+
+    def __init__(self, wl, rotation_mode=ROTATION_POLAR, exp_mode=EXP_PADE, n_threads=1, native=False):
+        self.wl = wl
+        self.L = lib(native)
+        self.rotation_mode, self.exp_mode, self.n_threads = rotation_mode, exp_mode, n_threads
+        nb = wl.n_bodies
+        self.rp = region_params(wl.region) if wl.region else None
+        self.dp = depth_params(wl.depth) if wl.depth else None
+        self.rm = make_model(wl.region_model) if wl.region else None
+        self.dm = make_model(wl.depth_model) if wl.depth else None
+        self.bodies = (Body * nb)()
+        self.color_frames = (ColorFrame * nb)()
+        self.depth_frames = (DepthFrame * nb)()
+        nbins = wl.region.n_histogram_bins if wl.region else 1
+        self.hist_f = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
+        self.hist_b = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
+        self.lines = np.zeros((nb, max(wl.lines_per_body, 1)), REGION_LINE_DTYPE)
+        self.points = np.zeros((nb, max(wl.points_per_body, 1)), DEPTH_POINT_DTYPE)
+        for b in range(nb):
+            B = self.bodies[b]
+            if wl.region:
+                cf = self.color_frames[b]
+                cf.intrinsics = _intr(wl.color_intrinsics)
+                cf.world2camera[:] = f32(wl.color_world2camera).reshape(12).tolist()
+                cf.bgr = wl.color_frames[b].ctypes.data
+                cf.pitch = wl.color_frames[b].strides[0]
+                B.region = C.pointer(self.rp)
+                B.region_model = C.pointer(self.rm)
+                B.color = C.pointer(cf)
+                B.histogram_f = ptr(self.hist_f[b])
+                B.histogram_b = ptr(self.hist_b[b])
+                B.lines = self.lines[b].ctypes.data_as(C.POINTER(RegionLine))
+            if wl.depth:
+                df = self.depth_frames[b]
+                df.intrinsics = _intr(wl.depth_intrinsics)
+                df.world2camera[:] = f32(wl.depth_world2camera).reshape(12).tolist()
+                df.depth = wl.depth_frames[b].ctypes.data
+                df.pitch = wl.depth_frames[b].strides[0]
+                df.depth_scale = wl.depth_scale
+                B.depth = C.pointer(self.dp)
+                B.depth_model = C.pointer(self.dm)
+                B.depth_frame = C.pointer(df)
+                B.points = self.points[b].ctypes.data_as(C.POINTER(DepthPoint))
+            B.tikhonov_rotation = wl.tikhonov_rotation
+            B.tikhonov_translation = wl.tikhonov_translation
+        self.set_poses(wl.start_body2world)
+
+    def set_poses(self, poses):
+        p = f32(poses).reshape(self.wl.n_bodies, 12)
+        for b in range(self.wl.n_bodies):
+            self.bodies[b].body2world[:] = p[b].tolist()
+
+    def get_poses(self):
+        return np.array([list(self.bodies[b].body2world) for b in range(self.wl.n_bodies)], np.float32).reshape(-1, 3, 4)
+
+    def start_modalities(self, iteration=0):
+        self.L.orc_start_modalities(self.bodies, self.wl.n_bodies, iteration, self.rotation_mode, self.n_threads)
+
+    def tracking_step(self, iteration=0, n_corr=None, n_update=None, first=None, count=None):
+        """Runs bodies [first, first+count). Returns the 3 phase times (s, summed over threads)."""
+        n_corr = self.wl.n_corr_iterations if n_corr is None else n_corr
+        n_update = self.wl.n_update_iterations if n_update is None else n_update
+        first = 0 if first is None else first
+        count = self.wl.n_bodies - first if count is None else count
+        phases = (C.c_double * 4)()
+        base = C.cast(C.byref(self.bodies, first * C.sizeof(Body)), C.POINTER(Body))
+        self.L.orc_tracking_step(base, count, iteration, n_corr, n_update, self.rotation_mode, self.exp_mode,
+                                 self.n_threads, phases)
+        return list(phases)
+
+    def calculate_results(self, iteration=0):
+        self.L.orc_calculate_results(self.bodies, self.wl.n_bodies, iteration, self.rotation_mode, self.n_threads)
+
+    # fine-grained, one body
+    def region_correspondences(self, b, iteration, corr):
+        B = self.bodies[b]
+        view = C.c_int(0)
+        n = self.L.orc_region_correspondences(B.region, B.region_model, B.color, None, B.histogram_f, B.histogram_b,
+                                              B.body2world, iteration, B.first_iteration, corr, self.rotation_mode,
+                                              B.lines, C.byref(view))
+        B.n_lines, B.region_view = n, view.value
+        return n, view.value
+
+    def region_gradient_hessian(self, b, corr, opt):
+        B = self.bodies[b]
+        g = np.zeros(6, np.float32)
+        H = np.zeros(36, np.float32)
+        self.L.orc_region_gradient_hessian(B.region, B.color, B.body2world, B.lines, B.n_lines, corr, opt,
+                                           self.rotation_mode, ptr(g), ptr(H))
+        return g, H.reshape(6, 6)
+
+    def depth_correspondences(self, b, iteration, corr):
+        B = self.bodies[b]
+        view = C.c_int(0)
+        n = self.L.orc_depth_correspondences(B.depth, B.depth_model, B.depth_frame, B.body2world, iteration,
+                                             B.first_iteration, corr, self.rotation_mode, B.points, C.byref(view))
+        B.n_points, B.depth_view = n, view.value
+        return n, view.value
+
+    def depth_gradient_hessian(self, b, corr):
+        B = self.bodies[b]
+        g = np.zeros(6, np.float32)
+        H = np.zeros(36, np.float32)
+        self.L.orc_depth_gradient_hessian(B.depth, B.depth_frame, B.body2world, B.points, B.n_points, corr, ptr(g),
+                                          ptr(H))
+        return g, H.reshape(6, 6)
+
+    def optimize(self, b, g, H):
+        B = self.bodies[b]
+        theta = np.zeros(6, np.float32)
+        g, H = f32(g), f32(H).reshape(36)
+        ok = self.L.orc_optimize_rigid(ptr(g), ptr(H), B.tikhonov_rotation, B.tikhonov_translation, self.exp_mode,
+                                       B.body2world, ptr(theta))
+        return ok, theta
