@@ -1,0 +1,352 @@
+"""ctypes binding of libm3t_b200.so (include/m3t_b200.h) + a Workload -> context helper.
+
+This is the CUDA path and the only compute path of the package: loading fails loudly when the
+library is missing and every call raises M3TBError on a non-zero status (no CPU fallback).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _build
+from .synth import Intrinsics, Workload
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libm3t_b200.so")
+MAX_SCHEDULE = 8
+
+fp = C.POINTER(C.c_float)
+
+
+class M3TBError(RuntimeError):
+    pass
+
+
+class RegionParams(C.Structure):
+    _fields_ = [("n_lines_max", C.c_int32), ("use_adaptive_coverage", C.c_int32),
+                ("reference_contour_length", C.c_float), ("min_continuous_distance", C.c_float),
+                ("function_length", C.c_int32), ("distribution_length", C.c_int32),
+                ("function_amplitude", C.c_float), ("function_slope", C.c_float), ("learning_rate", C.c_float),
+                ("n_global_iterations", C.c_int32), ("n_scales", C.c_int32), ("scales", C.c_int32 * MAX_SCHEDULE),
+                ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
+                ("n_histogram_bins", C.c_int32), ("learning_rate_f", C.c_float), ("learning_rate_b", C.c_float),
+                ("unconsidered_line_length", C.c_float), ("max_considered_line_length", C.c_float),
+                ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
+                ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32)]
+
+
+class DepthParams(C.Structure):
+    _fields_ = [("n_points_max", C.c_int32), ("use_adaptive_coverage", C.c_int32), ("use_depth_scaling", C.c_int32),
+                ("reference_surface_area", C.c_float), ("stride_length", C.c_float),
+                ("n_considered_distances", C.c_int32), ("considered_distances", C.c_float * MAX_SCHEDULE),
+                ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
+                ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
+                ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32)]
+
+
+class OptimizerParams(C.Structure):
+    _fields_ = [("tikhonov_parameter_rotation", C.c_float), ("tikhonov_parameter_translation", C.c_float)]
+
+
+REGION_LINE_DTYPE = np.dtype([("model_index", "<i4"), ("valid", "<i4"), ("center_f_body", "<f4", 3),
+                              ("center_u", "<f4"), ("center_v", "<f4"), ("normal_u", "<f4"), ("normal_v", "<f4"),
+                              ("delta_r", "<f4"), ("normal_component_to_scale", "<f4"), ("distribution", "<f4", 12),
+                              ("mean", "<f4"), ("measured_variance", "<f4")])
+DEPTH_POINT_DTYPE = np.dtype([("model_index", "<i4"), ("valid", "<i4"), ("center_f_body", "<f4", 3),
+                              ("normal_f_body", "<f4", 3), ("correspondence_center_f_camera", "<f4", 3)])
+
+# every symbol include/m3t_b200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "m3tb_region_params_default", "m3tb_depth_params_default", "m3tb_optimizer_params_default", "m3tb_create",
+    "m3tb_destroy", "m3tb_set_stream", "m3tb_synchronize", "m3tb_last_error", "m3tb_launch_count",
+    "m3tb_set_region_model", "m3tb_set_depth_model", "m3tb_set_color_camera", "m3tb_set_depth_camera",
+    "m3tb_upload_color", "m3tb_upload_depth", "m3tb_upload_color_device", "m3tb_upload_depth_device",
+    "m3tb_upload_color_batch", "m3tb_upload_depth_batch", "m3tb_set_body", "m3tb_n_bodies", "m3tb_set_poses",
+    "m3tb_get_poses", "m3tb_set_histograms", "m3tb_get_histograms", "m3tb_tracking_step", "m3tb_corr_iteration",
+    "m3tb_start_modalities", "m3tb_calculate_results", "m3tb_region_correspondences",
+    "m3tb_region_gradient_hessian", "m3tb_depth_correspondences", "m3tb_depth_gradient_hessian",
+    "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
+]
+
+_lib = None
+
+
+def lib():
+    """Loads libm3t_b200.so (building it in-tree with nvcc if the sources are newer). Raises if that fails."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        _build.build_cuda()
+    L = C.CDLL(LIB_PATH)
+    vp, ci = C.c_void_p, C.c_int
+    L.m3tb_region_params_default.argtypes = [C.POINTER(RegionParams)]
+    L.m3tb_depth_params_default.argtypes = [C.POINTER(DepthParams)]
+    L.m3tb_optimizer_params_default.argtypes = [C.POINTER(OptimizerParams)]
+    L.m3tb_create.argtypes = [ci, ci, ci, ci, C.POINTER(vp)]
+    L.m3tb_destroy.argtypes = [vp]
+    L.m3tb_set_stream.argtypes = [vp, vp]
+    L.m3tb_synchronize.argtypes = [vp]
+    L.m3tb_last_error.argtypes = [vp]
+    L.m3tb_last_error.restype = C.c_char_p
+    L.m3tb_launch_count.argtypes = [vp]
+    L.m3tb_launch_count.restype = C.c_int64
+    for n in ("m3tb_set_region_model", "m3tb_set_depth_model"):
+        getattr(L, n).argtypes = [vp, ci, ci, ci, fp, fp, vp, C.c_float, C.c_float]
+    L.m3tb_set_color_camera.argtypes = [vp, ci, C.POINTER(Intrinsics), fp]
+    L.m3tb_set_depth_camera.argtypes = [vp, ci, C.POINTER(Intrinsics), fp, C.c_float]
+    for n in ("m3tb_upload_color", "m3tb_upload_depth", "m3tb_upload_color_device", "m3tb_upload_depth_device"):
+        getattr(L, n).argtypes = [vp, ci, vp, C.c_size_t]
+    for n in ("m3tb_upload_color_batch", "m3tb_upload_depth_batch"):
+        getattr(L, n).argtypes = [vp, ci, ci, vp, C.c_size_t, C.c_size_t]
+    L.m3tb_set_body.argtypes = [vp, ci, C.POINTER(RegionParams), C.POINTER(DepthParams), C.POINTER(OptimizerParams),
+                                ci, ci, ci, ci]
+    L.m3tb_n_bodies.argtypes = [vp]
+    L.m3tb_set_poses.argtypes = [vp, ci, ci, fp]
+    L.m3tb_get_poses.argtypes = [vp, ci, ci, fp]
+    L.m3tb_set_histograms.argtypes = [vp, ci, fp, fp]
+    L.m3tb_get_histograms.argtypes = [vp, ci, fp, fp]
+    L.m3tb_tracking_step.argtypes = [vp, ci, ci, ci]
+    L.m3tb_corr_iteration.argtypes = [vp, ci, ci, ci]
+    L.m3tb_start_modalities.argtypes = [vp, ci]
+    L.m3tb_calculate_results.argtypes = [vp, ci]
+    L.m3tb_region_correspondences.argtypes = [vp, ci, ci]
+    L.m3tb_depth_correspondences.argtypes = [vp, ci, ci]
+    L.m3tb_region_gradient_hessian.argtypes = [vp, ci, ci, ci, fp, fp]
+    L.m3tb_depth_gradient_hessian.argtypes = [vp, ci, ci, ci, fp, fp]
+    L.m3tb_calculate_optimization.argtypes = [vp, ci, ci, ci]
+    L.m3tb_get_region_lines.argtypes = [vp, ci, vp, ci, C.POINTER(ci)]
+    L.m3tb_get_depth_points.argtypes = [vp, ci, vp, ci, C.POINTER(ci)]
+    L.m3tb_get_closest_views.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    _lib = L
+    return L
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a):
+    return a.ctypes.data_as(fp)
+
+
+def region_params(settings=None) -> RegionParams:
+    p = RegionParams()
+    lib().m3tb_region_params_default(C.byref(p))
+    if settings is None:
+        return p
+    for k in ("n_lines_max", "min_continuous_distance", "function_amplitude", "function_slope", "learning_rate",
+              "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
+              "unconsidered_line_length", "max_considered_line_length"):
+        setattr(p, k, getattr(settings, k))
+    p.n_scales = len(settings.scales)
+    p.n_standard_deviations = len(settings.standard_deviations)
+    for i, s in enumerate(settings.scales):
+        p.scales[i] = int(s)
+    for i, s in enumerate(settings.standard_deviations):
+        p.standard_deviations[i] = float(s)
+    return p
+
+
+def depth_params(settings=None) -> DepthParams:
+    p = DepthParams()
+    lib().m3tb_depth_params_default(C.byref(p))
+    if settings is None:
+        return p
+    p.n_points_max = settings.n_points_max
+    p.stride_length = settings.stride_length
+    p.n_considered_distances = len(settings.considered_distances)
+    p.n_standard_deviations = len(settings.standard_deviations)
+    for i, s in enumerate(settings.considered_distances):
+        p.considered_distances[i] = float(s)
+    for i, s in enumerate(settings.standard_deviations):
+        p.standard_deviations[i] = float(s)
+    return p
+
+
+class Context:
+    """Thin object wrapper over an m3tb_ctx."""
+
+    def __init__(self, device=0, max_bodies=1, max_cameras=1, max_models=1, stream=None):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.m3tb_create(device, max_bodies, max_cameras, max_models, C.byref(h))
+        if rc != 0:
+            raise M3TBError(f"m3tb_create failed with status {rc} (no usable sm_100 CUDA device?)")
+        self.h = h
+        self.n_bodies = 0
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise M3TBError(f"status {rc}: {self.L.m3tb_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.m3tb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.L.m3tb_set_stream(self.h, C.c_void_p(cuda_stream_handle)))
+
+    def synchronize(self):
+        self._ck(self.L.m3tb_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(self.L.m3tb_launch_count(self.h))
+
+    def set_region_model(self, model_id, m):
+        self._ck(self.L.m3tb_set_region_model(self.h, model_id, m.n_views, m.n_points, _p(m.orientations),
+                                              _p(m.view_scalars), m.points.ctypes.data_as(C.c_void_p),
+                                              m.stride_depth_offset, m.max_radius_depth_offset))
+
+    def set_depth_model(self, model_id, m):
+        self._ck(self.L.m3tb_set_depth_model(self.h, model_id, m.n_views, m.n_points, _p(m.orientations),
+                                             _p(m.view_scalars), m.points.ctypes.data_as(C.c_void_p),
+                                             m.stride_depth_offset, m.max_radius_depth_offset))
+
+    def set_color_camera(self, cam, intr, w2c):
+        w = _f32(w2c).reshape(12)
+        self._ck(self.L.m3tb_set_color_camera(self.h, cam, C.byref(intr), _p(w)))
+
+    def set_depth_camera(self, cam, intr, w2c, depth_scale):
+        w = _f32(w2c).reshape(12)
+        self._ck(self.L.m3tb_set_depth_camera(self.h, cam, C.byref(intr), _p(w), depth_scale))
+
+    def upload_color(self, cam, frame):
+        self._ck(self.L.m3tb_upload_color(self.h, cam, frame.ctypes.data_as(C.c_void_p), frame.strides[0]))
+
+    def upload_depth(self, cam, frame):
+        self._ck(self.L.m3tb_upload_depth(self.h, cam, frame.ctypes.data_as(C.c_void_p), frame.strides[0]))
+
+    def upload_color_batch(self, first, frames):
+        """frames: [n,H,pitch] u8 (numpy or a pinned torch tensor's numpy view)."""
+        self._ck(self.L.m3tb_upload_color_batch(self.h, first, frames.shape[0], C.c_void_p(frames.ctypes.data),
+                                                frames.strides[0], frames.strides[1]))
+
+    def upload_depth_batch(self, first, frames):
+        self._ck(self.L.m3tb_upload_depth_batch(self.h, first, frames.shape[0], C.c_void_p(frames.ctypes.data),
+                                                frames.strides[0], frames.strides[1]))
+
+    def upload_batch_ptr(self, color, first, count, ptr, frame_stride, pitch):
+        f = self.L.m3tb_upload_color_batch if color else self.L.m3tb_upload_depth_batch
+        self._ck(f(self.h, first, count, C.c_void_p(ptr), frame_stride, pitch))
+
+    def set_body(self, body, region, depth, optimizer, region_model=0, depth_model=0, color_camera=0, depth_camera=0):
+        self._ck(self.L.m3tb_set_body(self.h, body, C.byref(region) if region is not None else None,
+                                      C.byref(depth) if depth is not None else None,
+                                      C.byref(optimizer) if optimizer is not None else None, region_model,
+                                      depth_model, color_camera, depth_camera))
+        self.n_bodies = max(self.n_bodies, body + 1)
+
+    def set_poses(self, poses, first=0):
+        p = _f32(poses).reshape(-1, 12)
+        self._ck(self.L.m3tb_set_poses(self.h, first, p.shape[0], _p(p)))
+
+    def get_poses(self, first=0, count=None):
+        count = self.n_bodies - first if count is None else count
+        out = np.zeros((count, 12), np.float32)
+        self._ck(self.L.m3tb_get_poses(self.h, first, count, _p(out)))
+        return out.reshape(count, 3, 4)
+
+    def set_histograms(self, body, hf, hb):
+        hf, hb = _f32(hf), _f32(hb)
+        self._ck(self.L.m3tb_set_histograms(self.h, body, _p(hf), _p(hb)))
+        self.synchronize()  # hf / hb are temporaries
+
+    def get_histograms(self, body, n_bins):
+        hf = np.zeros(n_bins ** 3, np.float32)
+        hb = np.zeros(n_bins ** 3, np.float32)
+        self._ck(self.L.m3tb_get_histograms(self.h, body, _p(hf), _p(hb)))
+        return hf, hb
+
+    def tracking_step(self, iteration, n_corr, n_update):
+        self._ck(self.L.m3tb_tracking_step(self.h, iteration, n_corr, n_update))
+
+    def corr_iteration(self, iteration, corr, n_update):
+        self._ck(self.L.m3tb_corr_iteration(self.h, iteration, corr, n_update))
+
+    def start_modalities(self, iteration):
+        self._ck(self.L.m3tb_start_modalities(self.h, iteration))
+
+    def calculate_results(self, iteration):
+        self._ck(self.L.m3tb_calculate_results(self.h, iteration))
+
+    def region_correspondences(self, iteration, corr):
+        self._ck(self.L.m3tb_region_correspondences(self.h, iteration, corr))
+
+    def depth_correspondences(self, iteration, corr):
+        self._ck(self.L.m3tb_depth_correspondences(self.h, iteration, corr))
+
+    def region_gradient_hessian(self, iteration, corr, opt):
+        g = np.zeros((self.n_bodies, 6), np.float32)
+        H = np.zeros((self.n_bodies, 6, 6), np.float32)
+        self._ck(self.L.m3tb_region_gradient_hessian(self.h, iteration, corr, opt, _p(g), _p(H)))
+        return g, H
+
+    def depth_gradient_hessian(self, iteration, corr, opt):
+        g = np.zeros((self.n_bodies, 6), np.float32)
+        H = np.zeros((self.n_bodies, 6, 6), np.float32)
+        self._ck(self.L.m3tb_depth_gradient_hessian(self.h, iteration, corr, opt, _p(g), _p(H)))
+        return g, H
+
+    def calculate_optimization(self, iteration, corr, opt):
+        self._ck(self.L.m3tb_calculate_optimization(self.h, iteration, corr, opt))
+
+    def get_region_lines(self, body, capacity):
+        out = np.zeros(capacity, REGION_LINE_DTYPE)
+        n = C.c_int(0)
+        self._ck(self.L.m3tb_get_region_lines(self.h, body, out.ctypes.data_as(C.c_void_p), capacity, C.byref(n)))
+        return out[:min(n.value, capacity)]
+
+    def get_depth_points(self, body, capacity):
+        out = np.zeros(capacity, DEPTH_POINT_DTYPE)
+        n = C.c_int(0)
+        self._ck(self.L.m3tb_get_depth_points(self.h, body, out.ctypes.data_as(C.c_void_p), capacity, C.byref(n)))
+        return out[:min(n.value, capacity)]
+
+    def get_closest_views(self, body):
+        a, b = C.c_int(0), C.c_int(0)
+        self._ck(self.L.m3tb_get_closest_views(self.h, body, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+
+def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=True, first=0, count=None) -> Context:
+    """One context holding bodies [first, first+count) of a workload: one colour + one depth camera per
+    body (one RGB-D pair per body), models shared."""
+    count = wl.n_bodies - first if count is None else count
+    ctx = Context(device, max_bodies=count, max_cameras=count, max_models=1, stream=stream)
+    if wl.region:
+        ctx.set_region_model(0, wl.region_model)
+    if wl.depth:
+        ctx.set_depth_model(0, wl.depth_model)
+    rp = region_params(wl.region) if wl.region else None
+    dp = depth_params(wl.depth) if wl.depth else None
+    op = OptimizerParams(wl.tikhonov_rotation, wl.tikhonov_translation)
+    for b in range(count):
+        if wl.region:
+            ctx.set_color_camera(b, wl.color_intrinsics, wl.color_world2camera)
+        if wl.depth:
+            ctx.set_depth_camera(b, wl.depth_intrinsics, wl.depth_world2camera, wl.depth_scale)
+    if upload_frames:
+        if wl.region:
+            ctx.upload_color_batch(0, wl.color_frames[first:first + count])
+        if wl.depth:
+            ctx.upload_depth_batch(0, wl.depth_frames[first:first + count])
+    for b in range(count):
+        ctx.set_body(b, rp, dp, op, 0, 0, b, b)
+    ctx.set_poses(wl.start_body2world[first:first + count])
+    ctx.synchronize()
+    return ctx

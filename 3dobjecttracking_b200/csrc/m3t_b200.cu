@@ -1,0 +1,884 @@
+// m3t_b200.cu — host side of libm3t_b200.so: context, device memory, launches; implements include/m3t_b200.h.
+// No CPU fallback anywhere: if CUDA is unusable every compute entry point returns M3TB_ERR_CUDA.
+#include "m3t_b200.h"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "m3t_b200_kernels.cuh"
+
+using namespace m3tb;
+
+namespace {
+
+struct ImagePool {
+  uint8_t* base = nullptr;
+  size_t frame_bytes = 0;
+  unsigned pitch = 0;
+  int width = 0, height = 0, capacity = 0;
+};
+
+struct ModelAlloc {
+  float* orientations = nullptr;
+  float* view_scalars = nullptr;
+  float4* points = nullptr;
+};
+
+}  // namespace
+
+struct m3tb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int max_bodies = 0, max_cameras = 0, max_models = 0;
+  int n_bodies = 0;
+  std::string err;
+  int64_t launches = 0;
+
+  std::vector<BodyDev> h_bodies;
+  std::vector<CameraDev> h_ccams, h_dcams;
+  std::vector<ModelDev> h_rmodels, h_dmodels;
+  std::vector<ModelAlloc> rmodel_alloc, dmodel_alloc;
+  std::vector<uint8_t*> private_color, private_depth;  // images that do not fit the pools
+  bool bodies_dirty = true, cams_dirty = true, models_dirty = true;
+
+  BodyDev* d_bodies = nullptr;
+  CameraDev *d_ccams = nullptr, *d_dcams = nullptr;
+  ModelDev *d_rmodels = nullptr, *d_dmodels = nullptr;
+  float* d_poses = nullptr;
+  ImagePool color_pool, depth_pool;
+
+  float *d_hist_f = nullptr, *d_hist_b = nullptr, *d_mem_f = nullptr, *d_mem_b = nullptr;
+  float2* d_lut = nullptr;
+  size_t hist_stride = 0;
+
+  float *d_rstate = nullptr, *d_dstate = nullptr;
+  int line_cap = 0, point_cap = 0;
+  int* d_counts = nullptr;
+  float *d_gh_region = nullptr, *d_gh_depth = nullptr;
+  size_t max_dyn_smem = 0;
+};
+
+namespace {
+
+int Fail(m3tb_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define CU(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess)                                                                             \
+      return Fail(ctx, M3TB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+
+#define CHECK_CTX()                                          \
+  do {                                                       \
+    if (!ctx) return M3TB_ERR_INVALID;                       \
+    cudaError_t e0_ = cudaSetDevice(ctx->device);            \
+    if (e0_ != cudaSuccess) return Fail(ctx, M3TB_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e0_)); \
+  } while (0)
+
+int Bitshift(int n_bins) {  // color_histograms.cpp:131-159
+  switch (n_bins) {
+    case 2: return 7;
+    case 4: return 6;
+    case 8: return 5;
+    case 16: return 4;
+    case 32: return 3;
+    case 64: return 2;
+    default: return -1;
+  }
+}
+
+size_t Align(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int EnsureHist(m3tb_ctx* ctx, size_t stride) {
+  if (stride <= ctx->hist_stride) return M3TB_OK;
+  const size_t nb = size_t(ctx->max_bodies);
+  float* nf[4] = {nullptr, nullptr, nullptr, nullptr};
+  float2* nl = nullptr;
+  for (int k = 0; k < 4; ++k) {
+    CU(cudaMalloc(&nf[k], nb * stride * sizeof(float)));
+    CU(cudaMemsetAsync(nf[k], 0, nb * stride * sizeof(float), ctx->stream));
+  }
+  CU(cudaMalloc(&nl, nb * stride * sizeof(float2)));
+  CU(cudaMemsetAsync(nl, 0, nb * stride * sizeof(float2), ctx->stream));
+  float* old[4] = {ctx->d_hist_f, ctx->d_hist_b, ctx->d_mem_f, ctx->d_mem_b};
+  if (ctx->hist_stride) {
+    for (int k = 0; k < 4; ++k)
+      CU(cudaMemcpy2DAsync(nf[k], stride * sizeof(float), old[k], ctx->hist_stride * sizeof(float),
+                           ctx->hist_stride * sizeof(float), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(nl, stride * sizeof(float2), ctx->d_lut, ctx->hist_stride * sizeof(float2),
+                         ctx->hist_stride * sizeof(float2), nb, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 4; ++k) cudaFree(old[k]);
+    cudaFree(ctx->d_lut);
+  }
+  ctx->d_hist_f = nf[0]; ctx->d_hist_b = nf[1]; ctx->d_mem_f = nf[2]; ctx->d_mem_b = nf[3];
+  ctx->d_lut = nl;
+  ctx->hist_stride = stride;
+  return M3TB_OK;
+}
+
+int EnsureState(m3tb_ctx* ctx) {
+  int lc = 0, pc = 0;
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const BodyDev& B = ctx->h_bodies[b];
+    if (!B.set) continue;
+    if (B.has_region) lc = std::max(lc, B.rp.n_lines_max);
+    if (B.has_depth) pc = std::max(pc, B.dp.n_points_max);
+  }
+  lc = int(Align(size_t(std::max(lc, 1)), 32));
+  pc = int(Align(size_t(std::max(pc, 1)), 32));
+  if (lc > ctx->line_cap || !ctx->d_rstate) {
+    if (ctx->d_rstate) cudaFree(ctx->d_rstate);
+    CU(cudaMalloc(&ctx->d_rstate, size_t(ctx->max_bodies) * RF_COUNT * lc * sizeof(float)));
+    CU(cudaMemsetAsync(ctx->d_rstate, 0, size_t(ctx->max_bodies) * RF_COUNT * lc * sizeof(float), ctx->stream));
+    ctx->line_cap = lc;
+  }
+  if (pc > ctx->point_cap || !ctx->d_dstate) {
+    if (ctx->d_dstate) cudaFree(ctx->d_dstate);
+    CU(cudaMalloc(&ctx->d_dstate, size_t(ctx->max_bodies) * DF_COUNT * pc * sizeof(float)));
+    CU(cudaMemsetAsync(ctx->d_dstate, 0, size_t(ctx->max_bodies) * DF_COUNT * pc * sizeof(float), ctx->stream));
+    ctx->point_cap = pc;
+  }
+  return M3TB_OK;
+}
+
+int SyncTables(m3tb_ctx* ctx) {
+  if (ctx->bodies_dirty) {
+    CU(cudaMemcpyAsync(ctx->d_bodies, ctx->h_bodies.data(), sizeof(BodyDev) * ctx->max_bodies, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ctx->bodies_dirty = false;
+  }
+  if (ctx->cams_dirty) {
+    CU(cudaMemcpyAsync(ctx->d_ccams, ctx->h_ccams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_dcams, ctx->h_dcams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ctx->cams_dirty = false;
+  }
+  if (ctx->models_dirty) {
+    CU(cudaMemcpyAsync(ctx->d_rmodels, ctx->h_rmodels.data(), sizeof(ModelDev) * ctx->max_models, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_dmodels, ctx->h_dmodels.data(), sizeof(ModelDev) * ctx->max_models, cudaMemcpyHostToDevice,
+                       ctx->stream));
+    ctx->models_dirty = false;
+  }
+  return M3TB_OK;
+}
+
+// Checks that every set body references set-up objects ("Set up ... first").
+int ValidateBodies(m3tb_ctx* ctx) {
+  if (ctx->n_bodies == 0) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "no body set");
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const BodyDev& B = ctx->h_bodies[b];
+    if (!B.set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "body " + std::to_string(b) + " not set (bodies must be dense)");
+    if (B.has_region) {
+      if (!ctx->h_rmodels[B.region_model].set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "region model not set");
+      const CameraDev& c = ctx->h_ccams[B.color_camera];
+      if (!c.set || !c.image) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "color camera not set / no image uploaded");
+    }
+    if (B.has_depth) {
+      if (!ctx->h_dmodels[B.depth_model].set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "depth model not set");
+      const CameraDev& c = ctx->h_dcams[B.depth_camera];
+      if (!c.set || !c.image) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "depth camera not set / no image uploaded");
+    }
+  }
+  return M3TB_OK;
+}
+
+int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update, int opt_base,
+                unsigned phases) {
+  int rc = ValidateBodies(ctx);
+  if (rc) return rc;
+  rc = EnsureState(ctx);
+  if (rc) return rc;
+  rc = SyncTables(ctx);
+  if (rc) return rc;
+  TrackArgs a;
+  a.bodies = ctx->d_bodies;
+  a.poses = ctx->d_poses;
+  a.color_cams = ctx->d_ccams;
+  a.depth_cams = ctx->d_dcams;
+  a.region_models = ctx->d_rmodels;
+  a.depth_models = ctx->d_dmodels;
+  a.lut = ctx->d_lut;
+  a.lut_stride = ctx->hist_stride;
+  a.region_state = ctx->d_rstate;
+  a.depth_state = ctx->d_dstate;
+  a.line_cap = ctx->line_cap;
+  a.point_cap = ctx->point_cap;
+  a.counts = ctx->d_counts;
+  a.gh_region = ctx->d_gh_region;
+  a.gh_depth = ctx->d_gh_depth;
+  a.iteration = iteration;
+  a.corr_begin = corr_begin;
+  a.corr_end = corr_end;
+  a.n_update = n_update;
+  a.opt_base = opt_base;
+  a.phases = phases;
+  size_t dyn = (size_t(RF_COUNT) * ctx->line_cap + size_t(DF_COUNT) * ctx->point_cap) * sizeof(float);
+  if (dyn > ctx->max_dyn_smem) {
+    if (dyn > 200 * 1024) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "n_lines_max / n_points_max too large for shared memory");
+    CU(cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));
+    ctx->max_dyn_smem = dyn;
+  }
+  k_track<<<ctx->n_bodies, kBlockThreads, dyn, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return M3TB_OK;
+}
+
+int LaunchHistogram(m3tb_ctx* ctx, int mode) {
+  int rc = ValidateBodies(ctx);
+  if (rc) return rc;
+  rc = SyncTables(ctx);
+  if (rc) return rc;
+  if (!ctx->hist_stride) return M3TB_OK;  // no region modality anywhere
+  HistArgs a;
+  a.bodies = ctx->d_bodies;
+  a.poses = ctx->d_poses;
+  a.color_cams = ctx->d_ccams;
+  a.region_models = ctx->d_rmodels;
+  a.hist_f = ctx->d_hist_f;
+  a.hist_b = ctx->d_hist_b;
+  a.mem_f = ctx->d_mem_f;
+  a.mem_b = ctx->d_mem_b;
+  a.lut = ctx->d_lut;
+  a.stride = ctx->hist_stride;
+  a.mode = mode;
+  k_histogram<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return M3TB_OK;
+}
+
+int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points, const float* orientations,
+             const float* scalars, const void* points) {
+  if (model_id < 0 || model_id >= ctx->max_models || n_views <= 0 || n_points <= 0 || !orientations || !points)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad model arguments");
+  std::vector<ModelAlloc>& allocs = region ? ctx->rmodel_alloc : ctx->dmodel_alloc;
+  ModelAlloc& al = allocs[model_id];
+  if (al.orientations) { cudaFree(al.orientations); cudaFree(al.view_scalars); cudaFree(al.points); al = ModelAlloc(); }
+  // Repack the .bin AoS DataPoints (152 B / 144 B) into the 32 B records the kernels read:
+  // region (cx,cy,cz,nx)(ny,nz,fg,bg), depth (cx,cy,cz,nx)(ny,nz,0,0). One-time setup, not on the hot path.
+  const int fl = region ? M3TB_REGION_POINT_BYTES / 4 : M3TB_DEPTH_POINT_BYTES / 4;
+  const float* src = static_cast<const float*>(points);
+  std::vector<float> packed(size_t(n_views) * n_points * 8);
+  for (size_t k = 0; k < size_t(n_views) * n_points; ++k) {
+    const float* s = src + k * fl;
+    float* d = packed.data() + k * 8;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; d[4] = s[4]; d[5] = s[5];
+    d[6] = region ? s[6] : 0.0f;
+    d[7] = region ? s[7] : 0.0f;
+  }
+  std::vector<float> sc(n_views, 0.0f);
+  float max_scalar = 0.0f;
+  for (int v = 0; v < n_views; ++v) {
+    if (scalars) sc[v] = scalars[v];
+    max_scalar = std::max(max_scalar, sc[v]);
+  }
+  CU(cudaMalloc(&al.orientations, sizeof(float) * 3 * n_views));
+  CU(cudaMalloc(&al.view_scalars, sizeof(float) * n_views));
+  CU(cudaMalloc(&al.points, sizeof(float) * packed.size()));
+  CU(cudaMemcpyAsync(al.orientations, orientations, sizeof(float) * 3 * n_views, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(al.view_scalars, sc.data(), sizeof(float) * n_views, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(al.points, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
+  ModelDev& m = (region ? ctx->h_rmodels : ctx->h_dmodels)[model_id];
+  m.n_views = n_views;
+  m.n_points = n_points;
+  m.orientations = al.orientations;
+  m.view_scalars = al.view_scalars;
+  m.points = al.points;
+  m.max_view_scalar = max_scalar;
+  m.set = 1;
+  ctx->models_dirty = true;
+  return M3TB_OK;
+}
+
+int SetCamera(m3tb_ctx* ctx, bool color, int cam, const m3tb_intrinsics* in, const float* w2c, float depth_scale) {
+  if (cam < 0 || cam >= ctx->max_cameras || !in || !w2c || in->width <= 0 || in->height <= 0)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad camera arguments");
+  CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[cam];
+  const bool dims_changed = c.set && (c.width != in->width || c.height != in->height);
+  c.fu = in->fu; c.fv = in->fv; c.ppu = in->ppu; c.ppv = in->ppv;
+  c.width = in->width; c.height = in->height;
+  std::memcpy(c.w2c, w2c, sizeof(float) * 12);
+  c.depth_scale = depth_scale;
+  if (dims_changed) c.image = nullptr;
+  c.set = 1;
+  ctx->cams_dirty = true;
+  return M3TB_OK;
+}
+
+// Device storage of camera `cam`'s frame: a slot of the shared pool when the dimensions match the
+// pool's (so that a batch of frames is one contiguous copy), a private allocation otherwise.
+int EnsureImage(m3tb_ctx* ctx, bool color, int cam) {
+  CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[cam];
+  if (!c.set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "set the camera before uploading images");
+  if (c.image) return M3TB_OK;
+  ImagePool& pool = color ? ctx->color_pool : ctx->depth_pool;
+  const unsigned pitch = unsigned(Align(size_t(c.width) * (color ? 3 : 2), 16));
+  if (!pool.base) {
+    pool.width = c.width; pool.height = c.height; pool.pitch = pitch;
+    pool.frame_bytes = size_t(pitch) * c.height;
+    pool.capacity = ctx->max_cameras;
+    CU(cudaMalloc(&pool.base, pool.frame_bytes * pool.capacity));
+  }
+  if (pool.width == c.width && pool.height == c.height) {
+    c.image = pool.base + pool.frame_bytes * cam;
+    c.pitch = pool.pitch;
+  } else {
+    uint8_t*& priv = (color ? ctx->private_color : ctx->private_depth)[cam];
+    if (priv) cudaFree(priv);
+    CU(cudaMalloc(&priv, size_t(pitch) * c.height));
+    c.image = priv;
+    c.pitch = pitch;
+  }
+  ctx->cams_dirty = true;
+  return M3TB_OK;
+}
+
+int Upload(m3tb_ctx* ctx, bool color, int cam, const void* src, size_t pitch, cudaMemcpyKind kind) {
+  if (cam < 0 || cam >= ctx->max_cameras || !src) return Fail(ctx, M3TB_ERR_INVALID, "bad upload arguments");
+  int rc = EnsureImage(ctx, color, cam);
+  if (rc) return rc;
+  CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[cam];
+  const size_t row = size_t(c.width) * (color ? 3 : 2);
+  if (pitch < row) return Fail(ctx, M3TB_ERR_INVALID, "pitch smaller than a row");
+  CU(cudaMemcpy2DAsync(const_cast<uint8_t*>(c.image), c.pitch, src, pitch, row, c.height, kind, ctx->stream));
+  return M3TB_OK;
+}
+
+int UploadBatch(m3tb_ctx* ctx, bool color, int first, int count, const void* src, size_t frame_stride, size_t pitch) {
+  if (first < 0 || count <= 0 || first + count > ctx->max_cameras || !src)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad batch upload arguments");
+  ImagePool& pool = color ? ctx->color_pool : ctx->depth_pool;
+  bool pooled = true;
+  for (int k = 0; k < count; ++k) {
+    int rc = EnsureImage(ctx, color, first + k);
+    if (rc) return rc;
+    const CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[first + k];
+    pooled = pooled && pool.base && c.image == pool.base + pool.frame_bytes * (first + k);
+  }
+  const uint8_t* s = static_cast<const uint8_t*>(src);
+  if (pooled && frame_stride == pitch * size_t(pool.height)) {
+    const size_t row = size_t(pool.width) * (color ? 3 : 2);
+    uint8_t* dst = pool.base + pool.frame_bytes * first;
+    if (pitch == pool.pitch) {
+      CU(cudaMemcpyAsync(dst, s, pool.frame_bytes * count, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      CU(cudaMemcpy2DAsync(dst, pool.pitch, s, pitch, row, size_t(pool.height) * count, cudaMemcpyHostToDevice,
+                           ctx->stream));
+    }
+    return M3TB_OK;
+  }
+  for (int k = 0; k < count; ++k) {
+    int rc = Upload(ctx, color, first + k, s + frame_stride * k, pitch, cudaMemcpyHostToDevice);
+    if (rc) return rc;
+  }
+  return M3TB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void m3tb_region_params_default(m3tb_region_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->n_lines_max = 200;
+  p->min_continuous_distance = 3.0f;
+  p->function_length = 8;
+  p->distribution_length = 12;
+  p->function_amplitude = 0.43f;
+  p->function_slope = 0.5f;
+  p->learning_rate = 1.3f;
+  p->n_global_iterations = 1;
+  p->n_scales = 4;
+  const int s[4] = {6, 4, 2, 1};
+  const float sd[4] = {15.0f, 5.0f, 3.5f, 1.5f};
+  for (int i = 0; i < 4; ++i) { p->scales[i] = s[i]; p->standard_deviations[i] = sd[i]; }
+  p->n_standard_deviations = 4;
+  p->n_histogram_bins = 16;
+  p->learning_rate_f = 0.2f;
+  p->learning_rate_b = 0.2f;
+  p->unconsidered_line_length = 0.5f;
+  p->max_considered_line_length = 20.0f;
+  p->measured_depth_offset_radius = 0.01f;
+  p->measured_occlusion_radius = 0.01f;
+  p->measured_occlusion_threshold = 0.03f;
+  p->n_unoccluded_iterations = 10;
+  p->min_n_unoccluded_lines = 0;
+}
+
+void m3tb_depth_params_default(m3tb_depth_params* p) {
+  std::memset(p, 0, sizeof(*p));
+  p->n_points_max = 200;
+  p->stride_length = 0.005f;
+  p->n_considered_distances = 3;
+  const float cd[3] = {0.05f, 0.02f, 0.01f};
+  const float sd[3] = {0.05f, 0.03f, 0.02f};
+  for (int i = 0; i < 3; ++i) { p->considered_distances[i] = cd[i]; p->standard_deviations[i] = sd[i]; }
+  p->n_standard_deviations = 3;
+  p->measured_depth_offset_radius = 0.01f;
+  p->measured_occlusion_radius = 0.01f;
+  p->measured_occlusion_threshold = 0.03f;
+  p->n_unoccluded_iterations = 10;
+  p->min_n_unoccluded_points = 0;
+}
+
+void m3tb_optimizer_params_default(m3tb_optimizer_params* p) {
+  p->tikhonov_parameter_rotation = 1000.0f;
+  p->tikhonov_parameter_translation = 30000.0f;
+}
+
+int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3tb_ctx** out) {
+  if (!out || max_bodies <= 0 || max_cameras <= 0 || max_models <= 0) return M3TB_ERR_INVALID;
+  *out = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || device < 0 || device >= n_dev) return M3TB_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return M3TB_ERR_CUDA;
+  if (prop.major != 10) return M3TB_ERR_CUDA;  // sm_100a cubin only: no other architecture can run it
+  m3tb_ctx* ctx = new m3tb_ctx();
+  ctx->device = device;
+  ctx->max_bodies = max_bodies;
+  ctx->max_cameras = max_cameras;
+  ctx->max_models = max_models;
+  ctx->h_bodies.assign(max_bodies, BodyDev());
+  std::memset(ctx->h_bodies.data(), 0, sizeof(BodyDev) * max_bodies);
+  ctx->h_ccams.assign(max_cameras, CameraDev());
+  ctx->h_dcams.assign(max_cameras, CameraDev());
+  std::memset(ctx->h_ccams.data(), 0, sizeof(CameraDev) * max_cameras);
+  std::memset(ctx->h_dcams.data(), 0, sizeof(CameraDev) * max_cameras);
+  ctx->h_rmodels.assign(max_models, ModelDev());
+  ctx->h_dmodels.assign(max_models, ModelDev());
+  std::memset(ctx->h_rmodels.data(), 0, sizeof(ModelDev) * max_models);
+  std::memset(ctx->h_dmodels.data(), 0, sizeof(ModelDev) * max_models);
+  ctx->rmodel_alloc.assign(max_models, ModelAlloc());
+  ctx->dmodel_alloc.assign(max_models, ModelAlloc());
+  ctx->private_color.assign(max_cameras, nullptr);
+  ctx->private_depth.assign(max_cameras, nullptr);
+  auto alloc = [&]() -> int {
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(&ctx->d_bodies, sizeof(BodyDev) * max_bodies));
+    CU(cudaMalloc(&ctx->d_ccams, sizeof(CameraDev) * max_cameras));
+    CU(cudaMalloc(&ctx->d_dcams, sizeof(CameraDev) * max_cameras));
+    CU(cudaMalloc(&ctx->d_rmodels, sizeof(ModelDev) * max_models));
+    CU(cudaMalloc(&ctx->d_dmodels, sizeof(ModelDev) * max_models));
+    CU(cudaMalloc(&ctx->d_poses, sizeof(float) * 12 * max_bodies));
+    CU(cudaMalloc(&ctx->d_counts, sizeof(int) * 4 * max_bodies));
+    CU(cudaMalloc(&ctx->d_gh_region, sizeof(float) * 27 * max_bodies));
+    CU(cudaMalloc(&ctx->d_gh_depth, sizeof(float) * 27 * max_bodies));
+    CU(cudaMemset(ctx->d_poses, 0, sizeof(float) * 12 * max_bodies));
+    CU(cudaMemset(ctx->d_counts, 0, sizeof(int) * 4 * max_bodies));
+    CU(cudaMemset(ctx->d_gh_region, 0, sizeof(float) * 27 * max_bodies));
+    CU(cudaMemset(ctx->d_gh_depth, 0, sizeof(float) * 27 * max_bodies));
+    return M3TB_OK;
+  };
+  int rc = alloc();
+  if (rc != M3TB_OK) {
+    std::fprintf(stderr, "m3tb_create: %s\n", ctx->err.c_str());
+    m3tb_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return M3TB_OK;
+}
+
+int m3tb_destroy(m3tb_ctx* ctx) {
+  if (!ctx) return M3TB_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto* al : {&ctx->rmodel_alloc, &ctx->dmodel_alloc})
+    for (auto& a : *al) { cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); }
+  for (auto p : ctx->private_color) cudaFree(p);
+  for (auto p : ctx->private_depth) cudaFree(p);
+  cudaFree(ctx->color_pool.base); cudaFree(ctx->depth_pool.base);
+  cudaFree(ctx->d_bodies); cudaFree(ctx->d_ccams); cudaFree(ctx->d_dcams); cudaFree(ctx->d_rmodels);
+  cudaFree(ctx->d_dmodels); cudaFree(ctx->d_poses); cudaFree(ctx->d_counts); cudaFree(ctx->d_gh_region);
+  cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
+  cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
+  delete ctx;
+  return M3TB_OK;
+}
+
+int m3tb_set_stream(m3tb_ctx* ctx, void* cuda_stream) {
+  CHECK_CTX();
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = static_cast<cudaStream_t>(cuda_stream);
+  return M3TB_OK;
+}
+
+int m3tb_synchronize(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
+const char* m3tb_last_error(const m3tb_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t m3tb_launch_count(const m3tb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int m3tb_n_bodies(const m3tb_ctx* ctx) { return ctx ? ctx->n_bodies : 0; }
+
+int m3tb_set_region_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points, const float* orientations,
+                          const float* contour_lengths, const void* points, float, float) {
+  CHECK_CTX();
+  return SetModel(ctx, true, model_id, n_views, n_points, orientations, contour_lengths, points);
+}
+
+int m3tb_set_depth_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points, const float* orientations,
+                         const float* surface_areas, const void* points, float, float) {
+  CHECK_CTX();
+  return SetModel(ctx, false, model_id, n_views, n_points, orientations, surface_areas, points);
+}
+
+int m3tb_set_color_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics, const float world2camera[12]) {
+  CHECK_CTX();
+  return SetCamera(ctx, true, cam, intrinsics, world2camera, 0.0f);
+}
+
+int m3tb_set_depth_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics, const float world2camera[12],
+                          float depth_scale) {
+  CHECK_CTX();
+  if (!(depth_scale > 0.0f)) return Fail(ctx, M3TB_ERR_INVALID, "depth_scale must be positive");
+  return SetCamera(ctx, false, cam, intrinsics, world2camera, depth_scale);
+}
+
+int m3tb_upload_color(m3tb_ctx* ctx, int cam, const uint8_t* bgr, size_t pitch) {
+  CHECK_CTX();
+  return Upload(ctx, true, cam, bgr, pitch, cudaMemcpyHostToDevice);
+}
+int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitch) {
+  CHECK_CTX();
+  return Upload(ctx, false, cam, depth, pitch, cudaMemcpyHostToDevice);
+}
+int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch) {
+  CHECK_CTX();
+  return Upload(ctx, true, cam, dev_bgr, pitch, cudaMemcpyDeviceToDevice);
+}
+int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch) {
+  CHECK_CTX();
+  return Upload(ctx, false, cam, dev_depth, pitch, cudaMemcpyDeviceToDevice);
+}
+int m3tb_upload_color_batch(m3tb_ctx* ctx, int first_cam, int count, const uint8_t* bgr, size_t frame_stride,
+                            size_t pitch) {
+  CHECK_CTX();
+  return UploadBatch(ctx, true, first_cam, count, bgr, frame_stride, pitch);
+}
+int m3tb_upload_depth_batch(m3tb_ctx* ctx, int first_cam, int count, const uint16_t* depth, size_t frame_stride,
+                            size_t pitch) {
+  CHECK_CTX();
+  return UploadBatch(ctx, false, first_cam, count, depth, frame_stride, pitch);
+}
+
+int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, const m3tb_depth_params* depth,
+                  const m3tb_optimizer_params* optimizer, int region_model, int depth_model, int color_camera,
+                  int depth_camera) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->max_bodies) return Fail(ctx, M3TB_ERR_INVALID, "body index out of range");
+  if (!region && !depth) return Fail(ctx, M3TB_ERR_INVALID, "a body needs at least one modality");
+  BodyDev B;
+  std::memset(&B, 0, sizeof(B));
+  B.first_iteration = ctx->h_bodies[body].first_iteration;
+  m3tb_optimizer_params op;
+  m3tb_optimizer_params_default(&op);
+  if (optimizer) op = *optimizer;
+  B.tikhonov_rotation = op.tikhonov_parameter_rotation;
+  B.tikhonov_translation = op.tikhonov_parameter_translation;
+  if (region) {
+    if (region_model < 0 || region_model >= ctx->max_models || color_camera < 0 || color_camera >= ctx->max_cameras)
+      return Fail(ctx, M3TB_ERR_INVALID, "region model / color camera id out of range");
+    if (region->function_length != M3TB_FUNCTION_LENGTH || region->distribution_length != M3TB_DISTRIBUTION_LENGTH)
+      return Fail(ctx, M3TB_ERR_UNSUPPORTED, "function_length / distribution_length other than 8 / 12");
+    if (region->measure_occlusions) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "measure_occlusions (SURVEY f4) not built yet");
+    if (region->n_scales < 1 || region->n_scales > M3TB_MAX_SCHEDULE || region->n_standard_deviations < 1 ||
+        region->n_standard_deviations > M3TB_MAX_SCHEDULE || region->n_lines_max < 1)
+      return Fail(ctx, M3TB_ERR_INVALID, "bad region schedule / n_lines_max");
+    int bs = Bitshift(region->n_histogram_bins);
+    if (bs < 0) return Fail(ctx, M3TB_ERR_INVALID, "n_histogram_bins has to be 2, 4, 8, 16, 32 or 64");
+    RegionParamsDev& r = B.rp;
+    r.n_lines_max = region->n_lines_max;
+    r.use_adaptive_coverage = region->use_adaptive_coverage;
+    r.reference_contour_length = region->reference_contour_length;
+    r.min_continuous_distance = region->min_continuous_distance;
+    r.learning_rate = region->learning_rate;
+    r.n_global_iterations = region->n_global_iterations;
+    r.n_scales = region->n_scales;
+    r.n_standard_deviations = region->n_standard_deviations;
+    for (int i = 0; i < M3TB_MAX_SCHEDULE; ++i) {
+      r.scales[i] = region->scales[i];
+      r.standard_deviations[i] = region->standard_deviations[i];
+    }
+    for (int i = 0; i < r.n_scales; ++i)
+      if (r.scales[i] < 1) return Fail(ctx, M3TB_ERR_INVALID, "scales must be >= 1");
+    r.n_bins = region->n_histogram_bins;
+    r.bitshift = bs;
+    r.learning_rate_f = region->learning_rate_f;
+    r.learning_rate_b = region->learning_rate_b;
+    r.unconsidered_line_length = region->unconsidered_line_length;
+    r.max_considered_line_length = region->max_considered_line_length;
+    // PrecalculateFunctionLookup / PrecalculateDistributionVariables (region_modality.cpp:910-936): host libm,
+    // exactly where the reference evaluates tanh / atanh (SetUp time, not the hot path).
+    for (int i = 0; i < kFunctionLength; ++i) {
+      float x = float(i) - float(kFunctionLength - 1) / 2.0f;
+      if (region->function_slope == 0.0f)
+        r.lookup_f[i] = 0.5f - region->function_amplitude * float((0.0f < x) - (x < 0.0f));
+      else
+        r.lookup_f[i] = 0.5f - region->function_amplitude * std::tanh(x / (2.0f * region->function_slope));
+      r.lookup_b[i] = 1.0f - r.lookup_f[i];
+    }
+    float laplace = 1.0f / (2.0f * powf(atanhf(2.0f * region->function_amplitude), 2.0f));
+    r.min_expected_variance = std::max(laplace, region->function_slope);
+    B.has_region = 1;
+    B.region_model = region_model;
+    B.color_camera = color_camera;
+    const size_t n3 = size_t(r.n_bins) * r.n_bins * r.n_bins;
+    int rc = EnsureHist(ctx, n3);
+    if (rc) return rc;
+    // ColorHistograms::SetUpHistograms (color_histograms.cpp:161-172): uniform histograms
+    std::vector<float> uni(n3, 1.0f / float(n3));
+    std::vector<float2> half(n3, make_float2(0.5f, 0.5f));
+    CU(cudaMemcpyAsync(ctx->d_hist_f + size_t(body) * ctx->hist_stride, uni.data(), n3 * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_hist_b + size_t(body) * ctx->hist_stride, uni.data(), n3 * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_lut + size_t(body) * ctx->hist_stride, half.data(), n3 * sizeof(float2),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (depth) {
+    if (depth_model < 0 || depth_model >= ctx->max_models || depth_camera < 0 || depth_camera >= ctx->max_cameras)
+      return Fail(ctx, M3TB_ERR_INVALID, "depth model / depth camera id out of range");
+    if (depth->measure_occlusions) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "measure_occlusions (SURVEY f4) not built yet");
+    if (depth->n_considered_distances < 1 || depth->n_considered_distances > M3TB_MAX_SCHEDULE ||
+        depth->n_standard_deviations < 1 || depth->n_standard_deviations > M3TB_MAX_SCHEDULE ||
+        depth->n_points_max < 1 || !(depth->stride_length > 0.0f))
+      return Fail(ctx, M3TB_ERR_INVALID, "bad depth schedule / n_points_max / stride_length");
+    DepthParamsDev& d = B.dp;
+    d.n_points_max = depth->n_points_max;
+    d.use_adaptive_coverage = depth->use_adaptive_coverage;
+    d.use_depth_scaling = depth->use_depth_scaling;
+    d.reference_surface_area = depth->reference_surface_area;
+    d.stride_length = depth->stride_length;
+    d.n_considered_distances = depth->n_considered_distances;
+    d.n_standard_deviations = depth->n_standard_deviations;
+    for (int i = 0; i < M3TB_MAX_SCHEDULE; ++i) {
+      d.considered_distances[i] = depth->considered_distances[i];
+      d.standard_deviations[i] = depth->standard_deviations[i];
+    }
+    B.has_depth = 1;
+    B.depth_model = depth_model;
+    B.depth_camera = depth_camera;
+  }
+  B.set = 1;
+  ctx->h_bodies[body] = B;
+  ctx->n_bodies = std::max(ctx->n_bodies, body + 1);
+  ctx->bodies_dirty = true;
+  return M3TB_OK;
+}
+
+int m3tb_set_poses(m3tb_ctx* ctx, int first, int count, const float* body2world) {
+  CHECK_CTX();
+  if (first < 0 || count <= 0 || first + count > ctx->max_bodies || !body2world)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad pose range");
+  CU(cudaMemcpyAsync(ctx->d_poses + 12 * first, body2world, sizeof(float) * 12 * count, cudaMemcpyHostToDevice,
+                     ctx->stream));
+  return M3TB_OK;
+}
+
+int m3tb_get_poses(m3tb_ctx* ctx, int first, int count, float* body2world) {
+  CHECK_CTX();
+  if (first < 0 || count <= 0 || first + count > ctx->max_bodies || !body2world)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad pose range");
+  CU(cudaMemcpyAsync(body2world, ctx->d_poses + 12 * first, sizeof(float) * 12 * count, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
+int m3tb_set_histograms(m3tb_ctx* ctx, int body, const float* histogram_f, const float* histogram_b) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->n_bodies || !ctx->h_bodies[body].has_region || !histogram_f || !histogram_b)
+    return Fail(ctx, M3TB_ERR_INVALID, "body has no region modality");
+  const int nb = ctx->h_bodies[body].rp.n_bins;
+  const int n3 = nb * nb * nb;
+  CU(cudaMemcpyAsync(ctx->d_hist_f + size_t(body) * ctx->hist_stride, histogram_f, n3 * sizeof(float),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_hist_b + size_t(body) * ctx->hist_stride, histogram_b, n3 * sizeof(float),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  dim3 grid((n3 + 255) / 256, 1);
+  k_lut<<<grid, 256, 0, ctx->stream>>>(ctx->d_hist_f, ctx->d_hist_b, ctx->d_lut, n3, ctx->hist_stride, body);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return M3TB_OK;
+}
+
+int m3tb_get_histograms(m3tb_ctx* ctx, int body, float* histogram_f, float* histogram_b) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->n_bodies || !ctx->h_bodies[body].has_region || !histogram_f || !histogram_b)
+    return Fail(ctx, M3TB_ERR_INVALID, "body has no region modality");
+  const int nb = ctx->h_bodies[body].rp.n_bins;
+  const int n3 = nb * nb * nb;
+  CU(cudaMemcpyAsync(histogram_f, ctx->d_hist_f + size_t(body) * ctx->hist_stride, n3 * sizeof(float),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(histogram_b, ctx->d_hist_b + size_t(body) * ctx->hist_stride, n3 * sizeof(float),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
+int m3tb_tracking_step(m3tb_ctx* ctx, int iteration, int n_corr_iterations, int n_update_iterations) {
+  CHECK_CTX();
+  if (n_corr_iterations < 0 || n_update_iterations < 0) return Fail(ctx, M3TB_ERR_INVALID, "negative iteration count");
+  return LaunchTrack(ctx, iteration, 0, n_corr_iterations, n_update_iterations, 0,
+                     PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_SOLVE | PH_STORE_REGION |
+                         PH_STORE_DEPTH);
+}
+
+int m3tb_corr_iteration(m3tb_ctx* ctx, int iteration, int corr_iteration, int n_update_iterations) {
+  CHECK_CTX();
+  if (corr_iteration < 0 || n_update_iterations < 0) return Fail(ctx, M3TB_ERR_INVALID, "negative iteration count");
+  return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, n_update_iterations, 0,
+                     PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_SOLVE | PH_STORE_REGION |
+                         PH_STORE_DEPTH);
+}
+
+int m3tb_start_modalities(m3tb_ctx* ctx, int iteration) {
+  CHECK_CTX();
+  for (int b = 0; b < ctx->n_bodies; ++b) ctx->h_bodies[b].first_iteration = iteration;
+  ctx->bodies_dirty = true;
+  return LaunchHistogram(ctx, 0);
+}
+
+int m3tb_calculate_results(m3tb_ctx* ctx, int iteration) {
+  CHECK_CTX();
+  (void)iteration;
+  return LaunchHistogram(ctx, 1);
+}
+
+int m3tb_region_correspondences(m3tb_ctx* ctx, int iteration, int corr_iteration) {
+  CHECK_CTX();
+  return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 0, 0, PH_REGION_CORR | PH_STORE_REGION);
+}
+
+static int ReadGH(m3tb_ctx* ctx, const float* d_gh, float* gradients, float* hessians) {
+  if (!gradients && !hessians) return M3TB_OK;
+  std::vector<float> h(size_t(27) * ctx->n_bodies);
+  CU(cudaMemcpyAsync(h.data(), d_gh, h.size() * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const float* s = h.data() + 27 * b;
+    if (gradients)
+      for (int i = 0; i < 6; ++i) gradients[6 * b + i] = s[i];
+    if (hessians)
+      for (int i = 0; i < 6; ++i)
+        for (int j = 0; j < 6; ++j) hessians[36 * b + 6 * i + j] = s[6 + (i >= j ? Tri(i, j) : Tri(j, i))];
+  }
+  return M3TB_OK;
+}
+
+int m3tb_region_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration, float* gradients,
+                                 float* hessians) {
+  CHECK_CTX();
+  int rc = LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 1, opt_iteration,
+                       PH_LOAD_REGION | PH_REGION_GH | PH_STORE_GH);
+  if (rc) return rc;
+  return ReadGH(ctx, ctx->d_gh_region, gradients, hessians);
+}
+
+int m3tb_depth_correspondences(m3tb_ctx* ctx, int iteration, int corr_iteration) {
+  CHECK_CTX();
+  return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 0, 0, PH_DEPTH_CORR | PH_STORE_DEPTH);
+}
+
+int m3tb_depth_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration, float* gradients,
+                                float* hessians) {
+  CHECK_CTX();
+  int rc = LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 1, opt_iteration,
+                       PH_LOAD_DEPTH | PH_DEPTH_GH | PH_STORE_GH);
+  if (rc) return rc;
+  return ReadGH(ctx, ctx->d_gh_depth, gradients, hessians);
+}
+
+int m3tb_calculate_optimization(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration) {
+  CHECK_CTX();
+  return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 1, opt_iteration, PH_LOAD_GH | PH_SOLVE);
+}
+
+int m3tb_get_region_lines(m3tb_ctx* ctx, int body, m3tb_region_line* lines, int capacity, int* n_out) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->n_bodies || !lines || !ctx->d_rstate) return Fail(ctx, M3TB_ERR_INVALID, "bad body / no state");
+  int counts[4];
+  CU(cudaMemcpyAsync(counts, ctx->d_counts + 4 * body, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+  const int cap = ctx->line_cap;
+  std::vector<float> st(size_t(RF_COUNT) * cap);
+  CU(cudaMemcpyAsync(st.data(), ctx->d_rstate + size_t(body) * RF_COUNT * cap, st.size() * sizeof(float),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int n = std::min(counts[0], capacity);
+  for (int i = 0; i < n; ++i) {
+    m3tb_region_line& L = lines[i];
+    std::memset(&L, 0, sizeof(L));
+    L.model_index = i;
+    L.valid = st[RF_VALID * cap + i] != 0.0f;
+    L.center_f_body[0] = st[RF_CBX * cap + i]; L.center_f_body[1] = st[RF_CBY * cap + i]; L.center_f_body[2] = st[RF_CBZ * cap + i];
+    L.center_u = st[RF_CU * cap + i]; L.center_v = st[RF_CV * cap + i];
+    L.normal_u = st[RF_NU * cap + i]; L.normal_v = st[RF_NV * cap + i];
+    if (L.valid) {
+      L.delta_r = st[RF_DR * cap + i];
+      L.normal_component_to_scale = st[RF_NCTS * cap + i];
+      for (int d = 0; d < kDistributionLength; ++d) L.distribution[d] = st[(RF_DIST0 + d) * cap + i];
+      L.mean = st[RF_MEAN * cap + i];
+      L.measured_variance = st[RF_VAR * cap + i];
+    }
+  }
+  if (n_out) *n_out = counts[0];
+  return M3TB_OK;
+}
+
+int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int capacity, int* n_out) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->n_bodies || !points || !ctx->d_dstate) return Fail(ctx, M3TB_ERR_INVALID, "bad body / no state");
+  int counts[4];
+  CU(cudaMemcpyAsync(counts, ctx->d_counts + 4 * body, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+  const int cap = ctx->point_cap;
+  std::vector<float> st(size_t(DF_COUNT) * cap);
+  CU(cudaMemcpyAsync(st.data(), ctx->d_dstate + size_t(body) * DF_COUNT * cap, st.size() * sizeof(float),
+                     cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int n = std::min(counts[1], capacity);
+  for (int i = 0; i < n; ++i) {
+    m3tb_depth_point& P = points[i];
+    std::memset(&P, 0, sizeof(P));
+    P.model_index = i;
+    P.valid = st[DF_VALID * cap + i] != 0.0f;
+    P.center_f_body[0] = st[DF_CBX * cap + i]; P.center_f_body[1] = st[DF_CBY * cap + i]; P.center_f_body[2] = st[DF_CBZ * cap + i];
+    P.normal_f_body[0] = st[DF_NX * cap + i]; P.normal_f_body[1] = st[DF_NY * cap + i]; P.normal_f_body[2] = st[DF_NZ * cap + i];
+    if (P.valid) {
+      P.correspondence_center_f_camera[0] = st[DF_YX * cap + i];
+      P.correspondence_center_f_camera[1] = st[DF_YY * cap + i];
+      P.correspondence_center_f_camera[2] = st[DF_YZ * cap + i];
+    }
+  }
+  if (n_out) *n_out = counts[1];
+  return M3TB_OK;
+}
+
+int m3tb_get_closest_views(m3tb_ctx* ctx, int body, int* region_view, int* depth_view) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->n_bodies) return Fail(ctx, M3TB_ERR_INVALID, "bad body");
+  int counts[4];
+  CU(cudaMemcpyAsync(counts, ctx->d_counts + 4 * body, sizeof(counts), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (region_view) *region_view = counts[2];
+  if (depth_view) *depth_view = counts[3];
+  return M3TB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,167 @@
+// m3t_b200_device.cuh — device-side data layout and math of the B200 pose-optimisation path.
+//
+// One CTA owns one body for a whole tracking step (all correspondence iterations x update
+// iterations); warps own groups of correspondence lines / surface points, lanes own lines.
+// Per-line state (RegionModality::DataLine, region_modality.h:150-165) lives in shared memory
+// between CalculateCorrespondences and the n_update gradient passes. All arithmetic is float32
+// with -fmad=false: every operation rounds once, in the order the reference writes it, so that
+// control flow (int truncation, validity tests, branch selection) is bit-identical to a CPU
+// evaluation of the same expressions.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace m3tb {
+
+constexpr int kFunctionLength = 8;       // region_modality.h:415
+constexpr int kDistributionLength = 12;  // region_modality.h:416
+constexpr int kLineSegments = kFunctionLength + kDistributionLength - 1;  // 19, region_modality.cpp:926
+constexpr int kMaxSchedule = 8;
+constexpr int kBlockThreads = 256;
+constexpr int kWarps = kBlockThreads / 32;
+
+// per-line state fields (SoA, [field][line])
+enum RegionField {
+  RF_CBX = 0, RF_CBY, RF_CBZ, RF_CU, RF_CV, RF_NU, RF_NV, RF_DR, RF_NCTS, RF_MEAN, RF_VAR, RF_VALID,
+  RF_DIST0,  // 12 values
+  RF_COUNT = RF_DIST0 + kDistributionLength
+};
+enum DepthField { DF_CBX = 0, DF_CBY, DF_CBZ, DF_NX, DF_NY, DF_NZ, DF_YX, DF_YY, DF_YZ, DF_VALID, DF_COUNT };
+
+// phases of k_track
+enum Phase : unsigned {
+  PH_REGION_CORR = 1u, PH_DEPTH_CORR = 2u, PH_REGION_GH = 4u, PH_DEPTH_GH = 8u, PH_SOLVE = 16u,
+  PH_LOAD_REGION = 32u, PH_LOAD_DEPTH = 64u, PH_STORE_REGION = 128u, PH_STORE_DEPTH = 256u,
+  PH_STORE_GH = 512u, PH_LOAD_GH = 1024u
+};
+
+struct CameraDev {
+  float fu, fv, ppu, ppv;
+  int width, height;
+  float w2c[12];
+  float depth_scale;
+  const uint8_t* image;  // BGR8 or U16
+  unsigned pitch;        // bytes
+  int set;
+};
+
+struct ModelDev {
+  int n_views, n_points;
+  const float* orientations;  // [n_views][3]
+  const float* view_scalars;  // [n_views] contour_length | surface_area
+  const float4* points;       // [n_views][n_points][2]: region (cx,cy,cz,nx)(ny,nz,fg,bg); depth (cx,cy,cz,nx)(ny,nz,0,0)
+  float max_view_scalar;
+  int set;
+};
+
+struct RegionParamsDev {
+  int n_lines_max, use_adaptive_coverage;
+  float reference_contour_length, min_continuous_distance;
+  float learning_rate;
+  int n_global_iterations;
+  int n_scales, scales[kMaxSchedule];
+  int n_standard_deviations;
+  float standard_deviations[kMaxSchedule];
+  int n_bins, bitshift;
+  float learning_rate_f, learning_rate_b, unconsidered_line_length, max_considered_line_length;
+  float lookup_f[kFunctionLength], lookup_b[kFunctionLength];  // PrecalculateFunctionLookup
+  float min_expected_variance;                                  // PrecalculateDistributionVariables
+};
+
+struct DepthParamsDev {
+  int n_points_max, use_adaptive_coverage, use_depth_scaling;
+  float reference_surface_area, stride_length;
+  int n_considered_distances;
+  float considered_distances[kMaxSchedule];
+  int n_standard_deviations;
+  float standard_deviations[kMaxSchedule];
+};
+
+struct BodyDev {
+  int has_region, has_depth;
+  int region_model, depth_model, color_camera, depth_camera;
+  float tikhonov_rotation, tikhonov_translation;
+  int first_iteration;
+  int set;
+  RegionParamsDev rp;
+  DepthParamsDev dp;
+};
+
+struct TrackArgs {
+  const BodyDev* bodies;
+  float* poses;                 // [n_bodies][12] body2world
+  const CameraDev* color_cams;
+  const CameraDev* depth_cams;
+  const ModelDev* region_models;
+  const ModelDev* depth_models;
+  const float2* lut;            // [n_bodies][lut_stride] normalised (pf, pb) per bin
+  size_t lut_stride;
+  float* region_state;          // [n_bodies][RF_COUNT][line_cap]
+  float* depth_state;           // [n_bodies][DF_COUNT][point_cap]
+  int line_cap, point_cap;
+  int* counts;                  // [n_bodies][4]: n_lines, n_points, region_view, depth_view
+  float* gh_region;             // [n_bodies][27]: g[6], H lower [21]
+  float* gh_depth;              // [n_bodies][27]
+  int iteration, corr_begin, corr_end, n_update, opt_base;
+  unsigned phases;
+};
+
+// ---------------------------------------------------------------------------------------------
+// pose helpers: float[12] row-major 3x4, same expressions as the reference's Eigen calls
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void PoseMul(const float* a, const float* b, float* o) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      o[4 * i + j] = a[4 * i + 0] * b[0 + j] + a[4 * i + 1] * b[4 + j] + a[4 * i + 2] * b[8 + j];
+    o[4 * i + 3] = a[4 * i + 0] * b[3] + a[4 * i + 1] * b[7] + a[4 * i + 2] * b[11] + a[4 * i + 3];
+  }
+}
+
+__device__ __forceinline__ void PoseApply(const float* p, float vx, float vy, float vz, float& x, float& y, float& z) {
+  x = p[0] * vx + p[1] * vy + p[2] * vz + p[3];
+  y = p[4] * vx + p[5] * vy + p[6] * vz + p[7];
+  z = p[8] * vx + p[9] * vy + p[10] * vz + p[11];
+}
+
+// Transform3fA::inverse() (Affine): 3x3 cofactor inverse, translation = -inv * t  (depth_modality.cpp:644)
+__device__ __forceinline__ void PoseInverse(const float* p, float* o) {
+  float m[9] = {p[0], p[1], p[2], p[4], p[5], p[6], p[8], p[9], p[10]};
+  float inv[9];
+#define M3TB_COF(i, j) (m[3 * (((i) + 1) % 3) + (((j) + 1) % 3)] * m[3 * (((i) + 2) % 3) + (((j) + 2) % 3)] - \
+                        m[3 * (((i) + 1) % 3) + (((j) + 2) % 3)] * m[3 * (((i) + 2) % 3) + (((j) + 1) % 3)])
+  float c00 = M3TB_COF(0, 0), c10 = M3TB_COF(1, 0), c20 = M3TB_COF(2, 0);
+  float det = c00 * m[0] + c10 * m[3] + c20 * m[6];
+  float invdet = 1.0f / det;
+  inv[0] = c00 * invdet; inv[1] = c10 * invdet; inv[2] = c20 * invdet;
+  inv[3] = M3TB_COF(0, 1) * invdet; inv[4] = M3TB_COF(1, 1) * invdet; inv[5] = M3TB_COF(2, 1) * invdet;
+  inv[6] = M3TB_COF(0, 2) * invdet; inv[7] = M3TB_COF(1, 2) * invdet; inv[8] = M3TB_COF(2, 2) * invdet;
+#undef M3TB_COF
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    o[4 * i + 0] = inv[3 * i + 0]; o[4 * i + 1] = inv[3 * i + 1]; o[4 * i + 2] = inv[3 * i + 2];
+    o[4 * i + 3] = (-inv[3 * i + 0]) * p[3] + (-inv[3 * i + 1]) * p[7] + (-inv[3 * i + 2]) * p[11];
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T LastValid(const T* v, int n, int idx) {  // common.h:170-176
+  return idx < n ? v[idx] : v[n - 1];
+}
+
+__device__ __forceinline__ int AdaptiveCount(int n_max, int use_adaptive, float reference, float view_scalar,
+                                             float max_scalar, int n_model) {
+  int n = n_max;  // region_modality.cpp:414-430, depth_modality.cpp:281-293
+  if (use_adaptive) {
+    if (reference > 0.0f)
+      n = int(float(n_max) * fminf(1.0f, view_scalar / reference));
+    else
+      n = int(float(n_max) * view_scalar / max_scalar);
+  }
+  if (n > n_model) n = n_model;
+  return n;
+}
+
+}  // namespace m3tb

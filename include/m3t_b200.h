@@ -180,6 +180,14 @@ int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitc
 int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch);
 int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch);
 
+/* Loader-style batch ingest: `count` frames for cameras [first_cam, first_cam+count), frame k at
+ * base + k*frame_stride bytes. Cameras of equal size share one device pool, so this is a single
+ * host->device copy when the host frames are contiguous (frame_stride == height*pitch). */
+int m3tb_upload_color_batch(m3tb_ctx* ctx, int first_cam, int count, const uint8_t* bgr,
+                            size_t frame_stride, size_t pitch);
+int m3tb_upload_depth_batch(m3tb_ctx* ctx, int first_cam, int count, const uint16_t* depth,
+                            size_t frame_stride, size_t pitch);
+
 /* ---- bodies: one rigid body = Body + RegionModality and/or DepthModality + root Link + Optimizer.
  * region == NULL / depth == NULL leaves that modality out (model / camera id then ignored).
  * Equivalent of constructing the objects and calling their SetUp() (region_modality.cpp:37-77,

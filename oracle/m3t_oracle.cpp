@@ -1055,9 +1055,9 @@ void orc_calculate_results(orc_body* bodies, int n_bodies, int iteration, int ro
 }
 
 // Tracker::ExecuteTrackingStep (tracker.cpp:344-361) for one body (= one optimizer with a root link).
-static void StepOne(orc_body* b, int iteration, int n_corr, int n_update, int rotation_mode, int exp_mode,
-                    double* phase) {
-  for (int corr = 0; corr < n_corr; ++corr) {
+static void StepOne(orc_body* b, int iteration, int corr_begin, int corr_end, int n_update, int rotation_mode,
+                    int exp_mode, double* phase) {
+  for (int corr = corr_begin; corr < corr_end; ++corr) {
     double t0 = Now();
     if (b->region)
       b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, nullptr, b->histogram_f,
@@ -1092,13 +1092,13 @@ static void StepOne(orc_body* b, int iteration, int n_corr, int n_update, int ro
   }
 }
 
-void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int n_corr, int n_update, int rotation_mode,
-                       int exp_mode, int n_threads, double* phase_seconds) {
+void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int corr_begin, int corr_end, int n_update,
+                       int rotation_mode, int exp_mode, int n_threads, double* phase_seconds) {
   double p0 = 0, p1 = 0, p2 = 0;
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1) reduction(+ : p0, p1, p2)
   for (int i = 0; i < n_bodies; ++i) {
     double phase[3] = {0, 0, 0};
-    StepOne(&bodies[i], iteration, n_corr, n_update, rotation_mode, exp_mode, phase);
+    StepOne(&bodies[i], iteration, corr_begin, corr_end, n_update, rotation_mode, exp_mode, phase);
     p0 += phase[0]; p1 += phase[1]; p2 += phase[2];
   }
   if (phase_seconds) {

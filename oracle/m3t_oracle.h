@@ -220,7 +220,7 @@ int orc_optimize_rigid(const float g[6], const float H[36], float tikhonov_rotat
 void orc_start_modalities(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads);
 /* phase_seconds[4] (may be NULL): correspondences / gradient+hessian / optimisation / results,
  * summed over threads, like examples/rbot_evaluator.cpp:354-414. */
-void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int n_corr_iterations,
+void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int corr_begin, int corr_end,
                        int n_update_iterations, int rotation_mode, int exp_mode, int n_threads,
                        double* phase_seconds);
 void orc_calculate_results(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads);

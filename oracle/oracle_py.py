@@ -147,7 +147,7 @@ def lib(native=False):
     L.orc_optimize_rigid.restype = C.c_int
     L.orc_start_modalities.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_tracking_step.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                    C.POINTER(C.c_double)]
+                                    C.c_int, C.POINTER(C.c_double)]
     L.orc_calculate_results.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_max_threads.restype = C.c_int
     _libs[key] = L
@@ -273,16 +273,17 @@ class OracleTracker:
     def start_modalities(self, iteration=0):
         self.L.orc_start_modalities(self.bodies, self.wl.n_bodies, iteration, self.rotation_mode, self.n_threads)
 
-    def tracking_step(self, iteration=0, n_corr=None, n_update=None, first=None, count=None):
-        """Runs bodies [first, first+count). Returns the 3 phase times (s, summed over threads)."""
+    def tracking_step(self, iteration=0, n_corr=None, n_update=None, first=None, count=None, corr_begin=0):
+        """Runs corr iterations [corr_begin, n_corr) for bodies [first, first+count).
+        Returns the 3 phase times (s, summed over threads)."""
         n_corr = self.wl.n_corr_iterations if n_corr is None else n_corr
         n_update = self.wl.n_update_iterations if n_update is None else n_update
         first = 0 if first is None else first
         count = self.wl.n_bodies - first if count is None else count
         phases = (C.c_double * 4)()
         base = C.cast(C.byref(self.bodies, first * C.sizeof(Body)), C.POINTER(Body))
-        self.L.orc_tracking_step(base, count, iteration, n_corr, n_update, self.rotation_mode, self.exp_mode,
-                                 self.n_threads, phases)
+        self.L.orc_tracking_step(base, count, iteration, corr_begin, n_corr, n_update, self.rotation_mode,
+                                 self.exp_mode, self.n_threads, phases)
         return list(phases)
 
     def calculate_results(self, iteration=0):

@@ -1,0 +1,168 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star / SURVEY §8c):
+  * per-line / per-point state: bit-exact (integer control flow AND float payload) against the oracle in
+    ROTATION_LINEAR mode (same expressions, -fmad=false vs -ffp-contract=off);
+  * gradient / Hessian: <= 1e-5 of max|H| (summation order differs: warp tree vs serial);
+  * pose after every correspondence iteration: <= 1e-4 rad and <= 1e-4 m against the reference-faithful oracle
+    (polar rotation(), Pade exp).
+"""
+import numpy as np
+import pytest
+
+from helpers import assert_lines_bit_equal, assert_points_bit_equal, pose_error, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+TOL_POSE_M = 1e-4
+TOL_POSE_RAD = 1e-4
+
+
+@pytest.fixture(scope="module")
+def wl_c2(synth):
+    return synth.make_workload("c2", n_bodies=4, n_divides=4, seed=3)
+
+
+@pytest.fixture(scope="module")
+def wl_c3(synth):
+    return synth.make_workload("c3", n_bodies=6, n_divides=4, seed=5)
+
+
+def _setup(capi, oracle, wl, rotation_mode, exp_mode):
+    ctx = capi.context_from_workload(wl)
+    orc = oracle.OracleTracker(wl, rotation_mode=rotation_mode, exp_mode=exp_mode)
+    return ctx, orc
+
+
+def test_histograms_start_and_update_exact(capi, oracle, wl_c2):
+    """StartModality / CalculateResults histogram side: counts are integers, blend is two roundings -> exact."""
+    ctx, orc = _setup(capi, oracle, wl_c2, oracle.ROTATION_LINEAR, oracle.EXP_RODRIGUES)
+    orc.start_modalities(0)
+    ctx.start_modalities(0)
+    nb = wl_c2.region.n_histogram_bins
+    for b in range(wl_c2.n_bodies):
+        hf, hb = ctx.get_histograms(b, nb)
+        assert np.array_equal(hf.view(np.uint32), orc.hist_f[b].view(np.uint32))
+        assert np.array_equal(hb.view(np.uint32), orc.hist_b[b].view(np.uint32))
+        assert hf.sum() > 0.99 and hb.sum() > 0.99
+    orc.calculate_results(0)
+    ctx.calculate_results(0)
+    for b in range(wl_c2.n_bodies):
+        hf, hb = ctx.get_histograms(b, nb)
+        assert np.array_equal(hf.view(np.uint32), orc.hist_f[b].view(np.uint32))
+        assert np.array_equal(hb.view(np.uint32), orc.hist_b[b].view(np.uint32))
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_fine_grained_calls_match_oracle(capi, oracle, wl_c2, wl_c3, which):
+    """Modality-level API, call by call, for every corr / update iteration of one tracking step."""
+    wl = wl_c2 if which == "c2" else wl_c3
+    ctx, orc = _setup(capi, oracle, wl, oracle.ROTATION_LINEAR, oracle.EXP_RODRIGUES)
+    orc.start_modalities(0)
+    for b in range(wl.n_bodies):
+        ctx.set_histograms(b, orc.hist_f[b], orc.hist_b[b])
+    nl, npnt = wl.lines_per_body, wl.points_per_body
+    for corr in range(wl.n_corr_iterations):
+        # both sides start the iteration from the same poses (the oracle's)
+        ctx.set_poses(orc.get_poses())
+        if wl.region:
+            ctx.region_correspondences(0, corr)
+        if wl.depth:
+            ctx.depth_correspondences(0, corr)
+        for b in range(wl.n_bodies):
+            if wl.region:
+                n, view = orc.region_correspondences(b, 0, corr)
+                assert ctx.get_closest_views(b)[0] == view
+                assert_lines_bit_equal(ctx.get_region_lines(b, nl), orc.lines[b][:n])
+            if wl.depth:
+                n, view = orc.depth_correspondences(b, 0, corr)
+                assert ctx.get_closest_views(b)[1] == view
+                assert_points_bit_equal(ctx.get_depth_points(b, npnt), orc.points[b][:n])
+        for upd in range(wl.n_update_iterations):
+            ctx.set_poses(orc.get_poses())
+            g_r = H_r = g_d = H_d = None
+            if wl.region:
+                g_r, H_r = ctx.region_gradient_hessian(0, corr, upd)
+            if wl.depth:
+                g_d, H_d = ctx.depth_gradient_hessian(0, corr, upd)
+            ctx.calculate_optimization(0, corr, upd)
+            gpu_poses = ctx.get_poses()
+            for b in range(wl.n_bodies):
+                g = np.zeros(6, np.float32)
+                H = np.zeros((6, 6), np.float32)
+                if wl.region:
+                    og, oH = orc.region_gradient_hessian(b, corr, upd)
+                    assert rel_to_max(H_r[b], oH) < 1e-5 and rel_to_max(g_r[b], og) < 1e-4
+                    assert np.array_equal(H_r[b], H_r[b].T)
+                    g, H = g + og, H + oH
+                if wl.depth:
+                    og, oH = orc.depth_gradient_hessian(b, corr)
+                    assert rel_to_max(H_d[b], oH) < 1e-5 and rel_to_max(g_d[b], og) < 1e-4
+                    g, H = g + og, H + oH
+                ok, theta = orc.optimize(b, g, H)
+                assert ok
+            dt, dr = pose_error(gpu_poses, orc.get_poses())
+            assert dt.max() < 1e-5 and dr.max() < 1e-5, (corr, upd, dt.max(), dr.max())  # logf ulp differences in local mode
+    ctx.close()
+
+
+@pytest.mark.parametrize("which", ["c2", "c3"])
+def test_tracking_step_pose_parity_per_iteration(capi, oracle, wl_c2, wl_c3, which):
+    """The contract gate: pose after every correspondence iteration within 1e-4 rad / 1e-4 m of the
+    reference-faithful oracle, both sides free-running from the same start (no re-synchronisation)."""
+    wl = wl_c2 if which == "c2" else wl_c3
+    ctx, orc = _setup(capi, oracle, wl, oracle.ROTATION_POLAR, oracle.EXP_PADE)
+    orc.start_modalities(0)
+    ctx.start_modalities(0)
+    for corr in range(wl.n_corr_iterations):
+        ctx.corr_iteration(0, corr, wl.n_update_iterations)
+        orc.tracking_step(0, n_corr=corr + 1, corr_begin=corr)
+        dt, dr = pose_error(ctx.get_poses(), orc.get_poses())
+        assert dt.max() < TOL_POSE_M and dr.max() < TOL_POSE_RAD, (corr, dt, dr)
+    ctx.close()
+
+
+def test_fused_step_equals_iteration_by_iteration(capi, oracle, wl_c2):
+    """m3tb_tracking_step (one launch) == 7 x m3tb_corr_iteration, bit for bit; and it moves towards ground truth."""
+    ctx_a = capi.context_from_workload(wl_c2)
+    ctx_b = capi.context_from_workload(wl_c2)
+    for c in (ctx_a, ctx_b):
+        c.start_modalities(0)
+    ctx_a.tracking_step(0, wl_c2.n_corr_iterations, wl_c2.n_update_iterations)
+    for corr in range(wl_c2.n_corr_iterations):
+        ctx_b.corr_iteration(0, corr, wl_c2.n_update_iterations)
+    pa, pb = ctx_a.get_poses(), ctx_b.get_poses()
+    assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32))
+    dt0, dr0 = pose_error(wl_c2.start_body2world, wl_c2.gt_body2world)
+    dt1, dr1 = pose_error(pa, wl_c2.gt_body2world)
+    assert (dt1 < dt0).all() and (dr1 < dr0).all(), (dt0, dt1, dr0, dr1)
+    ctx_a.close()
+    ctx_b.close()
+
+
+def test_full_cycle_two_frames(capi, oracle, wl_c2):
+    """StartModalities + 2 x (tracking step + CalculateResults): poses within tolerance of the oracle."""
+    ctx, orc = _setup(capi, oracle, wl_c2, oracle.ROTATION_POLAR, oracle.EXP_PADE)
+    orc.start_modalities(0)
+    ctx.start_modalities(0)
+    for it in range(2):
+        ctx.tracking_step(it, wl_c2.n_corr_iterations, wl_c2.n_update_iterations)
+        ctx.calculate_results(it)
+        orc.tracking_step(it)
+        orc.calculate_results(it)
+        dt, dr = pose_error(ctx.get_poses(), orc.get_poses())
+        assert dt.max() < TOL_POSE_M and dr.max() < TOL_POSE_RAD, (it, dt, dr)
+    ctx.close()
+
+
+def test_errors_are_loud(capi):
+    """No silent fallbacks: bad use returns an error status with a message."""
+    ctx = capi.Context(0, 2, 2, 1)
+    with pytest.raises(capi.M3TBError):
+        ctx.tracking_step(0, 1, 1)  # nothing set up
+    rp = capi.region_params()
+    rp.function_length = 6
+    with pytest.raises(capi.M3TBError):
+        ctx.set_body(0, rp, None, None)
+    ctx.close()
