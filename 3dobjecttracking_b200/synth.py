@@ -240,8 +240,12 @@ def _rot(axis, deg):
 
 
 def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divides=4, seed=0, rot_deg=3.0,
-                  trans_m=0.005, rbot=None, model_points=None, frames=True, color_sigma=10.0) -> Workload:
-    """Build one of the BASELINE.json workloads (optionally resized) from (seed, body index)."""
+                  trans_m=0.005, rbot=None, model_points=None, frames=True, color_sigma=10.0, first_body=0,
+                  models=None) -> Workload:
+    """Build one of the BASELINE.json workloads (optionally resized) from (seed, global body index).
+
+    first_body: global index of this shard's first body (multi-GPU sharding: rank r of a weak-scaled job
+    builds bodies [r*n_bodies, (r+1)*n_bodies)). models: optional (region_model, depth_model) to reuse."""
     preset = dict(PRESETS[name])
     if n_bodies is not None:
         preset["n_bodies"] = n_bodies
@@ -278,8 +282,11 @@ def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divid
 
     mp_r = model_points or max(preset["n_lines"], 1)
     mp_d = model_points or max(preset["n_points"], 1)
-    region_model = generate_region_model(n_divides, mp_r, 0.8, seed) if region else None
-    depth_model = generate_depth_model(n_divides, mp_d, 0.8, seed) if depth else None
+    if models is not None:
+        region_model, depth_model = models
+    else:
+        region_model = generate_region_model(n_divides, mp_r, 0.8, seed) if region else None
+        depth_model = generate_depth_model(n_divides, mp_d, 0.8, seed) if depth else None
 
     max_scale = max(region.scales) if region else 0
     margin = 19 * max_scale / 2 + 75.0  # longest line half-length + body radius in px (+ slack for the depth camera)
@@ -289,18 +296,20 @@ def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divid
     color = np.zeros((nb, ci.height, pitch), np.uint8) if (region and frames) else None
     dframes = np.zeros((nb, di.height, di.width), np.uint16) if (depth and frames) else None
     for b in range(nb):
-        b2c = ground_truth_pose(seed, b, ci, margin, 0.5, 0.7)
+        gb = first_body + b  # global body index: the only thing (besides seed) a body's data depends on
+        b2c = ground_truth_pose(seed, gb, ci, margin, 0.5, 0.7)
         b2w = pose_mul(c_c2w, b2c)
         gt[b] = b2w
-        start[b] = perturb_pose(seed, b, rot_deg, trans_m, b2w)
+        start[b] = perturb_pose(seed, gb, rot_deg, trans_m, b2w)
         if color is not None:
-            render_color(ci, pose_mul(c_w2c, b2w), seed * 1000003 + b, sigma=color_sigma, out=color[b])
+            render_color(ci, pose_mul(c_w2c, b2w), seed * 1000003 + gb, sigma=color_sigma, out=color[b])
         if dframes is not None:
-            render_depth(di, pose_mul(d_w2c, b2w), seed * 1000003 + b, depth_scale=0.001, out=dframes[b])
+            render_depth(di, pose_mul(d_w2c, b2w), seed * 1000003 + gb, depth_scale=0.001, out=dframes[b])
     lam = (1000.0, 30000.0)  # optimizer.h:52-53
     return Workload(name=name, n_bodies=nb, region=region, depth=depth, tikhonov_rotation=lam[0],
                     tikhonov_translation=lam[1], n_corr_iterations=7, n_update_iterations=2,
                     color_intrinsics=ci, depth_intrinsics=di, color_world2camera=c_w2c, depth_world2camera=d_w2c,
                     depth_scale=0.001, region_model=region_model, depth_model=depth_model, color_frames=color,
                     depth_frames=dframes, gt_body2world=gt, start_body2world=start, seed=seed,
-                    notes=dict(n_divides=n_divides, rot_deg=rot_deg, trans_m=trans_m, rbot=rb, color_sigma=color_sigma))
+                    notes=dict(n_divides=n_divides, rot_deg=rot_deg, trans_m=trans_m, rbot=rb, color_sigma=color_sigma,
+                               first_body=first_body))

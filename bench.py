@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — pose-opt iterations/s (bodies x corr_iters) of the M3T pose-optimisation hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                      (the CPU arm: the oracle port on the host cores)
+
+A "step" is one Tracker::ExecuteTrackingStep pass (n_corr correspondence iterations x n_update update
+iterations, tracker.cpp:344-361) over this GPU's batch of bodies = ONE launch of the fused kernel k_track.
+Default workload: the per-GPU shard of BASELINE.json configs[3] ("1024 bodies Region+Depth, 512 lines each,
+640x480 RGB-D, sharded 8xB200" -> 128 bodies per GPU, weak scaling), the configuration the metric's
+1/2/4/8-GPU numbers are quoted on; `--workload c2|c3` selects the other configs.
+
+value : whole-job throughput, frames already resident in HBM, timed with CUDA events around each step on the
+        launching stream, L2 flushed between steps (untimed), max over ranks.
+e2e   : the same through the C ABI with HOST buffers: per step the pinned-host -> device copy of every body's
+        RGB-D frame + start poses, the step, the device -> host read of the solved poses (+ the pose all-gather
+        at N>1); wall clock around synchronised regions, max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pose-opt iterations/sec (bodies x corr_iters)"
+UNIT = "pose-opt iterations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4"])
+    ap.add_argument("--bodies", type=int, default=None, help="bodies per GPU (default: the preset's)")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_description(wl, args, per_gpu=None):
+    r = f"{wl.lines_per_body} lines" if wl.region else ""
+    d = f"{wl.points_per_body} depth points" if wl.depth else ""
+    both = " + ".join(x for x in (r, d) if x)
+    preset = {"c2": "configs[1]", "c3": "configs[2]", "c4": "configs[3] per-GPU shard (1024 bodies / 8 GPUs)"}[args.workload]
+    return (f"{preset}: {per_gpu or wl.n_bodies} bodies/GPU x ({both}), one 640x480 "
+            f"{'RGB-D pair' if wl.depth and wl.region else 'frame'} per body, "
+            f"{wl.n_corr_iterations} corr x {wl.n_update_iterations} update iterations")
+
+
+def build_workload(args, rank, n_shards=1):
+    """Bodies [rank*nb, (rank+n_shards)*nb) of the weak-scaled job (nb bodies per GPU)."""
+    pkg = importlib.import_module("3dobjecttracking_b200")
+    nb = args.bodies or pkg.synth.PRESETS[args.workload]["n_bodies"]
+    wl = pkg.synth.make_workload(args.workload, n_bodies=nb * n_shards, n_divides=4, seed=args.seed,
+                                 first_body=rank * nb)
+    return pkg, wl
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+_THREADS = {}
+
+
+def calibrate_threads(oracle_py, wl):
+    """"All the host threads it can use": the OpenMP thread count that is fastest on this box among
+    {affinity mask size, half of it (physical cores), cgroup CPU quota}; oversubscribing a cgroup-limited
+    container makes the CPU arm slower, which would flatter the GPU arm."""
+    if "n" in _THREADS:
+        return _THREADS["n"]
+    cands = set()
+    try:
+        n_aff = len(os.sched_getaffinity(0))
+    except Exception:
+        n_aff = os.cpu_count() or 1
+    cands.update({n_aff, max(1, n_aff // 2)})
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            cands.add(max(1, int(float(q) / float(p))))
+    except Exception:
+        pass
+    cands.add(oracle_py.lib(native=True).orc_max_threads())
+    cands = sorted(c for c in cands if c >= 1)
+    best, best_t = cands[0], None
+    for c in cands:
+        if c > max(1, wl.n_bodies):
+            continue
+        trk = oracle_py.OracleTracker(wl, n_threads=c, native=True)
+        trk.tracking_step(0)  # warm-up (thread pool)
+        trk.set_poses(wl.start_body2world)
+        t0 = time.perf_counter()
+        trk.tracking_step(0)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = c, dt
+    _THREADS["n"] = best
+    return best
+
+
+def cpu_reference_run(args, wl, steps, warmup, threads=None):
+    """Times the oracle port (the reference's CPU algorithm; -O3 -march=native like M3T/CMakeLists.txt) on
+    the host cores, OpenMP over bodies (how the reference parallelises independent runs,
+    examples/rbot_evaluator.cpp:144). One step = the same full-batch tracking step the GPU arm times."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    if threads is None:
+        threads = calibrate_threads(oracle_py, wl)
+    trk = oracle_py.OracleTracker(wl, rotation_mode=oracle_py.ROTATION_POLAR, exp_mode=oracle_py.EXP_PADE,
+                                  n_threads=threads, native=True)
+    trk.start_modalities(0)
+    phases = np.zeros(3)
+    for _ in range(warmup):
+        trk.set_poses(wl.start_body2world)
+        trk.tracking_step(0)
+    t_total = 0.0
+    for _ in range(steps):
+        trk.set_poses(wl.start_body2world)
+        t0 = time.perf_counter()
+        ph = trk.tracking_step(0)
+        t_total += time.perf_counter() - t0
+        phases += np.array(ph[:3])
+    its = wl.n_bodies * wl.n_corr_iterations * steps
+    return {"value": its / t_total, "ms_per_step": 1e3 * t_total / steps, "cores": int(threads),
+            "phase_split_cpu_seconds": {"correspondences": phases[0], "gradient_hessian": phases[1],
+                                        "optimization": phases[2]}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # under torchrun only rank 0 runs the CPU arm
+    pkg, wl = build_workload(args, 0, n_shards=args.gpus)  # the whole N-GPU job on this host's cores
+    r = cpu_reference_run(args, wl, args.steps, args.warmup)
+    total_b, *_ = pkg.roofline.algorithmic_bytes_per_step(wl)
+    sample = f"{args.steps} full steps of the workload ({wl.n_bodies} bodies x {wl.n_corr_iterations} corr iterations each)"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_description(wl, args, per_gpu=wl.n_bodies // args.gpus),
+                   "note": f"CPU arm: the whole {args.gpus}-GPU job ({wl.n_bodies} bodies) on this host's cores, OpenMP over bodies"},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
+                         "phase_split_cpu_seconds": r["phase_split_cpu_seconds"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+
+    pkg, wl = build_workload(args, rank)
+    capi = importlib.import_module("3dobjecttracking_b200.capi")
+    stream = torch.cuda.current_stream(dev)
+    ctx = capi.context_from_workload(wl, device=local_rank, stream=stream.cuda_stream)
+    ctx.start_modalities(0)  # histogram initialisation (once; not part of the timed step)
+    ctx.synchronize()
+
+    nb, n_corr, n_upd = wl.n_bodies, wl.n_corr_iterations, wl.n_update_iterations
+    its_per_step = nb * n_corr
+    start_poses = torch.from_numpy(np.ascontiguousarray(wl.start_body2world.reshape(nb, 12))).pin_memory()
+    poses_np = start_poses.numpy()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step():
+        ctx.tracking_step(0, n_corr, n_upd)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # ---------------- value: device-resident frames, CUDA events per step, L2 flushed between steps --------
+    for _ in range(max(args.warmup, 3)):
+        ctx.set_poses(poses_np)
+        step()
+    torch.cuda.synchronize(dev)
+    barrier()
+    launches0 = ctx.launch_count
+    evs = []
+    for _ in range(args.steps):
+        flush.zero_()
+        ctx.set_poses(poses_np)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    torch.cuda.synchronize(dev)
+    launches = ctx.launch_count - launches0
+    barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * its_per_step / (ms_per_step * 1e-3)
+
+    # ---------------- e2e: host buffers through the C ABI ------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        h_color = h_depth = None
+        h2d = nb * 48
+        if wl.region:
+            h_color = torch.from_numpy(wl.color_frames).pin_memory()
+            h2d += h_color.numel()
+        if wl.depth:
+            h_depth = torch.from_numpy(wl.depth_frames.view(np.uint8).reshape(nb, wl.depth_frames.shape[1], -1)).pin_memory()
+            h2d += h_depth.numel()
+        d2h = nb * 48
+        out_poses = torch.empty((nb, 12), dtype=torch.float32).pin_memory()
+        gathered = None
+
+        def e2e_step():
+            nonlocal gathered
+            if h_color is not None:
+                ctx.upload_batch_ptr(True, 0, nb, h_color.data_ptr(), h_color.stride(0), h_color.stride(1))
+            if h_depth is not None:
+                ctx.upload_batch_ptr(False, 0, nb, h_depth.data_ptr(), h_depth.stride(0), h_depth.stride(1))
+            ctx.set_poses(poses_np)
+            step()
+            ctx._ck(ctx.L.m3tb_get_poses(ctx.h, 0, nb, capi._p(out_poses.numpy())))  # synchronises the stream
+            if world > 1:  # publish: NCCL all-gather of the solved poses, once per frame
+                gathered = pkg.sharding.all_gather_poses(out_poses.to(dev, non_blocking=True).reshape(nb, 3, 4))
+
+        for _ in range(max(args.warmup, 3)):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize(dev)
+        t1 = time.perf_counter()
+        barrier()
+        t = torch.tensor([t1 - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item()) / args.steps
+        e2e = {"value": world * its_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s}
+
+    # ---------------- clocks: keep the GPU under the same load for a while so nvidia-smi sees it ----------------
+    t_end = time.perf_counter() + 1.5
+    while time.perf_counter() < t_end:
+        for _ in range(50):
+            step()
+        torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    clocks["note"] = "sampled every 100 ms from before the timed region to the end of a 1.5 s repeat of the timed step"
+
+    if rank == 0:
+        total_b, region_b, depth_b, line_evals, point_evals = pkg.roofline.algorithmic_bytes_per_step(wl)
+        peak, peak_src = measured_peak_gbs()
+        kernel_s = ms_per_step * 1e-3  # one k_track launch per step; events bracket exactly that launch
+        achieved = total_b / kernel_s / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload if not args.bodies else f"{args.workload}-{args.bodies}")
+        except Exception:
+            pass
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_description(wl, args), "bodies_per_gpu": nb,
+                       "l2": "flushed (256 MiB memset) between timed steps; each step's frames are 189 MiB/GPU (> L2)",
+                       "timing": "CUDA events around each step on the launching stream, summed over K steps, max over ranks",
+                       "parallelism": f"bodies sharded x{world}, no data-path collective"},
+            "line_evals_per_s": world * line_evals / kernel_s,
+            "depth_point_evals_per_s": world * point_evals / kernel_s,
+            "roofline": {"bound": "hbm", "kernel": "k_track", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": total_b, "region_bytes": region_b, "depth_bytes": depth_b,
+                         "launch_ms": ms_per_step},
+            "clocks": clocks, "gpu_launches": int(launches),
+        }
+        if e2e:
+            out["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args, wl, steps=3, warmup=1)
+            r1 = cpu_reference_run(args, wl, steps=1, warmup=0, threads=1)
+            out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                   "sample": f"3 full steps of the same workload ({nb} bodies x {n_corr} corr iterations), OpenMP over bodies",
+                                   "single_thread_value": r1["value"],
+                                   "phase_split_cpu_seconds": r["phase_split_cpu_seconds"]}
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()
