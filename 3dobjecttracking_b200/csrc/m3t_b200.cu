@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -59,6 +60,7 @@ struct m3tb_ctx {
   int* d_counts = nullptr;
   float *d_gh_region = nullptr, *d_gh_depth = nullptr;
   size_t max_dyn_smem = 0;
+  bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
 };
 
 namespace {
@@ -222,13 +224,31 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   a.n_update = n_update;
   a.opt_base = opt_base;
   a.phases = phases;
-  size_t dyn = (size_t(RF_COUNT) * ctx->line_cap + size_t(DF_COUNT) * ctx->point_cap) * sizeof(float);
-  if (dyn > ctx->max_dyn_smem) {
-    if (dyn > 200 * 1024) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "n_lines_max / n_points_max too large for shared memory");
-    CU(cudaFuncSetAttribute(k_track, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));
-    ctx->max_dyn_smem = dyn;
-  }
-  k_track<<<ctx->n_bodies, kBlockThreads, dyn, ctx->stream>>>(a);
+  // thread <-> line mapping: T threads per body, K lines and K points per thread (state in registers)
+  const int items = std::max(ctx->line_cap, ctx->point_cap);
+  bool lut_smem = true;  // normalised LUT staged in shared memory when every region body has <= 16 bins (32 KB)
+  for (int b = 0; b < ctx->n_bodies; ++b)
+    if (ctx->h_bodies[b].has_region && ctx->h_bodies[b].rp.n_bins > 16) lut_smem = false;
+  // dynamic shared memory: [normalised LUT 32 KB (16 bins)] [colour bin-index tile] [depth tile]
+  const size_t lut_bytes = lut_smem ? size_t(16 * 16 * 16) * sizeof(float2) : 0;
+  const size_t dyn = ctx->use_tiles ? size_t(kDynSmemBytes) : lut_bytes;
+  a.tile_bytes = ctx->use_tiles ? int(dyn - lut_bytes) : 0;
+#define M3TB_LAUNCH(T_, K_)                                                                       \
+  do {                                                                                            \
+    if (lut_smem) {                                                                               \
+      CU(cudaFuncSetAttribute(k_track<T_, K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn))); \
+      k_track<T_, K_, true><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                          \
+    } else {                                                                                      \
+      CU(cudaFuncSetAttribute(k_track<T_, K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn))); \
+      k_track<T_, K_, false><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                         \
+    }                                                                                             \
+  } while (0)
+  if (items <= 256) M3TB_LAUNCH(256, 1);
+  else if (items <= 512) M3TB_LAUNCH(512, 1);
+  else if (items <= 1024) M3TB_LAUNCH(512, 2);
+  else if (items <= 2048) M3TB_LAUNCH(512, 4);
+  else return Fail(ctx, M3TB_ERR_UNSUPPORTED, "n_lines_max / n_points_max above 2048");
+#undef M3TB_LAUNCH
   CU(cudaGetLastError());
   ctx->launches++;
   return M3TB_OK;
@@ -277,6 +297,11 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
     d[6] = region ? s[6] : 0.0f;
     d[7] = region ? s[7] : 0.0f;
   }
+  float radius2 = 0.0f;
+  for (size_t k = 0; k < size_t(n_views) * n_points; ++k) {
+    const float* d = packed.data() + k * 8;
+    radius2 = std::max(radius2, d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+  }
   std::vector<float> sc(n_views, 0.0f);
   float max_scalar = 0.0f;
   for (int v = 0; v < n_views; ++v) {
@@ -297,6 +322,7 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   m.view_scalars = al.view_scalars;
   m.points = al.points;
   m.max_view_scalar = max_scalar;
+  m.radius = std::sqrt(radius2);
   m.set = 1;
   ctx->models_dirty = true;
   return M3TB_OK;
@@ -465,6 +491,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->dmodel_alloc.assign(max_models, ModelAlloc());
   ctx->private_color.assign(max_cameras, nullptr);
   ctx->private_depth.assign(max_cameras, nullptr);
+  if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
   auto alloc = [&]() -> int {
     CU(cudaSetDevice(device));
     CU(cudaMalloc(&ctx->d_bodies, sizeof(BodyDev) * max_bodies));

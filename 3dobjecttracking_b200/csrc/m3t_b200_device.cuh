@@ -52,6 +52,7 @@ struct ModelDev {
   const float* view_scalars;  // [n_views] contour_length | surface_area
   const float4* points;       // [n_views][n_points][2]: region (cx,cy,cz,nx)(ny,nz,fg,bg); depth (cx,cy,cz,nx)(ny,nz,0,0)
   float max_view_scalar;
+  float radius;               // max |center_f_body| over all points: bounding sphere used for the ROI tiles
   int set;
 };
 
@@ -105,6 +106,7 @@ struct TrackArgs {
   float* gh_depth;              // [n_bodies][27]
   int iteration, corr_begin, corr_end, n_update, opt_base;
   unsigned phases;
+  int tile_bytes;               // dynamic shared memory available for the colour / depth ROI tiles (0: no tiling)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -1,10 +1,17 @@
 // m3t_b200_kernels.cuh — the kernels of the pose-optimisation path.
 //
-//   k_track      one CTA per body: K5 closest view -> K1 region lines (project, validate, DDA gather,
-//                normalised-LUT lookup, segment products, distribution, moments) + K3 depth
-//                correspondence search -> n_update x ( K2 gradient/Hessian accumulate with warp-shuffle
-//                reduction -> K4 6x6 pivoted LDL^T + SE(3) exponential update ), for corr in
-//                [corr_begin, corr_end). The same kernel serves the fine-grained C-ABI calls via `phases`.
+//   k_track<T,K,LUT_SMEM>
+//       one CTA of T threads per body for a whole tracking step; thread t owns correspondence lines /
+//       surface points t, t+T, ... (K of each) and keeps their state (RegionModality::DataLine,
+//       DepthModality::DataPoint) in REGISTERS between CalculateCorrespondences and the n_update
+//       gradient passes. Per correspondence iteration:
+//         K5 closest view (block arg-max)  ->  K1 region lines (project, validate, DDA gather,
+//         normalised-LUT lookup, segment products, distribution, moments)  +  K3 depth search
+//         ->  n_update x ( K2 gradient/Hessian (27 accumulators/thread, warp-shuffle + one smem hop)
+//                          ->  K4 in-warp 6x6 pivoted LDL^T + SE(3) update ).
+//       The normalised histogram LUT (32 KB at 16 bins) is staged into shared memory once per launch
+//       by a TMA bulk copy (cp.async.bulk + mbarrier). The same kernel serves the fine-grained C-ABI
+//       calls via `phases`.
 //   k_histogram  RegionModality::StartModality / CalculateResults histogram side.
 //   k_lut        per-bin normalisation of (hist_f, hist_b) -> float2 LUT.
 #pragma once
@@ -13,61 +20,131 @@
 
 namespace m3tb {
 
+constexpr int kMaxWarps = 16;
+constexpr int kDynSmemBytes = 220 * 1024;  // dynamic shared memory per CTA when ROI tiles are on (1 CTA / SM)
+
+// ROI tile staged in shared memory: pixels [x0, x0+w) x [y0, y0+h) of one camera frame, `pitch` elements per row.
+// Colour tiles hold the histogram BIN INDEX of every pixel (u16, computed once per launch instead of once per
+// line sample); depth tiles hold the raw U16 depth, copied row by row with TMA bulk copies.
+struct Tile {
+  int x0, y0, w, h, pitch;
+  unsigned offset;  // byte offset in dynamic shared memory
+};
+
 struct Shared {
-  float pose[12];            // body2world (Body::body2world_pose)
-  float red[kWarps][54];     // per-warp partial sums: region g[6]+H[21], depth g[6]+H[21]
-  float gh[54];              // block totals
-  float a[36];               // normal matrix (lower)
+  Tile ctile, dtile;
+  unsigned long long depth_bar;  // mbarrier of the depth-tile bulk copies
+  float pose[12];                // body2world (Body::body2world_pose)
+  float red[kMaxWarps][27];      // per-warp partial sums: g[6] + H lower[21]
+  float a[36];                   // normal matrix, full symmetric
   float b[6];
-  float best_dot[kWarps];
-  int best_idx[kWarps];
-  int view[2];               // closest view: region, depth
-  int n_items[2];            // n_lines, n_points
+  float x[6];
+  float best_dot[2][kMaxWarps];
+  int best_idx[2][kMaxWarps];
+  unsigned long long lut_bar;    // mbarrier of the LUT bulk copy
 };
 
 // index of (i, j), i >= j, in the packed lower triangle
 __host__ __device__ __forceinline__ constexpr int Tri(int i, int j) { return i * (i + 1) / 2 + j; }
 
 // ---------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned SmemAddr(const void* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void MbarInit(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(SmemAddr(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void MbarExpectTx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(SmemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void BulkCopyG2S(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   SmemAddr(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(SmemAddr(bar))
+               : "memory");
+}
+__device__ __forceinline__ bool MbarTryWait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(SmemAddr(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void MbarWait(unsigned long long* bar, unsigned parity) {
+  while (!MbarTryWait(bar, parity)) {
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K5: RegionModel/DepthModel::GetClosestView (region_model.cpp:105-130, depth_model.cpp:81-106)
 // orientation = R^T * normalize(t) (linear block of body2camera, see DESIGN.md "Numerics");
-// argmax of the dot product, first maximum wins.
+// arg-max of the dot product, first maximum wins. Two models (region + depth) share one block pass.
 // ---------------------------------------------------------------------------------------------
-__device__ int ClosestView(const ModelDev& m, const float* b2c, Shared& sh) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ bool ViewOrientation(const float* b2c, float& o0, float& o1, float& o2) {
   float tx = b2c[3], ty = b2c[7], tz = b2c[11];
   float z = tx * tx + ty * ty + tz * tz;
   float norm = sqrtf(z);
-  if (norm == 0.0f) return 0;  // uniform across the block
+  if (norm == 0.0f) return false;  // reference returns views_[0]
   if (z > 0.0f) { tx /= norm; ty /= norm; tz /= norm; }
-  float o0 = b2c[0] * tx + b2c[4] * ty + b2c[8] * tz;
-  float o1 = b2c[1] * tx + b2c[5] * ty + b2c[9] * tz;
-  float o2 = b2c[2] * tx + b2c[6] * ty + b2c[10] * tz;
-  float best = -1.0f;
-  int idx = 0x7fffffff;
-  for (int v = tid; v < m.n_views; v += kBlockThreads) {
-    const float* vo = m.orientations + 3 * v;
-    float dot = o0 * __ldg(vo) + o1 * __ldg(vo + 1) + o2 * __ldg(vo + 2);
-    if (dot > best) { best = dot; idx = v; }
-  }
+  o0 = b2c[0] * tx + b2c[4] * ty + b2c[8] * tz;
+  o1 = b2c[1] * tx + b2c[5] * ty + b2c[9] * tz;
+  o2 = b2c[2] * tx + b2c[6] * ty + b2c[10] * tz;
+  return true;
+}
+
+__device__ __forceinline__ void ArgmaxMerge(float& best, int& idx, float ob, int oi) {
+  if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+}
+
+template <int T>
+__device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelDev* m1, const float* b2c1, Shared& sh,
+                             int& view0, int& view1) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int kW = T / 32;
+  float best[2] = {-1.0f, -1.0f};
+  int idx[2] = {0x7fffffff, 0x7fffffff};
+  bool nonzero[2] = {false, false};
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) {
-    float ob = __shfl_down_sync(0xffffffffu, best, off);
-    int oi = __shfl_down_sync(0xffffffffu, idx, off);
-    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  for (int s = 0; s < 2; ++s) {
+    const ModelDev* m = s == 0 ? m0 : m1;
+    if (!m) continue;
+    float o0, o1, o2;
+    nonzero[s] = ViewOrientation(s == 0 ? b2c0 : b2c1, o0, o1, o2);
+    if (!nonzero[s]) continue;
+    const float* ori = m->orientations;
+    for (int v = tid; v < m->n_views; v += T) {
+      float dot = o0 * __ldg(ori + 3 * v) + o1 * __ldg(ori + 3 * v + 1) + o2 * __ldg(ori + 3 * v + 2);
+      if (dot > best[s]) { best[s] = dot; idx[s] = v; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      float ob = __shfl_down_sync(0xffffffffu, best[s], off);
+      int oi = __shfl_down_sync(0xffffffffu, idx[s], off);
+      ArgmaxMerge(best[s], idx[s], ob, oi);
+    }
+    if (lane == 0) { sh.best_dot[s][warp] = best[s]; sh.best_idx[s][warp] = idx[s]; }
   }
-  if (lane == 0) { sh.best_dot[warp] = best; sh.best_idx[warp] = idx; }
   __syncthreads();
-  float rb = sh.best_dot[0];
-  int ri = sh.best_idx[0];
+  int out[2] = {0, 0};
 #pragma unroll
-  for (int w = 1; w < kWarps; ++w) {
-    float ob = sh.best_dot[w];
-    int oi = sh.best_idx[w];
-    if (ob > rb || (ob == rb && oi < ri)) { rb = ob; ri = oi; }
+  for (int s = 0; s < 2; ++s) {
+    if (!(s == 0 ? m0 : m1) || !nonzero[s]) continue;
+    float rb = sh.best_dot[s][0];
+    int ri = sh.best_idx[s][0];
+#pragma unroll
+    for (int w = 1; w < kW; ++w) ArgmaxMerge(rb, ri, sh.best_dot[s][w], sh.best_idx[s][w]);
+    out[s] = ri == 0x7fffffff ? 0 : ri;
   }
-  __syncthreads();  // best_* reused by the next call
-  return ri == 0x7fffffff ? 0 : ri;
+  __syncthreads();  // best_* are reused by the next call
+  view0 = out[0];
+  view1 = out[1];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -99,10 +176,42 @@ __device__ __forceinline__ void MakeRegionIter(const RegionParamsDev& rp, const 
   it.variance = sd * sd;
 }
 
-// Writes the line state into st[field * cap + i]. Returns validity.
-__device__ bool RegionLine(const RegionIter& it, const RegionParamsDev& rp, const float4 p0, const float4 p1,
-                           const uint8_t* __restrict__ img, unsigned pitch, const float2* __restrict__ lut,
-                           float* st, int cap, int i) {
+// Histogram bin index of pixel (x, y): from the shared-memory tile when inside it, else straight from the frame
+// (same integer result either way, so tiling never changes a line).
+__device__ __forceinline__ int PixelBin(const Tile& t, const uint16_t* tile, const uint8_t* __restrict__ img,
+                                        unsigned pitch, int bs, int nb, int x, int y) {
+  const unsigned tx = unsigned(x - t.x0), ty = unsigned(y - t.y0);
+  if (tx < unsigned(t.w) && ty < unsigned(t.h)) return tile[ty * unsigned(t.pitch) + tx];
+  const uint8_t* px = img + size_t(unsigned(y)) * pitch + 3u * unsigned(x);
+  // ColorHistograms::GetProbabilities index (color_histograms.cpp:97-99), BGR memory order
+  return (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
+}
+
+__device__ __forceinline__ unsigned DepthAt(const Tile& t, const uint16_t* tile, const uint8_t* __restrict__ img,
+                                            unsigned pitch, int x, int y) {
+  const unsigned tx = unsigned(x - t.x0), ty = unsigned(y - t.y0);
+  if (tx < unsigned(t.w) && ty < unsigned(t.h)) return tile[ty * unsigned(t.pitch) + tx];
+  return __ldg(reinterpret_cast<const uint16_t*>(img + size_t(unsigned(y)) * pitch) + x);
+}
+
+struct LineState {  // RegionModality::DataLine (region_modality.h:150-165), the fields the math uses
+  float cbx, cby, cbz, cu, cv, nu, nv, dr, ncts, mean, var;
+  float dist[kDistributionLength];
+  bool valid;
+};
+
+template <bool LUT_SMEM>
+__device__ __forceinline__ float2 LutFetch(const float2* __restrict__ lut_g, const float2* lut_s, int idx) {
+  if (LUT_SMEM) return lut_s[idx];
+  return __ldg(lut_g + idx);
+}
+
+template <bool LUT_SMEM>
+__device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionParamsDev& rp, const float4 p0,
+                                           const float4 p1, const uint8_t* __restrict__ img, unsigned pitch,
+                                           const Tile& tile, const uint16_t* tile_px,
+                                           const float2* __restrict__ lut_g, const float2* lut_s, LineState& L) {
+  L.valid = false;
   // CalculateBasicLineData (:1231-1250)
   float x, y, z;
   PoseApply(it.b2c, p0.x, p0.y, p0.z, x, y, z);
@@ -114,15 +223,14 @@ __device__ bool RegionLine(const RegionIter& it, const RegionParamsDev& rp, cons
   }
   float center_u = x * it.fu / z + it.ppu;
   float center_v = y * it.fv / z + it.ppv;
-  st[RF_CBX * cap + i] = p0.x; st[RF_CBY * cap + i] = p0.y; st[RF_CBZ * cap + i] = p0.z;
-  st[RF_CU * cap + i] = center_u; st[RF_CV * cap + i] = center_v;
-  st[RF_NU * cap + i] = nu; st[RF_NV * cap + i] = nv;
+  L.cbx = p0.x; L.cby = p0.y; L.cbz = p0.z;
+  L.cu = center_u; L.cv = center_v; L.nu = nu; L.nv = nv;
   float continuous_distance = fminf(p1.w, p1.z) * it.fu / (z * it.fscale);
   // IsLineValid (:1252-1291)
-  if (continuous_distance < rp.min_continuous_distance) return false;
-  if (z <= 0.0f) return false;
+  if (continuous_distance < rp.min_continuous_distance) return;
+  if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
-  if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return false;
+  if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
 
   // CalculateSegmentProbabilities (:1433-1573); horizontal / vertical cases folded into major / minor axes
   const bool horizontal = fabsf(nv) < fabsf(nu);
@@ -140,23 +248,19 @@ __device__ bool RegionLine(const RegionIter& it, const RegionParamsDev& rp, cons
   const float minor_f_end = minor_f + step * float(it.ll_m1);
   if (major < 0 || major_end > major_m1 || int(minor_f) < 0 || int(minor_f) > minor_m1 || int(minor_f_end) < 1 ||
       int(minor_f_end) > minor_m2)
-    return false;
-  const size_t stride_major = horizontal ? 3u : size_t(pitch);
-  const size_t stride_minor = horizontal ? size_t(pitch) : 3u;
+    return;
   const int bs = rp.bitshift, nb = rp.n_bins;
   float sf[kLineSegments], sb[kLineSegments];
-  const uint8_t* pmaj = img + size_t(major) * stride_major;
 #pragma unroll
   for (int s = 0; s < kLineSegments; ++s) {
     float pf = 1.0f, pb = 1.0f;
     for (int k = 0; k < it.scale; ++k) {
-      const uint8_t* px = pmaj + size_t(int(minor_f)) * stride_minor;
-      // ColorHistograms::GetProbabilities index (color_histograms.cpp:97-99), BGR memory order
-      int idx = (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
-      float2 l = __ldg(lut + idx);  // already normalised per bin (MultiplyPixelColorProbability :1575-1598)
+      const int minor = int(minor_f);
+      const int idx = PixelBin(tile, tile_px, img, pitch, bs, nb, horizontal ? major : minor, horizontal ? minor : major);
+      float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);  // normalised per bin (MultiplyPixelColorProbability :1575-1598)
       pf *= l.x;
       pb *= l.y;
-      pmaj += stride_major;
+      ++major;
       minor_f += step;
     }
     sf[s] = pf;
@@ -183,39 +287,80 @@ __device__ bool RegionLine(const RegionIter& it, const RegionParamsDev& rp, cons
       }
     }
   }
-  float ncts = fabsf(n_major) / it.fscale;
-  float delta_r = (roundf(c_major - it.ll_m1_half) + it.ll_m1_half - c_major) / n_major;
-  st[RF_NCTS * cap + i] = ncts;
-  st[RF_DR * cap + i] = delta_r;
+  L.ncts = fabsf(n_major) / it.fscale;
+  L.dr = (roundf(c_major - it.ll_m1_half) + it.ll_m1_half - c_major) / n_major;
 
   // CalculateDistribution (:1600-1637)
-  float dist[kDistributionLength];
   float area = 0.0f;
 #pragma unroll
   for (int d = 0; d < kDistributionLength; ++d) {
     float val = 1.0f;
 #pragma unroll
     for (int k = 0; k < kFunctionLength; ++k) val *= sf[d + k] * rp.lookup_f[k] + sb[d + k] * rp.lookup_b[k];
-    dist[d] = val;
+    L.dist[d] = val;
     area += val;
   }
 #pragma unroll
-  for (int d = 0; d < kDistributionLength; ++d) dist[d] /= area;
+  for (int d = 0; d < kDistributionLength; ++d) L.dist[d] /= area;
   // CalculateDistributionMoments (:1639-1658)
   float mean_from_begin = 0.0f;
 #pragma unroll
-  for (int d = 0; d < kDistributionLength; ++d) mean_from_begin += float(d) * dist[d];
+  for (int d = 0; d < kDistributionLength; ++d) mean_from_begin += float(d) * L.dist[d];
   float var = 0.0f;
 #pragma unroll
   for (int d = 0; d < kDistributionLength; ++d) {
     float dd = float(d) - mean_from_begin;
-    var += (dd * dd) * dist[d];
+    var += (dd * dd) * L.dist[d];
   }
+  L.mean = mean_from_begin - (float(kDistributionLength) - 1.0f) / 2.0f;
+  L.var = fmaxf(var, rp.min_expected_variance);
+  L.valid = true;
+}
+
+__device__ __forceinline__ float Select12(const float (&d)[kDistributionLength], int i) {
+  float r = d[0];
 #pragma unroll
-  for (int d = 0; d < kDistributionLength; ++d) st[(RF_DIST0 + d) * cap + i] = dist[d];
-  st[RF_MEAN * cap + i] = mean_from_begin - (float(kDistributionLength) - 1.0f) / 2.0f;
-  st[RF_VAR * cap + i] = fmaxf(var, rp.min_expected_variance);
-  return true;
+  for (int k = 1; k < kDistributionLength; ++k) r = (i == k) ? d[k] : r;
+  return r;
+}
+
+// K2 region: one line's contribution to g / H (region_modality.cpp:485-558)
+__device__ __forceinline__ void RegionGradient(const RegionIter& it, const RegionParamsDev& rp, const LineState& L,
+                                               int opt_iteration, float (&acc)[27]) {
+  if (!L.valid) return;
+  float x, y, z;
+  PoseApply(it.b2c, L.cbx, L.cby, L.cbz, x, y, z);
+  float fu_z = it.fu / z, fv_z = it.fv / z;
+  float xfu_z = x * fu_z, yfv_z = y * fv_z;
+  float delta_cs = (L.nu * (xfu_z + it.ppu - L.cu) + L.nv * (yfv_z + it.ppv - L.cv) - L.dr) * L.ncts;
+  float dll;
+  if (opt_iteration < rp.n_global_iterations) {
+    dll = (L.mean - delta_cs) / L.var;
+  } else {
+    int upper = int(delta_cs + (float(kDistributionLength) + 1.0f) / 2.0f);
+    int lower = upper - 1;
+    if (upper <= 0 || upper >= kDistributionLength) return;
+    dll = (logf(Select12(L.dist, upper)) - logf(Select12(L.dist, lower))) * rp.learning_rate / L.var;
+  }
+  float dc0 = L.ncts * L.nu * fu_z;
+  float dc1 = L.ncts * L.nv * fv_z;
+  float dc2 = L.ncts * (-L.nu * xfu_z - L.nv * yfv_z) / z;
+  float J[6];
+  J[3] = dc0 * it.b2c[0] + dc1 * it.b2c[4] + dc2 * it.b2c[8];
+  J[4] = dc0 * it.b2c[1] + dc1 * it.b2c[5] + dc2 * it.b2c[9];
+  J[5] = dc0 * it.b2c[2] + dc1 * it.b2c[6] + dc2 * it.b2c[10];
+  J[0] = L.cby * J[5] - L.cbz * J[4];
+  J[1] = L.cbz * J[3] - L.cbx * J[5];
+  J[2] = L.cbx * J[4] - L.cby * J[3];
+  float weight = rp.min_expected_variance / (L.ncts * L.ncts * it.variance);
+  float wg = weight * dll;
+  float wh = weight / L.var;
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    acc[r] += wg * J[r];
+#pragma unroll
+    for (int c = 0; c <= r; ++c) acc[6 + Tri(r, c)] -= (wh * J[r]) * J[c];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -241,18 +386,25 @@ __device__ __forceinline__ void MakeDepthIter(const DepthParamsDev& dp, const Ca
   it.standard_deviation = LastValid(dp.standard_deviations, dp.n_standard_deviations, corr_iteration);
 }
 
-__device__ bool DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
-                           const uint8_t* __restrict__ img, unsigned pitch, float* st, int cap, int i) {
+struct PointState {  // DepthModality::DataPoint (depth_modality.h:139-150)
+  float cbx, cby, cbz, nx, ny, nz, yx, yy, yz;
+  bool valid;
+};
+
+__device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
+                                           const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
+                                           const uint16_t* tile_px, PointState& P) {
+  P.valid = false;
   float x, y, z;
   PoseApply(it.b2c, p0.x, p0.y, p0.z, x, y, z);
-  st[DF_CBX * cap + i] = p0.x; st[DF_CBY * cap + i] = p0.y; st[DF_CBZ * cap + i] = p0.z;
-  st[DF_NX * cap + i] = p0.w; st[DF_NY * cap + i] = p1.x; st[DF_NZ * cap + i] = p1.y;
+  P.cbx = p0.x; P.cby = p0.y; P.cbz = p0.z;
+  P.nx = p0.w; P.ny = p1.x; P.nz = p1.y;
   float center_u = x * it.fu / z + it.ppu;
   float center_v = y * it.fv / z + it.ppv;
   // IsPointValid (:697-726)
-  if (z <= 0.0f) return false;
+  if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
-  if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return false;
+  if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
   // FindCorrespondence (:826-884)
   float considered_distance = it.considered_distance;
   if (dp.use_depth_scaling) considered_distance *= z;
@@ -276,9 +428,8 @@ __device__ bool DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const 
   float best = min_considered_distance_square;
   float bx = 0.0f, by = 0.0f, bz = 0.0f;
   for (int v = v_min; v <= v_max; v += stride) {
-    const uint16_t* row = reinterpret_cast<const uint16_t*>(img + size_t(v) * pitch);
     for (int u = u_min; u <= u_max; u += stride) {
-      float depth = float(__ldg(row + u));
+      float depth = float(DepthAt(tile, tile_px, img, pitch, u, v));
       if (depth > min_depth_value && depth < max_depth_value) {
         depth *= it.depth_scale;
         float tx = (float(u) - it.ppu) * depth / it.fu;
@@ -289,75 +440,46 @@ __device__ bool DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const 
       }
     }
   }
-  if (best == min_considered_distance_square) return false;
-  st[DF_YX * cap + i] = bx; st[DF_YY * cap + i] = by; st[DF_YZ * cap + i] = bz;
-  return true;
+  if (best == min_considered_distance_square) return;
+  P.yx = bx; P.yy = by; P.yz = bz;
+  P.valid = true;
+}
+
+// K2 depth: one point's contribution (depth_modality.cpp:333-381)
+__device__ __forceinline__ void DepthGradient(const DepthIter& it, const PointState& P, float (&acc)[27]) {
+  if (!P.valid) return;
+  float yb0, yb1, yb2;
+  PoseApply(it.c2b, P.yx, P.yy, P.yz, yb0, yb1, yb2);
+  float epsilon = P.nx * (P.cbx - yb0) + P.ny * (P.cby - yb1) + P.nz * (P.cbz - yb2);
+  float cx[3] = {yb1 * P.nz - yb2 * P.ny, yb2 * P.nx - yb0 * P.nz, yb0 * P.ny - yb1 * P.nx};
+  float weight = 1.0f / (it.standard_deviation * P.yz);
+  float squared_weight = weight * weight;
+  float v[6] = {weight * cx[0], weight * cx[1], weight * cx[2], weight * P.nx, weight * P.ny, weight * P.nz};
+  float se = squared_weight * epsilon;
+  float nn[3] = {P.nx, P.ny, P.nz};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    acc[r] -= se * cx[r];
+    acc[3 + r] -= se * nn[r];
+  }
+  // upper-triangle products v[r] * v[c], r <= c, stored at the mirrored lower index
+#pragma unroll
+  for (int c = 0; c < 6; ++c)
+#pragma unroll
+    for (int r = 0; r <= c; ++r) acc[6 + Tri(c, r)] -= v[r] * v[c];
 }
 
 // ---------------------------------------------------------------------------------------------
 // K4: Optimizer::CalculateOptimization for a rigid body (optimizer.cpp:144-167): Eigen LDLT<Lower>
-// with diagonal pivoting restated for n = 6, then Link::UpdatePoses (link.cpp:205-241).
-// Runs on one thread; a: 6x6 row-major (lower used), b: rhs, result in theta.
+// (diagonal pivoting, left-looking) restated for n = 6, then Link::UpdatePoses (link.cpp:205-241).
+// Executed redundantly by every lane of warp 0 (no divergence, no shuffles). Because the left-looking
+// factorisation never touches a diagonal entry before it is chosen as pivot, the whole transposition
+// sequence follows from the original diagonal: it is computed first, the symmetrically permuted matrix
+// is gathered from shared memory, and the factorisation itself runs fully unrolled in registers.
 // ---------------------------------------------------------------------------------------------
-__device__ void LdltSolve6(float* a, const float* b, float* theta) {
-  constexpr int n = 6;
-  int trans[n];
-  float temp[n];
-#define A_(i, j) a[(i) * n + (j)]
-  for (int k = 0; k < n; ++k) {
-    int biggest = k;
-    float big = fabsf(A_(k, k));
-    for (int i = k + 1; i < n; ++i) {
-      float v = fabsf(A_(i, i));
-      if (v > big) { big = v; biggest = i; }
-    }
-    trans[k] = biggest;
-    if (k != biggest) {
-      for (int j = 0; j < k; ++j) { float t = A_(k, j); A_(k, j) = A_(biggest, j); A_(biggest, j) = t; }
-      for (int i = biggest + 1; i < n; ++i) { float t = A_(i, k); A_(i, k) = A_(i, biggest); A_(i, biggest) = t; }
-      { float t = A_(k, k); A_(k, k) = A_(biggest, biggest); A_(biggest, biggest) = t; }
-      for (int i = k + 1; i < biggest; ++i) { float t = A_(i, k); A_(i, k) = A_(biggest, i); A_(biggest, i) = t; }
-    }
-    if (k > 0) {
-      for (int j = 0; j < k; ++j) temp[j] = A_(j, j) * A_(k, j);
-      float dot = 0.0f;
-      for (int j = 0; j < k; ++j) dot += A_(k, j) * temp[j];
-      A_(k, k) -= dot;
-      for (int i = k + 1; i < n; ++i) {
-        float acc = 0.0f;
-        for (int j = 0; j < k; ++j) acc += A_(i, j) * temp[j];
-        A_(i, k) -= acc;
-      }
-    }
-    float akk = A_(k, k);
-    bool pivot_is_valid = fabsf(akk) > 0.0f;
-    if (k == 0 && !pivot_is_valid) {
-      for (int j = 0; j < n; ++j) trans[j] = j;
-      break;
-    }
-    if (k < n - 1 && pivot_is_valid)
-      for (int i = k + 1; i < n; ++i) A_(i, k) /= akk;
-  }
-  float dst[n];
-  for (int i = 0; i < n; ++i) dst[i] = b[i];
-  for (int k = 0; k < n; ++k) { float t = dst[k]; dst[k] = dst[trans[k]]; dst[trans[k]] = t; }
-  for (int j = 0; j < n; ++j)
-    for (int i = j + 1; i < n; ++i) dst[i] -= A_(i, j) * dst[j];
-  const float tolerance = 1.0f / 3.402823466e+38f;
-  for (int i = 0; i < n; ++i) {
-    if (fabsf(A_(i, i)) > tolerance) dst[i] /= A_(i, i);
-    else dst[i] = 0.0f;
-  }
-  for (int j = n - 1; j >= 0; --j)
-    for (int i = 0; i < j; ++i) dst[i] -= A_(j, i) * dst[j];
-  for (int k = n - 1; k >= 0; --k) { float t = dst[k]; dst[k] = dst[trans[k]]; dst[trans[k]] = t; }
-  for (int i = 0; i < n; ++i) theta[i] = dst[i];
-#undef A_
-}
-
-// Vector2Skewsymmetric(w).exp() in closed form (Rodrigues); the reference uses Eigen's Pade
-// approximant (link.cpp:224), the two agree to < 1e-7 for |w| <= 1 (tests/test_oracle_math.py).
-__device__ void ExpSkew(const float* w, float* r) {
+__device__ __forceinline__ void ExpSkew(const float* w, float* r) {
+  // Vector2Skewsymmetric(w).exp() in closed form (Rodrigues); the reference uses Eigen's Pade approximant
+  // (link.cpp:224), the two agree to < 1e-7 for |w| <= 1 (tests/test_oracle_math.py).
   float t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   float a, b;
   if (t2 < 1e-8f) {
@@ -379,220 +501,404 @@ __device__ void ExpSkew(const float* w, float* r) {
   for (int k = 0; k < 9; ++k) r[k] = ((k % 4 == 0) ? 1.0f : 0.0f) + a * A[k] + b * A2[k];
 }
 
-__device__ void SolveAndUpdate(const BodyDev& body, Shared& sh) {
-  // Link::CalculateGradientAndHessian (link.cpp:184-193): region first, then depth.
-  // Optimizer: b = J^T g, a(lower) = -J^T H J with J = I6, a.diagonal() += tikhonov (:144-159)
-  float* a = sh.a;
-  for (int i = 0; i < 6; ++i) {
-    sh.b[i] = 0.0f + (0.0f + sh.gh[i] + sh.gh[27 + i]);
-    for (int j = 0; j < 6; ++j) {
-      float v = 0.0f;
-      if (j <= i) {
-        float h = 0.0f + sh.gh[6 + Tri(i, j)] + sh.gh[27 + 6 + Tri(i, j)];
-        v = 0.0f - h;
+// sh.a (full symmetric 6x6) and sh.b must be visible to the calling warp. Returns true if the pose was updated.
+__device__ __forceinline__ bool SolveAndUpdateWarp(Shared& sh) {
+  constexpr int n = 6;
+  // transposition sequence from the original diagonal (first maximum wins)
+  float dv[n];
+  int pm[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) { dv[i] = fabsf(sh.a[i * n + i]); pm[i] = i; }
+#pragma unroll
+  for (int k = 0; k < n - 1; ++k) {
+    int p = k;
+    float big = dv[k];
+#pragma unroll
+    for (int i = k + 1; i < n; ++i)
+      if (dv[i] > big) { big = dv[i]; p = i; }
+#pragma unroll
+    for (int c = k + 1; c < n; ++c)
+      if (p == c) {
+        float t = dv[k]; dv[k] = dv[c]; dv[c] = t;
+        int ti = pm[k]; pm[k] = pm[c]; pm[c] = ti;
       }
-      a[6 * i + j] = v;
+  }
+  // gather P A P^T (lower) and P b
+  float A[n][n];
+  float dst[n];
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) A[i][j] = sh.a[pm[i] * n + pm[j]];
+    dst[i] = sh.b[pm[i]];
+  }
+  // ldlt_inplace<Lower>::unblocked
+  bool zero_matrix = false;
+#pragma unroll
+  for (int k = 0; k < n; ++k) {
+    if (!zero_matrix) {
+      if (k > 0) {
+        float temp[n];
+#pragma unroll
+        for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
+        float dot = 0.0f;
+#pragma unroll
+        for (int j = 0; j < k; ++j) dot += A[k][j] * temp[j];
+        A[k][k] -= dot;
+#pragma unroll
+        for (int i = k + 1; i < n; ++i) {
+          float acc = 0.0f;
+#pragma unroll
+          for (int j = 0; j < k; ++j) acc += A[i][j] * temp[j];
+          A[i][k] -= acc;
+        }
+      }
+      float akk = A[k][k];
+      bool pivot_is_valid = fabsf(akk) > 0.0f;
+      if (k == 0 && !pivot_is_valid) zero_matrix = true;
+      if (!zero_matrix && pivot_is_valid) {
+#pragma unroll
+        for (int i = k + 1; i < n; ++i) A[i][k] /= akk;
+      }
     }
   }
-  for (int i = 0; i < 6; ++i) a[6 * i + i] += (i < 3) ? body.tikhonov_rotation : body.tikhonov_translation;
-  float theta[6];
-  LdltSolve6(a, sh.b, theta);
+  // LDLT::_solve_impl
+#pragma unroll
+  for (int j = 0; j < n; ++j)
+#pragma unroll
+    for (int i = j + 1; i < n; ++i) dst[i] -= A[i][j] * dst[j];
+  const float tolerance = 1.0f / 3.402823466e+38f;
+#pragma unroll
+  for (int i = 0; i < n; ++i) {
+    if (fabsf(A[i][i]) > tolerance) dst[i] /= A[i][i];
+    else dst[i] = 0.0f;
+  }
+#pragma unroll
+  for (int j = n - 1; j >= 0; --j)
+#pragma unroll
+    for (int i = 0; i < j; ++i) dst[i] -= A[j][i] * dst[j];
+#pragma unroll
+  for (int i = 0; i < n; ++i) sh.x[pm[i]] = dst[i];  // P^T; every lane stores the same values
+  __syncwarp();
+  float theta[n];
   bool nan = false;
-  for (int i = 0; i < 6; ++i) nan = nan || isnan(theta[i]);
-  if (nan) return;  // optimizer.cpp:165
+#pragma unroll
+  for (int i = 0; i < n; ++i) { theta[i] = sh.x[i]; nan = nan || isnan(theta[i]); }
+  if (nan) return false;  // optimizer.cpp:165
   float e[9];
   ExpSkew(theta, e);
   float var[12] = {e[0], e[1], e[2], theta[3], e[3], e[4], e[5], theta[4], e[6], e[7], e[8], theta[5]};
-  float np[12];
-  PoseMul(sh.pose, var, np);  // link2world * [exp | t] (link.cpp:222-238, body2joint = I)
-  for (int i = 0; i < 12; ++i) sh.pose[i] = np[i];
+  float cur[12], np[12];
+#pragma unroll
+  for (int i = 0; i < 12; ++i) cur[i] = sh.pose[i];
+  PoseMul(cur, var, np);  // link2world * [exp | t] (link.cpp:222-238, body2joint = I)
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sh.pose[i] = np[i];
+  }
+  return true;
+}
+
+// (i, j) of packed lower-triangle index e
+__device__ __forceinline__ void TriInv(int e, int& i, int& j) {
+  i = (e >= 15) ? 5 : (e >= 10) ? 4 : (e >= 6) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0;
+  j = e - i * (i + 1) / 2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ROI tiles. The rectangle every line sample / depth window of this launch can touch is bounded by the
+// projected bounding sphere of the model plus the longest line (or the widest search window) plus a
+// motion margin; it is computed once from the pose at launch. Samples that still fall outside (large pose
+// updates, clipped tiles) are read from the frame in global memory, so tiling never changes a result.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void RoiRect(const float* b2c, float fu, float fv, float ppu, float ppv, int width, int height,
+                                        float radius, float reach_px, int align_x, Tile& t) {
+  const float z = b2c[11];
+  t.x0 = t.y0 = t.w = t.h = t.pitch = 0;
+  if (!(z > 2.0f * radius)) return;  // too close / behind: no tile, global path only
+  const float cu = b2c[3] * fu / z + ppu, cv = b2c[7] * fv / z + ppv;
+  const float ru = radius * fu / (z - radius) + reach_px, rv = radius * fv / (z - radius) + reach_px;
+  int x0 = int(floorf(cu - ru)), x1 = int(ceilf(cu + ru)) + 1;
+  int y0 = int(floorf(cv - rv)), y1 = int(ceilf(cv + rv)) + 1;
+  x0 = max(x0, 0) / align_x * align_x;
+  x1 = min((min(x1, width) + align_x - 1) / align_x * align_x, width / align_x * align_x);
+  y0 = max(y0, 0);
+  y1 = min(y1, height);
+  if (x1 <= x0 || y1 <= y0) return;
+  t.x0 = x0; t.y0 = y0; t.w = x1 - x0; t.h = y1 - y0; t.pitch = t.w;
+}
+
+// shrink symmetric about the centre until the tile fits `budget` bytes (2 bytes per pixel)
+__device__ __forceinline__ void FitTile(Tile& t, int budget, int align_x) {
+  while (t.w > 0 && t.h > 0 && t.w * t.h * 2 > budget) {
+    if (t.h >= t.w && t.h > 16) { t.y0 += 4; t.h -= 8; }
+    else if (t.w > 2 * align_x) { t.x0 += align_x; t.w -= 2 * align_x; }
+    else { t.w = t.h = 0; }
+  }
+  t.pitch = t.w;
 }
 
 // ---------------------------------------------------------------------------------------------
 // The fused kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlockThreads) k_track(TrackArgs args) {
-  extern __shared__ float dyn[];
+template <int T, int K, bool LUT_SMEM>
+__global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ TrackArgs args) {
+  extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Shared sh;
+  constexpr int kW = T / 32;
   const int body_id = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const BodyDev& body = args.bodies[body_id];
   if (!body.set) return;
   const bool has_region = body.has_region, has_depth = body.has_depth;
   const int lcap = args.line_cap, pcap = args.point_cap;
-  float* rst = dyn;                     // [RF_COUNT][lcap]
-  float* dst = dyn + RF_COUNT * lcap;   // [DF_COUNT][pcap]
   float* g_rst = args.region_state + size_t(body_id) * RF_COUNT * lcap;
   float* g_dst = args.depth_state + size_t(body_id) * DF_COUNT * pcap;
   int* counts = args.counts + 4 * body_id;
+  const float2* lut_g = args.lut + size_t(body_id) * args.lut_stride;
+  const float2* lut_s = reinterpret_cast<const float2*>(dyn);
 
-  if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
-  if (tid == 0) {
-    sh.n_items[0] = (args.phases & PH_LOAD_REGION) ? counts[0] : 0;
-    sh.n_items[1] = (args.phases & PH_LOAD_DEPTH) ? counts[1] : 0;
-  }
-  __syncthreads();
-  if (args.phases & PH_LOAD_REGION)
-    for (int k = tid; k < RF_COUNT * lcap; k += kBlockThreads) rst[k] = g_rst[k];
-  if (args.phases & PH_LOAD_DEPTH)
-    for (int k = tid; k < DF_COUNT * pcap; k += kBlockThreads) dst[k] = g_dst[k];
-  if (args.phases & PH_LOAD_GH) {
-    if (tid < 27) { sh.gh[tid] = args.gh_region[27 * body_id + tid]; sh.gh[27 + tid] = args.gh_depth[27 * body_id + tid]; }
-  }
-  __syncthreads();
-
+  // ---- prologue: pose, LUT bulk copy, ROI tiles ----------------------------------------------------
   const CameraDev* ccam = has_region ? &args.color_cams[body.color_camera] : nullptr;
   const CameraDev* dcam = has_depth ? &args.depth_cams[body.depth_camera] : nullptr;
   const ModelDev* rmodel = has_region ? &args.region_models[body.region_model] : nullptr;
   const ModelDev* dmodel = has_depth ? &args.depth_models[body.depth_model] : nullptr;
-  const float2* lut = args.lut + size_t(body_id) * args.lut_stride;
+  const bool do_rcorr = has_region && (args.phases & PH_REGION_CORR);
+  const bool do_dcorr = has_depth && (args.phases & PH_DEPTH_CORR);
+  if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
+  const bool need_lut = LUT_SMEM && do_rcorr;
+  const unsigned lut_bytes = LUT_SMEM ? unsigned(16 * 16 * 16 * sizeof(float2)) : 0u;
+  if (tid == 0) {
+    if (LUT_SMEM) MbarInit(&sh.lut_bar, 1);
+    MbarInit(&sh.depth_bar, 1);
+  }
+  __syncthreads();
+  if (need_lut && tid == 0) {
+    const unsigned bytes = unsigned(body.rp.n_bins * body.rp.n_bins * body.rp.n_bins) * sizeof(float2);
+    MbarExpectTx(&sh.lut_bar, bytes);
+    BulkCopyG2S(dyn, lut_g, bytes, &sh.lut_bar);
+  }
+  if (tid == 0) {
+    Tile ct, dt;
+    ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes;
+    dt = ct;
+    if (args.tile_bytes > 0) {
+      float b2c[12];
+      if (do_rcorr) {
+        int s_max = 1;
+        for (int c = args.corr_begin; c < args.corr_end; ++c) s_max = max(s_max, LastValid(body.rp.scales, body.rp.n_scales, c));
+        PoseMul(ccam->w2c, sh.pose, b2c);
+        RoiRect(b2c, ccam->fu, ccam->fv, ccam->ppu, ccam->ppv, ccam->width, ccam->height, rmodel->radius,
+                0.5f * float(kLineSegments * s_max) + 2.0f + 12.0f, 4, ct);
+      }
+      if (do_dcorr) {
+        float d_max = 0.0f;
+        for (int c = args.corr_begin; c < args.corr_end; ++c)
+          d_max = fmaxf(d_max, LastValid(body.dp.considered_distances, body.dp.n_considered_distances, c));
+        PoseMul(dcam->w2c, sh.pose, b2c);
+        const float z = b2c[11];
+        const float reach = (z > 2.0f * dmodel->radius) ? d_max * dcam->fu / (z - dmodel->radius) + 2.0f + 8.0f : 0.0f;
+        RoiRect(b2c, dcam->fu, dcam->fv, dcam->ppu, dcam->ppv, dcam->width, dcam->height, dmodel->radius, reach, 8, dt);
+      }
+      // split the budget: the depth tile is the smaller one, give it what it asks for up to 40 %
+      int budget = args.tile_bytes - 256;
+      FitTile(dt, budget * 2 / 5, 8);
+      const int dbytes = (dt.w * dt.h * 2 + 127) / 128 * 128;
+      FitTile(ct, budget - dbytes, 4);
+      const int cbytes = (ct.w * ct.h * 2 + 127) / 128 * 128;
+      dt.offset = lut_bytes + unsigned(cbytes);
+    }
+    sh.ctile = ct;
+    sh.dtile = dt;
+  }
+  __syncthreads();
+  const Tile ctile = sh.ctile, dtile = sh.dtile;
+  const uint16_t* ctile_px = reinterpret_cast<const uint16_t*>(dyn + ctile.offset);
+  const uint16_t* dtile_px = reinterpret_cast<const uint16_t*>(dyn + dtile.offset);
+  // depth tile: one TMA bulk copy per row (16 B aligned: x0 and w are multiples of 8 pixels), all rows complete
+  // on one mbarrier; issued by warp 1 so that it overlaps the colour conversion below.
+  bool depth_ready = true;
+  if (dtile.w > 0) {
+    depth_ready = false;
+    if (warp == 1 % kW) {
+      const unsigned row_bytes = unsigned(dtile.w) * 2u;
+      if (lane == 0) MbarExpectTx(&sh.depth_bar, row_bytes * unsigned(dtile.h));
+      __syncwarp();
+      for (int r = lane; r < dtile.h; r += 32)
+        BulkCopyG2S(dyn + dtile.offset + size_t(r) * row_bytes,
+                    dcam->image + size_t(dtile.y0 + r) * dcam->pitch + size_t(dtile.x0) * 2u, row_bytes, &sh.depth_bar);
+    }
+  }
+  // colour tile: 4 pixels (12 bytes, three aligned words) -> 4 bin indices (one 8-byte store) per work item
+  if (ctile.w > 0) {
+    const int groups_per_row = ctile.w >> 2;
+    const int n_groups = groups_per_row * ctile.h;
+    const int bs = body.rp.bitshift, nb = body.rp.n_bins;
+    uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
+    for (int g = tid; g < n_groups; g += T) {
+      const int r = g / groups_per_row, c = g - r * groups_per_row;
+      const unsigned* src = reinterpret_cast<const unsigned*>(ccam->image + size_t(ctile.y0 + r) * ccam->pitch +
+                                                              size_t(ctile.x0 + 4 * c) * 3u);
+      const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
+      auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
+        return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
+      };
+      const unsigned i0 = bin(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+      const unsigned i1 = bin(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+      const unsigned i2 = bin((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+      const unsigned i3 = bin((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+      out[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+    }
+    __syncthreads();
+  }
+
+  LineState L[K];
+  PointState P[K];
+  int n_lines = 0, n_points = 0, view_r = 0, view_d = 0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { L[k].valid = false; P[k].valid = false; }
+  if (args.phases & PH_LOAD_REGION) {
+    n_lines = counts[0];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * T;
+      if (i < n_lines) {
+        L[k].cbx = g_rst[RF_CBX * lcap + i]; L[k].cby = g_rst[RF_CBY * lcap + i]; L[k].cbz = g_rst[RF_CBZ * lcap + i];
+        L[k].cu = g_rst[RF_CU * lcap + i]; L[k].cv = g_rst[RF_CV * lcap + i];
+        L[k].nu = g_rst[RF_NU * lcap + i]; L[k].nv = g_rst[RF_NV * lcap + i];
+        L[k].dr = g_rst[RF_DR * lcap + i]; L[k].ncts = g_rst[RF_NCTS * lcap + i];
+        L[k].mean = g_rst[RF_MEAN * lcap + i]; L[k].var = g_rst[RF_VAR * lcap + i];
+#pragma unroll
+        for (int d = 0; d < kDistributionLength; ++d) L[k].dist[d] = g_rst[(RF_DIST0 + d) * lcap + i];
+        L[k].valid = g_rst[RF_VALID * lcap + i] != 0.0f;
+      }
+    }
+  }
+  if (args.phases & PH_LOAD_DEPTH) {
+    n_points = counts[1];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * T;
+      if (i < n_points) {
+        P[k].cbx = g_dst[DF_CBX * pcap + i]; P[k].cby = g_dst[DF_CBY * pcap + i]; P[k].cbz = g_dst[DF_CBZ * pcap + i];
+        P[k].nx = g_dst[DF_NX * pcap + i]; P[k].ny = g_dst[DF_NY * pcap + i]; P[k].nz = g_dst[DF_NZ * pcap + i];
+        P[k].yx = g_dst[DF_YX * pcap + i]; P[k].yy = g_dst[DF_YY * pcap + i]; P[k].yz = g_dst[DF_YZ * pcap + i];
+        P[k].valid = g_dst[DF_VALID * pcap + i] != 0.0f;
+      }
+    }
+  }
+
+  bool lut_ready = !need_lut;
 
   for (int corr = args.corr_begin; corr < args.corr_end; ++corr) {
     // ---------------- CalculateCorrespondences -------------------------------------------------
-    if (has_region && (args.phases & PH_REGION_CORR)) {
-      RegionIter it;
-      MakeRegionIter(body.rp, *ccam, sh.pose, corr, it);
-      int view = ClosestView(*rmodel, it.b2c, sh);
-      int n_lines = AdaptiveCount(body.rp.n_lines_max, body.rp.use_adaptive_coverage, body.rp.reference_contour_length,
-                                  __ldg(rmodel->view_scalars + view), rmodel->max_view_scalar, rmodel->n_points);
-      n_lines = min(n_lines, lcap);
-      if (tid == 0) { sh.view[0] = view; sh.n_items[0] = n_lines; }
-      const float4* pts = rmodel->points + size_t(view) * rmodel->n_points * 2;
-      for (int i = tid; i < n_lines; i += kBlockThreads) {
-        float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-        bool ok = RegionLine(it, body.rp, p0, p1, ccam->image, ccam->pitch, lut, rst, lcap, i);
-        rst[RF_VALID * lcap + i] = ok ? 1.0f : 0.0f;
+    if (do_rcorr || do_dcorr) {
+      int v0, v1;
+      {
+        float b2c_r[12], b2c_d[12];
+        if (do_rcorr) PoseMul(ccam->w2c, sh.pose, b2c_r);
+        if (do_dcorr) PoseMul(dcam->w2c, sh.pose, b2c_d);
+        ClosestViews<T>(do_rcorr ? rmodel : nullptr, b2c_r, do_dcorr ? dmodel : nullptr, b2c_d, sh, v0, v1);
+      }
+      if (do_rcorr) {
+        RegionIter rit;
+        MakeRegionIter(body.rp, *ccam, sh.pose, corr, rit);
+        view_r = v0;
+        n_lines = AdaptiveCount(body.rp.n_lines_max, body.rp.use_adaptive_coverage, body.rp.reference_contour_length,
+                                __ldg(rmodel->view_scalars + view_r), rmodel->max_view_scalar, rmodel->n_points);
+        n_lines = min(n_lines, min(lcap, K * T));
+        if (!lut_ready) { MbarWait(&sh.lut_bar, 0); lut_ready = true; }
+        const float4* pts = rmodel->points + size_t(view_r) * rmodel->n_points * 2;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int i = tid + k * T;
+          L[k].valid = false;
+          if (i < n_lines) {
+            float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
+            RegionLine<LUT_SMEM>(rit, body.rp, p0, p1, ccam->image, ccam->pitch, ctile, ctile_px, lut_g, lut_s, L[k]);
+          }
+        }
+      }
+      if (do_dcorr) {
+        DepthIter dit;
+        MakeDepthIter(body.dp, *dcam, sh.pose, corr, dit);
+        view_d = v1;
+        n_points = AdaptiveCount(body.dp.n_points_max, body.dp.use_adaptive_coverage, body.dp.reference_surface_area,
+                                 __ldg(dmodel->view_scalars + view_d), dmodel->max_view_scalar, dmodel->n_points);
+        n_points = min(n_points, min(pcap, K * T));
+        if (!depth_ready) { MbarWait(&sh.depth_bar, 0); depth_ready = true; }
+        const float4* pts = dmodel->points + size_t(view_d) * dmodel->n_points * 2;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          const int i = tid + k * T;
+          P[k].valid = false;
+          if (i < n_points) {
+            float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
+            DepthPoint(dit, body.dp, p0, p1, dcam->image, dcam->pitch, dtile, dtile_px, P[k]);
+          }
+        }
       }
     }
-    if (has_depth && (args.phases & PH_DEPTH_CORR)) {
-      DepthIter it;
-      MakeDepthIter(body.dp, *dcam, sh.pose, corr, it);
-      int view = ClosestView(*dmodel, it.b2c, sh);
-      int n_points = AdaptiveCount(body.dp.n_points_max, body.dp.use_adaptive_coverage, body.dp.reference_surface_area,
-                                   __ldg(dmodel->view_scalars + view), dmodel->max_view_scalar, dmodel->n_points);
-      n_points = min(n_points, pcap);
-      if (tid == 0) { sh.view[1] = view; sh.n_items[1] = n_points; }
-      const float4* pts = dmodel->points + size_t(view) * dmodel->n_points * 2;
-      for (int i = tid; i < n_points; i += kBlockThreads) {
-        float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-        bool ok = DepthPoint(it, body.dp, p0, p1, dcam->image, dcam->pitch, dst, pcap, i);
-        dst[DF_VALID * pcap + i] = ok ? 1.0f : 0.0f;
-      }
-    }
-    __syncthreads();
 
     // ---------------- n_update x (CalculateGradientAndHessian + CalculateOptimization) ---------
     for (int upd = 0; upd < args.n_update; ++upd) {
       const int opt_iteration = args.opt_base + upd;
-      float acc[54];
+      float acc[27];
 #pragma unroll
-      for (int k = 0; k < 54; ++k) acc[k] = 0.0f;
+      for (int k = 0; k < 27; ++k) acc[k] = 0.0f;
       if (has_region && (args.phases & PH_REGION_GH)) {
-        // K2 region: RegionModality::CalculateGradientAndHessian (region_modality.cpp:485-558)
-        RegionIter it;
-        MakeRegionIter(body.rp, *ccam, sh.pose, corr, it);
-        const int n_lines = sh.n_items[0];
-        for (int i = tid; i < n_lines; i += kBlockThreads) {
-          if (rst[RF_VALID * lcap + i] == 0.0f) continue;
-          float cbx = rst[RF_CBX * lcap + i], cby = rst[RF_CBY * lcap + i], cbz = rst[RF_CBZ * lcap + i];
-          float x, y, z;
-          PoseApply(it.b2c, cbx, cby, cbz, x, y, z);
-          float fu_z = it.fu / z, fv_z = it.fv / z;
-          float xfu_z = x * fu_z, yfv_z = y * fv_z;
-          float nu = rst[RF_NU * lcap + i], nv = rst[RF_NV * lcap + i];
-          float ncts = rst[RF_NCTS * lcap + i];
-          float measured_variance = rst[RF_VAR * lcap + i];
-          float delta_cs = (nu * (xfu_z + it.ppu - rst[RF_CU * lcap + i]) + nv * (yfv_z + it.ppv - rst[RF_CV * lcap + i]) -
-                            rst[RF_DR * lcap + i]) * ncts;
-          float dll;
-          if (opt_iteration < body.rp.n_global_iterations) {
-            dll = (rst[RF_MEAN * lcap + i] - delta_cs) / measured_variance;
-          } else {
-            int upper = int(delta_cs + (float(kDistributionLength) + 1.0f) / 2.0f);
-            int lower = upper - 1;
-            if (upper <= 0 || upper >= kDistributionLength) continue;
-            dll = (logf(rst[(RF_DIST0 + upper) * lcap + i]) - logf(rst[(RF_DIST0 + lower) * lcap + i])) *
-                  body.rp.learning_rate / measured_variance;
-          }
-          float dc0 = ncts * nu * fu_z;
-          float dc1 = ncts * nv * fv_z;
-          float dc2 = ncts * (-nu * xfu_z - nv * yfv_z) / z;
-          float J[6];
-          J[3] = dc0 * it.b2c[0] + dc1 * it.b2c[4] + dc2 * it.b2c[8];
-          J[4] = dc0 * it.b2c[1] + dc1 * it.b2c[5] + dc2 * it.b2c[9];
-          J[5] = dc0 * it.b2c[2] + dc1 * it.b2c[6] + dc2 * it.b2c[10];
-          J[0] = cby * J[5] - cbz * J[4];
-          J[1] = cbz * J[3] - cbx * J[5];
-          J[2] = cbx * J[4] - cby * J[3];
-          float weight = body.rp.min_expected_variance / (ncts * ncts * it.variance);
-          float wg = weight * dll;
-          float wh = weight / measured_variance;
+        RegionIter rit;
+        MakeRegionIter(body.rp, *ccam, sh.pose, corr, rit);
 #pragma unroll
-          for (int r = 0; r < 6; ++r) {
-            acc[r] += wg * J[r];
-#pragma unroll
-            for (int c = 0; c <= r; ++c) acc[6 + Tri(r, c)] -= (wh * J[r]) * J[c];
-          }
-        }
+        for (int k = 0; k < K; ++k) RegionGradient(rit, body.rp, L[k], opt_iteration, acc);
       }
       if (has_depth && (args.phases & PH_DEPTH_GH)) {
-        // K2 depth: DepthModality::CalculateGradientAndHessian (depth_modality.cpp:333-381)
-        DepthIter it;
-        MakeDepthIter(body.dp, *dcam, sh.pose, corr, it);
-        const int n_points = sh.n_items[1];
-        for (int i = tid; i < n_points; i += kBlockThreads) {
-          if (dst[DF_VALID * pcap + i] == 0.0f) continue;
-          float yc0 = dst[DF_YX * pcap + i], yc1 = dst[DF_YY * pcap + i], yc2 = dst[DF_YZ * pcap + i];
-          float yb0, yb1, yb2;
-          PoseApply(it.c2b, yc0, yc1, yc2, yb0, yb1, yb2);
-          float n0 = dst[DF_NX * pcap + i], n1 = dst[DF_NY * pcap + i], n2 = dst[DF_NZ * pcap + i];
-          float epsilon = n0 * (dst[DF_CBX * pcap + i] - yb0) + n1 * (dst[DF_CBY * pcap + i] - yb1) +
-                          n2 * (dst[DF_CBZ * pcap + i] - yb2);
-          float cx[3] = {yb1 * n2 - yb2 * n1, yb2 * n0 - yb0 * n2, yb0 * n1 - yb1 * n0};
-          float weight = 1.0f / (it.standard_deviation * yc2);
-          float squared_weight = weight * weight;
-          float v[6] = {weight * cx[0], weight * cx[1], weight * cx[2], weight * n0, weight * n1, weight * n2};
-          float se = squared_weight * epsilon;
-          float nn[3] = {n0, n1, n2};
+        DepthIter dit;
+        MakeDepthIter(body.dp, *dcam, sh.pose, corr, dit);
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            acc[27 + r] -= se * cx[r];
-            acc[27 + 3 + r] -= se * nn[r];
-          }
-          // upper-triangle products v[r] * v[c], r <= c, stored at the mirrored lower index
-#pragma unroll
-          for (int c = 0; c < 6; ++c)
-#pragma unroll
-            for (int r = 0; r <= c; ++r) acc[27 + 6 + Tri(c, r)] -= v[r] * v[c];
-        }
+        for (int k = 0; k < K; ++k) DepthGradient(dit, P[k], acc);
       }
-      // warp-shuffle reduction of the 54 partial sums, then across warps through shared memory
+      // warp-shuffle reduction of the 27 partial sums, then one hop through shared memory
 #pragma unroll
-      for (int k = 0; k < 54; ++k) {
+      for (int k = 0; k < 27; ++k) {
         float v = acc[k];
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
         if (lane == 0) sh.red[warp][k] = v;
       }
       __syncthreads();
-      if (tid < 54) {
-        const bool mine = tid < 27 ? (args.phases & PH_REGION_GH) : (args.phases & PH_DEPTH_GH);
-        if (mine || !(args.phases & PH_LOAD_GH)) {
-          float v = sh.red[0][tid];
+      if (warp == 0) {
+        if (lane < 27) {
+          float v = sh.red[0][lane];
 #pragma unroll
-          for (int w = 1; w < kWarps; ++w) v += sh.red[w][tid];
-          sh.gh[tid] = v;
+          for (int w = 1; w < kW; ++w) v += sh.red[w][lane];
+          if (args.phases & PH_STORE_GH) {
+            if (args.phases & PH_REGION_GH) args.gh_region[27 * body_id + lane] = v;
+            if (args.phases & PH_DEPTH_GH) args.gh_depth[27 * body_id + lane] = v;
+          }
+          if (args.phases & PH_LOAD_GH)  // Link::CalculateGradientAndHessian (link.cpp:184-193): region, then depth
+            v = 0.0f + args.gh_region[27 * body_id + lane] + args.gh_depth[27 * body_id + lane];
+          if (args.phases & PH_SOLVE) {
+            // Optimizer: b = J^T g, a(lower) = -J^T H J with J = I6, a.diagonal() += tikhonov (optimizer.cpp:144-159)
+            if (lane < 6) {
+              sh.b[lane] = 0.0f + v;
+            } else {
+              int i, j;
+              TriInv(lane - 6, i, j);
+              float val = 0.0f - v;
+              if (i == j) val += (i < 3) ? body.tikhonov_rotation : body.tikhonov_translation;
+              sh.a[i * 6 + j] = val;
+              sh.a[j * 6 + i] = val;
+            }
+          }
+        }
+        if (args.phases & PH_SOLVE) {
+          __syncwarp();
+          SolveAndUpdateWarp(sh);
         }
       }
       __syncthreads();
-      if (args.phases & PH_STORE_GH) {
-        if (tid < 27 && (args.phases & PH_REGION_GH)) args.gh_region[27 * body_id + tid] = sh.gh[tid];
-        if (tid >= 27 && tid < 54 && (args.phases & PH_DEPTH_GH)) args.gh_depth[27 * body_id + tid - 27] = sh.gh[tid];
-      }
-      if (args.phases & PH_SOLVE) {
-        if (tid == 0) SolveAndUpdate(body, sh);
-        __syncthreads();
-      }
     }
   }
 
@@ -600,13 +906,41 @@ __global__ void __launch_bounds__(kBlockThreads) k_track(TrackArgs args) {
   if (args.phases & PH_SOLVE)
     if (tid < 12) args.poses[12 * body_id + tid] = sh.pose[tid];
   if (args.phases & PH_STORE_REGION) {
-    for (int k = tid; k < RF_COUNT * lcap; k += kBlockThreads) g_rst[k] = rst[k];
-    if (tid == 0) { counts[0] = sh.n_items[0]; counts[2] = sh.view[0]; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * T;
+      if (i < n_lines) {
+        g_rst[RF_CBX * lcap + i] = L[k].cbx; g_rst[RF_CBY * lcap + i] = L[k].cby; g_rst[RF_CBZ * lcap + i] = L[k].cbz;
+        g_rst[RF_CU * lcap + i] = L[k].cu; g_rst[RF_CV * lcap + i] = L[k].cv;
+        g_rst[RF_NU * lcap + i] = L[k].nu; g_rst[RF_NV * lcap + i] = L[k].nv;
+        g_rst[RF_VALID * lcap + i] = L[k].valid ? 1.0f : 0.0f;
+        if (L[k].valid) {
+          g_rst[RF_DR * lcap + i] = L[k].dr; g_rst[RF_NCTS * lcap + i] = L[k].ncts;
+          g_rst[RF_MEAN * lcap + i] = L[k].mean; g_rst[RF_VAR * lcap + i] = L[k].var;
+#pragma unroll
+          for (int d = 0; d < kDistributionLength; ++d) g_rst[(RF_DIST0 + d) * lcap + i] = L[k].dist[d];
+        }
+      }
+    }
+    if (tid == 0) { counts[0] = n_lines; counts[2] = view_r; }
   }
   if (args.phases & PH_STORE_DEPTH) {
-    for (int k = tid; k < DF_COUNT * pcap; k += kBlockThreads) g_dst[k] = dst[k];
-    if (tid == 0) { counts[1] = sh.n_items[1]; counts[3] = sh.view[1]; }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      const int i = tid + k * T;
+      if (i < n_points) {
+        g_dst[DF_CBX * pcap + i] = P[k].cbx; g_dst[DF_CBY * pcap + i] = P[k].cby; g_dst[DF_CBZ * pcap + i] = P[k].cbz;
+        g_dst[DF_NX * pcap + i] = P[k].nx; g_dst[DF_NY * pcap + i] = P[k].ny; g_dst[DF_NZ * pcap + i] = P[k].nz;
+        g_dst[DF_VALID * pcap + i] = P[k].valid ? 1.0f : 0.0f;
+        if (P[k].valid) {
+          g_dst[DF_YX * pcap + i] = P[k].yx; g_dst[DF_YY * pcap + i] = P[k].yy; g_dst[DF_YZ * pcap + i] = P[k].yz;
+        }
+      }
+    }
+    if (tid == 0) { counts[1] = n_points; counts[3] = view_d; }
   }
+  if (need_lut && !lut_ready) MbarWait(&sh.lut_bar, 0);  // never leave with a bulk copy in flight
+  if (!depth_ready) MbarWait(&sh.depth_bar, 0);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -634,7 +968,7 @@ __global__ void k_lut(const float* hist_f, const float* hist_b, float2* lut, int
 // + ColorHistograms::InitializeHistograms / UpdateHistograms (color_histograms.cpp:72-92,174-214).
 // One CTA per body. Counts are integer-valued floats (< 2^24), so atomic accumulation order and the
 // tree-shaped sum are exact; the blend h = h*(1-lr) + mem*(lr/sum) rounds as the reference does.
-// mode 0: StartModality (learning rate 1, also records first_iteration on the host side), 1: CalculateResults.
+// mode 0: StartModality (learning rate 1), 1: CalculateResults.
 // ---------------------------------------------------------------------------------------------
 struct HistArgs {
   const BodyDev* bodies;
@@ -673,7 +1007,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   const ModelDev& model = args.region_models[body.region_model];
   RegionIter it;
   MakeRegionIter(rp, cam, sh.pose, 0, it);
-  int view = ClosestView(model, it.b2c, sh);
+  int view, unused;
+  ClosestViews<kBlockThreads>(&model, it.b2c, nullptr, it.b2c, sh, view, unused);
   int n_lines = AdaptiveCount(rp.n_lines_max, rp.use_adaptive_coverage, rp.reference_contour_length,
                               __ldg(model.view_scalars + view), model.max_view_scalar, model.n_points);
   const float4* pts = model.points + size_t(view) * model.n_points * 2;

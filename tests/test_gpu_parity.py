@@ -193,3 +193,20 @@ def test_errors_are_loud(capi):
     with pytest.raises(capi.M3TBError):
         ctx.set_body(0, rp, None, None)
     ctx.close()
+
+
+@pytest.mark.parametrize("rot_deg,trans_m", [(3.0, 0.005), (9.0, 0.03)])
+def test_tiles_do_not_change_results(capi, synth, monkeypatch, rot_deg, trans_m):
+    """Shared-memory ROI tiles are a pure staging optimisation: with tiles on / off (M3TB_NO_TILES=1) every pose
+    is bit-identical, including when the pose moves so far (3 cm ~ 30 px) that samples leave the tile and are
+    served by the global-memory fallback."""
+    wl = synth.make_workload("c2", n_bodies=6, n_divides=4, seed=11, rot_deg=rot_deg, trans_m=trans_m)
+    poses = []
+    for no_tiles in ("0", "1"):
+        monkeypatch.setenv("M3TB_NO_TILES", no_tiles)
+        ctx = capi.context_from_workload(wl)
+        ctx.start_modalities(0)
+        ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
+        poses.append(ctx.get_poses())
+        ctx.close()
+    assert np.array_equal(poses[0].view(np.uint32), poses[1].view(np.uint32))
