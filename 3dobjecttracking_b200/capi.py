@@ -70,6 +70,7 @@ SYMBOLS = [
     "m3tb_start_modalities", "m3tb_calculate_results", "m3tb_region_correspondences",
     "m3tb_region_gradient_hessian", "m3tb_depth_correspondences", "m3tb_depth_gradient_hessian",
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
+    "m3tb_debug_phase_clocks",
 ]
 
 _lib = None
@@ -316,6 +317,12 @@ class Context:
         n = C.c_int(0)
         self._ck(self.L.m3tb_get_depth_points(self.h, body, out.ctypes.data_as(C.c_void_p), capacity, C.byref(n)))
         return out[:min(n.value, capacity)]
+
+    def phase_clocks(self, body, n=128):
+        out = np.zeros(n, np.int64)
+        self.L.m3tb_debug_phase_clocks.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        self._ck(self.L.m3tb_debug_phase_clocks(self.h, body, out.ctypes.data_as(C.c_void_p), n))
+        return out
 
     def get_closest_views(self, body):
         a, b = C.c_int(0), C.c_int(0)

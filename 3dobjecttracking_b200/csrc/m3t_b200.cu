@@ -23,7 +23,7 @@ struct ImagePool {
 };
 
 struct ModelAlloc {
-  float* orientations = nullptr;
+  float4* orientations = nullptr;
   float* view_scalars = nullptr;
   float4* points = nullptr;
 };
@@ -60,6 +60,7 @@ struct m3tb_ctx {
   int* d_counts = nullptr;
   float *d_gh_region = nullptr, *d_gh_depth = nullptr;
   size_t max_dyn_smem = 0;
+  long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
 };
 
@@ -224,6 +225,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   a.n_update = n_update;
   a.opt_base = opt_base;
   a.phases = phases;
+  a.phase_clock = ctx->d_phase_clock;
   // thread <-> line mapping: T threads per body, K lines and K points per thread (state in registers)
   const int items = std::max(ctx->line_cap, ctx->point_cap);
   bool lut_smem = true;  // normalised LUT staged in shared memory when every region body has <= 16 bins (32 KB)
@@ -308,17 +310,20 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
     if (scalars) sc[v] = scalars[v];
     max_scalar = std::max(max_scalar, sc[v]);
   }
-  CU(cudaMalloc(&al.orientations, sizeof(float) * 3 * n_views));
+  std::vector<float> ori4(size_t(n_views) * 4, 0.0f);
+  for (int v = 0; v < n_views; ++v)
+    for (int c = 0; c < 3; ++c) ori4[size_t(v) * 4 + c] = orientations[3 * v + c];
+  CU(cudaMalloc(&al.orientations, sizeof(float4) * n_views));
   CU(cudaMalloc(&al.view_scalars, sizeof(float) * n_views));
   CU(cudaMalloc(&al.points, sizeof(float) * packed.size()));
-  CU(cudaMemcpyAsync(al.orientations, orientations, sizeof(float) * 3 * n_views, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(al.orientations, ori4.data(), sizeof(float4) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.view_scalars, sc.data(), sizeof(float) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.points, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
   ModelDev& m = (region ? ctx->h_rmodels : ctx->h_dmodels)[model_id];
   m.n_views = n_views;
   m.n_points = n_points;
-  m.orientations = al.orientations;
+  m.orientations4 = al.orientations;
   m.view_scalars = al.view_scalars;
   m.points = al.points;
   m.max_view_scalar = max_scalar;
@@ -492,6 +497,8 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->private_color.assign(max_cameras, nullptr);
   ctx->private_depth.assign(max_cameras, nullptr);
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
+  const char* timing_env = std::getenv("M3TB_TIMING");
+  const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {
     CU(cudaSetDevice(device));
     CU(cudaMalloc(&ctx->d_bodies, sizeof(BodyDev) * max_bodies));
@@ -507,6 +514,10 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
     CU(cudaMemset(ctx->d_counts, 0, sizeof(int) * 4 * max_bodies));
     CU(cudaMemset(ctx->d_gh_region, 0, sizeof(float) * 27 * max_bodies));
     CU(cudaMemset(ctx->d_gh_depth, 0, sizeof(float) * 27 * max_bodies));
+    if (want_timing) {
+      CU(cudaMalloc(&ctx->d_phase_clock, sizeof(long long) * kPhaseSlots * max_bodies));
+      CU(cudaMemset(ctx->d_phase_clock, 0, sizeof(long long) * kPhaseSlots * max_bodies));
+    }
     return M3TB_OK;
   };
   int rc = alloc();
@@ -532,6 +543,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_dmodels); cudaFree(ctx->d_poses); cudaFree(ctx->d_counts); cudaFree(ctx->d_gh_region);
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
+  cudaFree(ctx->d_phase_clock);
   delete ctx;
   return M3TB_OK;
 }
@@ -894,6 +906,17 @@ int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int
     }
   }
   if (n_out) *n_out = counts[1];
+  return M3TB_OK;
+}
+
+int m3tb_debug_phase_clocks(m3tb_ctx* ctx, int body, long long* out, int capacity) {
+  CHECK_CTX();
+  if (!ctx->d_phase_clock) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "create the context with M3TB_TIMING=1 in the environment");
+  if (body < 0 || body >= ctx->max_bodies || !out) return Fail(ctx, M3TB_ERR_INVALID, "bad body");
+  int n = std::min(capacity, int(kPhaseSlots));
+  CU(cudaMemcpyAsync(out, ctx->d_phase_clock + size_t(body) * kPhaseSlots, sizeof(long long) * n, cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return M3TB_OK;
 }
 

@@ -18,6 +18,7 @@ constexpr int kFunctionLength = 8;       // region_modality.h:415
 constexpr int kDistributionLength = 12;  // region_modality.h:416
 constexpr int kLineSegments = kFunctionLength + kDistributionLength - 1;  // 19, region_modality.cpp:926
 constexpr int kMaxSchedule = 8;
+constexpr int kPhaseSlots = 256;
 constexpr int kBlockThreads = 256;
 constexpr int kWarps = kBlockThreads / 32;
 
@@ -48,7 +49,7 @@ struct CameraDev {
 
 struct ModelDev {
   int n_views, n_points;
-  const float* orientations;  // [n_views][3]
+  const float4* orientations4; // [n_views] (x, y, z, 0): one 16-byte load per view in the closest-view scan
   const float* view_scalars;  // [n_views] contour_length | surface_area
   const float4* points;       // [n_views][n_points][2]: region (cx,cy,cz,nx)(ny,nz,fg,bg); depth (cx,cy,cz,nx)(ny,nz,0,0)
   float max_view_scalar;
@@ -107,6 +108,7 @@ struct TrackArgs {
   int iteration, corr_begin, corr_end, n_update, opt_base;
   unsigned phases;
   int tile_bytes;               // dynamic shared memory available for the colour / depth ROI tiles (0: no tiling)
+  long long* phase_clock;       // optional [n_bodies][kPhaseSlots] clock64() stamps of thread 0 (profiling aid), or null
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -32,10 +32,15 @@ struct Tile {
 };
 
 struct Shared {
+  // pose products shared by all threads; recomputed by warp 0 after every pose update
+  float rb2c[12];                // colour-camera body2camera  (region_modality.cpp:1001-1002)
+  float db2c[12];                // depth-camera body2camera   (depth_modality.cpp:642-643)
+  float dc2b[12];                // its inverse                (depth_modality.cpp:644)
+  float cw2c[12], dw2c[12];      // world2camera of the two cameras (copied once per launch)
   Tile ctile, dtile;
   unsigned long long depth_bar;  // mbarrier of the depth-tile bulk copies
   float pose[12];                // body2world (Body::body2world_pose)
-  float red[kMaxWarps][27];      // per-warp partial sums: g[6] + H lower[21]
+  float red[kMaxWarps][32];      // per-warp partial sums: g[6] + H lower[21] (+5 pad)
   float a[36];                   // normal matrix, full symmetric
   float b[6];
   float x[6];
@@ -110,19 +115,34 @@ __device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelD
   constexpr int kW = T / 32;
   float best[2] = {-1.0f, -1.0f};
   int idx[2] = {0x7fffffff, 0x7fffffff};
+  float o[2][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
   bool nonzero[2] = {false, false};
+  int nv[2] = {0, 0};
+  const float4* ori[2] = {nullptr, nullptr};
+  if (m0) { nonzero[0] = ViewOrientation(b2c0, o[0][0], o[0][1], o[0][2]); nv[0] = nonzero[0] ? m0->n_views : 0; ori[0] = m0->orientations4; }
+  if (m1) { nonzero[1] = ViewOrientation(b2c1, o[1][0], o[1][1], o[1][2]); nv[1] = nonzero[1] ? m1->n_views : 0; ori[1] = m1->orientations4; }
+  const int nv_max = max(nv[0], nv[1]);
+  // both models share one pass: eight independent 16-byte loads in flight per thread
+  for (int v0 = tid; v0 < nv_max; v0 += 4 * T) {
+    float4 q[2][4];
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * T;
+        q[s][u] = v < nv[s] ? __ldg(ori[s] + v) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int v = v0 + u * T;
+        const float dot = o[s][0] * q[s][u].x + o[s][1] * q[s][u].y + o[s][2] * q[s][u].z;
+        if (v < nv[s] && dot > best[s]) { best[s] = dot; idx[s] = v; }
+      }
+  }
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    const ModelDev* m = s == 0 ? m0 : m1;
-    if (!m) continue;
-    float o0, o1, o2;
-    nonzero[s] = ViewOrientation(s == 0 ? b2c0 : b2c1, o0, o1, o2);
-    if (!nonzero[s]) continue;
-    const float* ori = m->orientations;
-    for (int v = tid; v < m->n_views; v += T) {
-      float dot = o0 * __ldg(ori + 3 * v) + o1 * __ldg(ori + 3 * v + 1) + o2 * __ldg(ori + 3 * v + 2);
-      if (dot > best[s]) { best[s] = dot; idx[s] = v; }
-    }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       float ob = __shfl_down_sync(0xffffffffu, best[s], off);
@@ -135,12 +155,11 @@ __device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelD
   int out[2] = {0, 0};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    if (!(s == 0 ? m0 : m1) || !nonzero[s]) continue;
     float rb = sh.best_dot[s][0];
     int ri = sh.best_idx[s][0];
 #pragma unroll
     for (int w = 1; w < kW; ++w) ArgmaxMerge(rb, ri, sh.best_dot[s][w], sh.best_idx[s][w]);
-    out[s] = ri == 0x7fffffff ? 0 : ri;
+    out[s] = (ri == 0x7fffffff || !nonzero[s]) ? 0 : ri;
   }
   __syncthreads();  // best_* are reused by the next call
   view0 = out[0];
@@ -161,9 +180,10 @@ struct RegionIter {  // PrecalculateCameraVariables / PoseVariables / IterationD
   float variance;
 };
 
-__device__ __forceinline__ void MakeRegionIter(const RegionParamsDev& rp, const CameraDev& cam, const float* pose,
+__device__ __forceinline__ void MakeRegionIter(const RegionParamsDev& rp, const CameraDev& cam, const float* b2c,
                                                int corr_iteration, RegionIter& it) {
-  PoseMul(cam.w2c, pose, it.b2c);  // region_modality.cpp:1001-1002
+#pragma unroll
+  for (int i = 0; i < 12; ++i) it.b2c[i] = b2c[i];
   it.fu = cam.fu; it.fv = cam.fv; it.ppu = cam.ppu; it.ppv = cam.ppv;
   it.w_m1 = cam.width - 1; it.h_m1 = cam.height - 1; it.w_m2 = cam.width - 2; it.h_m2 = cam.height - 2;
   it.scale = LastValid(rp.scales, rp.n_scales, corr_iteration);  // :1011-1023
@@ -204,6 +224,68 @@ template <bool LUT_SMEM>
 __device__ __forceinline__ float2 LutFetch(const float2* __restrict__ lut_g, const float2* lut_s, int idx) {
   if (LUT_SMEM) return lut_s[idx];
   return __ldg(lut_g + idx);
+}
+
+// Hot gather: every sample of the line is inside the shared-memory tile. S > 0: compile-time scale, the S pixels
+// of a segment are unrolled (loads batched, multiplications still in pixel order); S == 0: run-time scale.
+template <bool LUT_SMEM, int S>
+__device__ __forceinline__ void GatherFast(int scale, int base, float minor_f, float step, int stride_major,
+                                           int stride_minor, const uint16_t* tile_px, const float2* __restrict__ lut_g,
+                                           const float2* lut_s, float (&sf)[kLineSegments], float (&sb)[kLineSegments]) {
+#pragma unroll
+  for (int s = 0; s < kLineSegments; ++s) {
+    float pf = 1.0f, pb = 1.0f;
+    if (S > 0) {
+      int idx[S > 0 ? S : 1];
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        idx[k] = tile_px[base + int(minor_f) * stride_minor];
+        base += stride_major;
+        minor_f += step;
+      }
+      float2 l[S > 0 ? S : 1];
+#pragma unroll
+      for (int k = 0; k < S; ++k) l[k] = LutFetch<LUT_SMEM>(lut_g, lut_s, idx[k]);  // normalised per bin (:1575-1598)
+#pragma unroll
+      for (int k = 0; k < S; ++k) { pf *= l[k].x; pb *= l[k].y; }
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < scale; ++k) {
+        const int idx = tile_px[base + int(minor_f) * stride_minor];
+        const float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);
+        pf *= l.x;
+        pb *= l.y;
+        base += stride_major;
+        minor_f += step;
+      }
+    }
+    sf[s] = pf;
+    sb[s] = pb;
+  }
+}
+
+// Generic (rare) gather: any sample may lie outside the tile. Kept out of line so that the hot loop stays small.
+template <bool LUT_SMEM>
+__device__ __noinline__ void GatherSlow(int scale, int bs, int nb, bool horizontal, int major, float minor_f, float step,
+                                        const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
+                                        const uint16_t* tile_px, const float2* __restrict__ lut_g, const float2* lut_s,
+                                        float* sf, float* sb) {
+#pragma unroll 1
+  for (int s = 0; s < kLineSegments; ++s) {
+    float pf = 1.0f, pb = 1.0f;
+#pragma unroll 1
+    for (int k = 0; k < scale; ++k) {
+      const int minor = int(minor_f);
+      const int idx = PixelBin(tile, tile_px, img, pitch, bs, nb, horizontal ? major : minor, horizontal ? minor : major);
+      const float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);
+      pf *= l.x;
+      pb *= l.y;
+      ++major;
+      minor_f += step;
+    }
+    sf[s] = pf;
+    sb[s] = pb;
+  }
 }
 
 template <bool LUT_SMEM>
@@ -249,22 +331,34 @@ __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionPar
   if (major < 0 || major_end > major_m1 || int(minor_f) < 0 || int(minor_f) > minor_m1 || int(minor_f_end) < 1 ||
       int(minor_f_end) > minor_m2)
     return;
-  const int bs = rp.bitshift, nb = rp.n_bins;
   float sf[kLineSegments], sb[kLineSegments];
+  {
+    // Is the whole line inside the shared-memory tile? (+-1 on the minor axis for the rounding of the running sum)
+    const int mi0 = int(minor_f), mi1 = int(minor_f_end);
+    const int minor_lo = min(mi0, mi1) - 1, minor_hi = max(mi0, mi1) + 1;
+    const int x_lo = horizontal ? major : minor_lo, x_hi = horizontal ? major_end : minor_hi;
+    const int y_lo = horizontal ? minor_lo : major, y_hi = horizontal ? minor_hi : major_end;
+    const bool inside = x_lo >= tile.x0 && x_hi < tile.x0 + tile.w && y_lo >= tile.y0 && y_hi < tile.y0 + tile.h;
+    if (inside) {
+      // fast path: no per-sample bounds checks; tile element index = base + int(minor_f) * stride_minor.
+      // For the usual scales the pixels of a segment are unrolled so that their loads are issued together.
+      const int stride_major = horizontal ? 1 : tile.pitch;
+      const int stride_minor = horizontal ? tile.pitch : 1;
+      int base = horizontal ? (major - tile.x0) - tile.y0 * tile.pitch : (major - tile.y0) * tile.pitch - tile.x0;
+      switch (it.scale) {
+        case 1: GatherFast<LUT_SMEM, 1>(1, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, sf, sb); break;
+        case 2: GatherFast<LUT_SMEM, 2>(2, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, sf, sb); break;
+        case 4: GatherFast<LUT_SMEM, 4>(4, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, sf, sb); break;
+        case 6: GatherFast<LUT_SMEM, 6>(6, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, sf, sb); break;
+        default: GatherFast<LUT_SMEM, 0>(it.scale, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, sf, sb); break;
+      }
+    } else {
+      float tf[kLineSegments], tb[kLineSegments];
+      GatherSlow<LUT_SMEM>(it.scale, rp.bitshift, rp.n_bins, horizontal, major, minor_f, step, img, pitch, tile, tile_px,
+                           lut_g, lut_s, tf, tb);
 #pragma unroll
-  for (int s = 0; s < kLineSegments; ++s) {
-    float pf = 1.0f, pb = 1.0f;
-    for (int k = 0; k < it.scale; ++k) {
-      const int minor = int(minor_f);
-      const int idx = PixelBin(tile, tile_px, img, pitch, bs, nb, horizontal ? major : minor, horizontal ? minor : major);
-      float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);  // normalised per bin (MultiplyPixelColorProbability :1575-1598)
-      pf *= l.x;
-      pb *= l.y;
-      ++major;
-      minor_f += step;
+      for (int s = 0; s < kLineSegments; ++s) { sf[s] = tf[s]; sb[s] = tb[s]; }
     }
-    sf[s] = pf;
-    sb[s] = pb;
   }
   if (!(n_major > 0.0f)) {  // segments are filled back to front (:1470-1484)
 #pragma unroll
@@ -374,10 +468,10 @@ struct DepthIter {
   int max_n_strides;
 };
 
-__device__ __forceinline__ void MakeDepthIter(const DepthParamsDev& dp, const CameraDev& cam, const float* pose,
-                                              int corr_iteration, DepthIter& it) {
-  PoseMul(cam.w2c, pose, it.b2c);  // depth_modality.cpp:641-646
-  PoseInverse(it.b2c, it.c2b);
+__device__ __forceinline__ void MakeDepthIter(const DepthParamsDev& dp, const CameraDev& cam, const float* b2c,
+                                              const float* c2b, int corr_iteration, DepthIter& it) {
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { it.b2c[i] = b2c[i]; it.c2b[i] = c2b[i]; }
   it.fu = cam.fu; it.fv = cam.fv; it.ppu = cam.ppu; it.ppv = cam.ppv;
   it.depth_scale = cam.depth_scale;
   it.w_m1 = cam.width - 1; it.h_m1 = cam.height - 1;
@@ -390,6 +484,27 @@ struct PointState {  // DepthModality::DataPoint (depth_modality.h:139-150)
   float cbx, cby, cbz, nx, ny, nz, yx, yy, yz;
   bool valid;
 };
+
+__device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int u_max, int v_min, int v_max, int stride,
+                                             float min_depth_value, float max_depth_value, float x, float y, float z,
+                                             const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
+                                             const uint16_t* tile_px, float* r) {
+  float best = r[0], bx = r[1], by = r[2], bz = r[3];
+  for (int v = v_min; v <= v_max; v += stride) {
+    for (int u = u_min; u <= u_max; u += stride) {
+      float depth = float(DepthAt(tile, tile_px, img, pitch, u, v));
+      if (depth > min_depth_value && depth < max_depth_value) {
+        depth *= it.depth_scale;
+        float tx = (float(u) - it.ppu) * depth / it.fu;
+        float ty = (float(v) - it.ppv) * depth / it.fv;
+        float dx = tx - x, dy = ty - y, dz = depth - z;
+        float d2 = dx * dx + dy * dy + dz * dz;
+        if (d2 < best) { bx = tx; by = ty; bz = depth; best = d2; }
+      }
+    }
+  }
+  r[0] = best; r[1] = bx; r[2] = by; r[3] = bz;
+}
 
 __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
                                            const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
@@ -427,18 +542,30 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
   float min_considered_distance_square = considered_distance * considered_distance;
   float best = min_considered_distance_square;
   float bx = 0.0f, by = 0.0f, bz = 0.0f;
-  for (int v = v_min; v <= v_max; v += stride) {
-    for (int u = u_min; u <= u_max; u += stride) {
-      float depth = float(DepthAt(tile, tile_px, img, pitch, u, v));
-      if (depth > min_depth_value && depth < max_depth_value) {
-        depth *= it.depth_scale;
-        float tx = (float(u) - it.ppu) * depth / it.fu;
-        float ty = (float(v) - it.ppv) * depth / it.fv;
-        float dx = tx - x, dy = ty - y, dz = depth - z;
-        float d2 = dx * dx + dy * dy + dz * dz;
-        if (d2 < best) { bx = tx; by = ty; bz = depth; best = d2; }
+  const bool inside = u_min >= tile.x0 && u_max < tile.x0 + tile.w && v_min >= tile.y0 && v_max < tile.y0 + tile.h;
+  if (inside) {
+    const uint16_t* trow = tile_px + (v_min - tile.y0) * tile.pitch - tile.x0;
+    const int row_step = stride * tile.pitch;
+    for (int v = v_min; v <= v_max; v += stride, trow += row_step) {
+      const float vy = float(v) - it.ppv;
+#pragma unroll 4
+      for (int u = u_min; u <= u_max; u += stride) {
+        float depth = float(trow[u]);
+        if (depth > min_depth_value && depth < max_depth_value) {
+          depth *= it.depth_scale;
+          float tx = (float(u) - it.ppu) * depth / it.fu;
+          float ty = vy * depth / it.fv;
+          float dx = tx - x, dy = ty - y, dz = depth - z;
+          float d2 = dx * dx + dy * dy + dz * dz;
+          if (d2 < best) { bx = tx; by = ty; bz = depth; best = d2; }
+        }
       }
     }
+  } else {
+    float r[4] = {best, bx, by, bz};
+    DepthSearchSlow(it, u_min, u_max, v_min, v_max, stride, min_depth_value, max_depth_value, x, y, z, img, pitch, tile,
+                    tile_px, r);
+    best = r[0]; bx = r[1]; by = r[2]; bz = r[3];
   }
   if (best == min_considered_distance_square) return;
   P.yx = bx; P.yy = by; P.yz = bz;
@@ -469,6 +596,11 @@ __device__ __forceinline__ void DepthGradient(const DepthIter& it, const PointSt
     for (int r = 0; r <= c; ++r) acc[6 + Tri(c, r)] -= v[r] * v[c];
 }
 
+#define M3TB_STAMP()                                                              \
+  do {                                                                            \
+    if (stamp_ptr && tid == 0 && stamp_i < kPhaseSlots) stamp_ptr[stamp_i++] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // K4: Optimizer::CalculateOptimization for a rigid body (optimizer.cpp:144-167): Eigen LDLT<Lower>
 // (diagonal pivoting, left-looking) restated for n = 6, then Link::UpdatePoses (link.cpp:205-241).
@@ -482,9 +614,10 @@ __device__ __forceinline__ void ExpSkew(const float* w, float* r) {
   // (link.cpp:224), the two agree to < 1e-7 for |w| <= 1 (tests/test_oracle_math.py).
   float t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   float a, b;
-  if (t2 < 1e-8f) {
-    a = 1.0f - t2 / 6.0f;
-    b = 0.5f - t2 / 24.0f;
+  if (t2 < 0.01f) {
+    // |w| < 0.1 rad (every realistic Gauss-Newton step): truncated series, remainder < 3e-14 relative
+    a = 1.0f + t2 * (-1.0f / 6.0f + t2 * (1.0f / 120.0f + t2 * (-1.0f / 5040.0f)));
+    b = 0.5f + t2 * (-1.0f / 24.0f + t2 * (1.0f / 720.0f + t2 * (-1.0f / 40320.0f)));
   } else {
     float t = sqrtf(t2);
     float sh = sinf(0.5f * t);
@@ -501,85 +634,129 @@ __device__ __forceinline__ void ExpSkew(const float* w, float* r) {
   for (int k = 0; k < 9; ++k) r[k] = ((k % 4 == 0) ? 1.0f : 0.0f) + a * A[k] + b * A2[k];
 }
 
-// sh.a (full symmetric 6x6) and sh.b must be visible to the calling warp. Returns true if the pose was updated.
-__device__ __forceinline__ bool SolveAndUpdateWarp(Shared& sh) {
+// Pose products every thread needs (one evaluation per pose instead of one per thread), SIMD across the
+// lanes of one warp: lanes 0-11 produce the 12 entries of the colour-camera body2camera, lanes 12-23 those of
+// the depth-camera body2camera, then lanes 0-8 the cofactor inverse. sh.pose, sh.cw2c, sh.dw2c must be visible.
+// Expressions and summation order are those of PoseMul / PoseInverse (Eigen Affine product / inverse).
+__device__ __forceinline__ void PoseProductsWarp(bool has_color, bool has_depth, Shared& sh) {
+  const int lane = threadIdx.x & 31;
+  {
+    const int e = lane < 12 ? lane : (lane < 24 ? lane - 12 : 0);
+    const int i = e >> 2, j = e & 3;
+    const bool second = lane >= 12;
+    const float* W = second ? sh.dw2c : sh.cw2c;
+    const float* P = sh.pose;
+    float out = W[4 * i + 0] * P[j] + W[4 * i + 1] * P[4 + j] + W[4 * i + 2] * P[8 + j];
+    if (j == 3) out += W[4 * i + 3];
+    if (lane < 12 && has_color) sh.rb2c[e] = out;
+    if (lane >= 12 && lane < 24 && has_depth) sh.db2c[e] = out;
+  }
+  __syncwarp();
+  if (has_depth) {
+    const float* M = sh.db2c;
+    auto m = [&](int r, int c) { return M[4 * r + c]; };
+    auto cof = [&](int a, int b) {
+      const int a1 = (a + 1) % 3, a2 = (a + 2) % 3, b1 = (b + 1) % 3, b2 = (b + 2) % 3;
+      return m(a1, b1) * m(a2, b2) - m(a1, b2) * m(a2, b1);
+    };
+    const float c00 = cof(0, 0), c10 = cof(1, 0), c20 = cof(2, 0);
+    const float det = c00 * m(0, 0) + c10 * m(1, 0) + c20 * m(2, 0);
+    const float invdet = 1.0f / det;
+    const int e = lane < 9 ? lane : 0;
+    const int i = e / 3, j = e - 3 * i;
+    const float inv = cof(j, i) * invdet;  // inverse(i, j) = cofactor(j, i) / det
+    if (lane < 9) sh.dc2b[4 * i + j] = inv;
+    __syncwarp();
+    if (lane < 3) {
+      const float* I = sh.dc2b;
+      sh.dc2b[4 * lane + 3] = (-I[4 * lane + 0]) * M[3] + (-I[4 * lane + 1]) * M[7] + (-I[4 * lane + 2]) * M[11];
+    }
+  }
+}
+
+// sh.a (full symmetric 6x6) and sh.b must be visible to the calling warp (all 32 lanes call this).
+// Lane r < 6 owns row r of the permuted matrix; lanes >= 6 shadow row 5 and never publish anything. The code is
+// deliberately compact (it runs on one warp while 15 others wait at the barrier, so its instruction-fetch
+// latency is fully exposed): one division per lane per elimination step, shuffles instead of unrolled copies.
+// Returns true if the pose was updated.
+__device__ __forceinline__ bool SolveAndUpdateWarp(Shared& sh, const CameraDev* ccam, const CameraDev* dcam,
+                                                   long long* stamp_ptr, int& stamp_i) {
+  const int tid = threadIdx.x;
   constexpr int n = 6;
-  // transposition sequence from the original diagonal (first maximum wins)
-  float dv[n];
-  int pm[n];
-#pragma unroll
-  for (int i = 0; i < n; ++i) { dv[i] = fabsf(sh.a[i * n + i]); pm[i] = i; }
+  constexpr unsigned kFull = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const int r = lane < n ? lane : n - 1;
+  // 1. transposition sequence from the ORIGINAL diagonal: the left-looking factorisation never touches a
+  //    diagonal entry before it is chosen as pivot (Eigen LDLT.h, "Find largest diagonal element"; first max wins)
+  //    |d| >= 0, so the float bit patterns order like the values: one REDUX.MAX + one ballot per step.
+  unsigned key = lane < n ? __float_as_uint(fabsf(sh.a[r * (n + 1)])) : 0u;
+  int pm = r;
 #pragma unroll
   for (int k = 0; k < n - 1; ++k) {
-    int p = k;
-    float big = dv[k];
-#pragma unroll
-    for (int i = k + 1; i < n; ++i)
-      if (dv[i] > big) { big = dv[i]; p = i; }
-#pragma unroll
-    for (int c = k + 1; c < n; ++c)
-      if (p == c) {
-        float t = dv[k]; dv[k] = dv[c]; dv[c] = t;
-        int ti = pm[k]; pm[k] = pm[c]; pm[c] = ti;
-      }
+    const bool eligible = lane >= k && lane < n;
+    const unsigned big = __reduce_max_sync(kFull, eligible ? key : 0u);
+    const int p = __ffs(__ballot_sync(kFull, eligible && key == big)) - 1;
+    const unsigned key_k = __shfl_sync(kFull, key, k), key_p = __shfl_sync(kFull, key, p);
+    const int pm_k = __shfl_sync(kFull, pm, k), pm_p = __shfl_sync(kFull, pm, p);
+    if (lane == k) { key = key_p; pm = pm_p; }
+    else if (lane == p) { key = key_k; pm = pm_k; }
   }
-  // gather P A P^T (lower) and P b
-  float A[n][n];
-  float dst[n];
+  M3TB_STAMP();  // pivot order
+  // 2. gather row r of P A P^T and entry r of P b
+  float A[n];
 #pragma unroll
-  for (int i = 0; i < n; ++i) {
-#pragma unroll
-    for (int j = 0; j <= i; ++j) A[i][j] = sh.a[pm[i] * n + pm[j]];
-    dst[i] = sh.b[pm[i]];
-  }
-  // ldlt_inplace<Lower>::unblocked
+  for (int j = 0; j < n; ++j) A[j] = sh.a[pm * n + __shfl_sync(kFull, pm, j)];
+  float dst = sh.b[pm];
+  // 3. ldlt_inplace<Lower>::unblocked, rows in parallel
+  float D[n];
   bool zero_matrix = false;
 #pragma unroll
   for (int k = 0; k < n; ++k) {
-    if (!zero_matrix) {
-      if (k > 0) {
-        float temp[n];
+    if (k > 0) {
+      float acc = 0.0f;  // sum_j A(i,j) * temp_j,  temp_j = D_j * A(k,j)
 #pragma unroll
-        for (int j = 0; j < k; ++j) temp[j] = A[j][j] * A[k][j];
-        float dot = 0.0f;
-#pragma unroll
-        for (int j = 0; j < k; ++j) dot += A[k][j] * temp[j];
-        A[k][k] -= dot;
-#pragma unroll
-        for (int i = k + 1; i < n; ++i) {
-          float acc = 0.0f;
-#pragma unroll
-          for (int j = 0; j < k; ++j) acc += A[i][j] * temp[j];
-          A[i][k] -= acc;
-        }
+      for (int j = 0; j < k; ++j) {
+        const float temp = D[j] * __shfl_sync(kFull, A[j], k);
+        acc += A[j] * temp;
       }
-      float akk = A[k][k];
-      bool pivot_is_valid = fabsf(akk) > 0.0f;
-      if (k == 0 && !pivot_is_valid) zero_matrix = true;
-      if (!zero_matrix && pivot_is_valid) {
-#pragma unroll
-        for (int i = k + 1; i < n; ++i) A[i][k] /= akk;
-      }
+      if (!zero_matrix && r >= k) A[k] -= acc;
     }
+    const float akk = __shfl_sync(kFull, A[k], k);
+    const bool pivot_is_valid = fabsf(akk) > 0.0f;
+    if (k == 0 && !pivot_is_valid) zero_matrix = true;
+    D[k] = akk;
+    if (!zero_matrix && pivot_is_valid && r > k) A[k] /= akk;
   }
-  // LDLT::_solve_impl
+  M3TB_STAMP();  // factorisation
+  // 4. LDLT::_solve_impl: L^-1, D^-1 (tolerance 1/highest), L^-T, P^T
 #pragma unroll
-  for (int j = 0; j < n; ++j)
-#pragma unroll
-    for (int i = j + 1; i < n; ++i) dst[i] -= A[i][j] * dst[j];
-  const float tolerance = 1.0f / 3.402823466e+38f;
-#pragma unroll
-  for (int i = 0; i < n; ++i) {
-    if (fabsf(A[i][i]) > tolerance) dst[i] /= A[i][i];
-    else dst[i] = 0.0f;
+  for (int j = 0; j < n; ++j) {
+    const float dj = __shfl_sync(kFull, dst, j);
+    if (r > j) dst -= A[j] * dj;
   }
+  {
+    float dr = D[0];
 #pragma unroll
-  for (int j = n - 1; j >= 0; --j)
-#pragma unroll
-    for (int i = 0; i < j; ++i) dst[i] -= A[j][i] * dst[j];
-#pragma unroll
-  for (int i = 0; i < n; ++i) sh.x[pm[i]] = dst[i];  // P^T; every lane stores the same values
+    for (int i = 1; i < n; ++i) dr = (r == i) ? D[i] : dr;
+    const float tolerance = 1.0f / 3.402823466e+38f;
+    if (fabsf(dr) > tolerance) dst /= dr;
+    else dst = 0.0f;
+  }
   __syncwarp();
+  if (lane < n) {
+#pragma unroll
+    for (int j = 0; j < n; ++j) sh.a[r * n + j] = A[j];  // publish L for the transposed solve
+  }
+  __syncwarp();
+#pragma unroll
+  for (int j = n - 1; j >= 1; --j) {
+    const float dj = __shfl_sync(kFull, dst, j);
+    const float lji = sh.a[j * n + r];
+    if (r < j) dst -= lji * dj;
+  }
+  if (lane < n) sh.x[pm] = dst;
+  __syncwarp();
+  M3TB_STAMP();  // substitution
   float theta[n];
   bool nan = false;
 #pragma unroll
@@ -587,16 +764,20 @@ __device__ __forceinline__ bool SolveAndUpdateWarp(Shared& sh) {
   if (nan) return false;  // optimizer.cpp:165
   float e[9];
   ExpSkew(theta, e);
+  M3TB_STAMP();  // exp
   float var[12] = {e[0], e[1], e[2], theta[3], e[3], e[4], e[5], theta[4], e[6], e[7], e[8], theta[5]};
   float cur[12], np[12];
 #pragma unroll
   for (int i = 0; i < 12; ++i) cur[i] = sh.pose[i];
   PoseMul(cur, var, np);  // link2world * [exp | t] (link.cpp:222-238, body2joint = I)
   __syncwarp();
-  if ((threadIdx.x & 31) == 0) {
+  if (lane == 0) {
 #pragma unroll
     for (int i = 0; i < 12; ++i) sh.pose[i] = np[i];
   }
+  __syncwarp();
+  PoseProductsWarp(ccam != nullptr, dcam != nullptr, sh);
+  M3TB_STAMP();  // pose products
   return true;
 }
 
@@ -642,6 +823,7 @@ __device__ __forceinline__ void FitTile(Tile& t, int budget, int align_x) {
 // ---------------------------------------------------------------------------------------------
 // The fused kernel
 // ---------------------------------------------------------------------------------------------
+
 template <int T, int K, bool LUT_SMEM>
 __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ TrackArgs args) {
   extern __shared__ __align__(128) unsigned char dyn[];
@@ -659,6 +841,9 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   const float2* lut_g = args.lut + size_t(body_id) * args.lut_stride;
   const float2* lut_s = reinterpret_cast<const float2*>(dyn);
 
+  long long* stamp_ptr = args.phase_clock ? args.phase_clock + size_t(body_id) * kPhaseSlots : nullptr;
+  int stamp_i = 0;
+  M3TB_STAMP();
   // ---- prologue: pose, LUT bulk copy, ROI tiles ----------------------------------------------------
   const CameraDev* ccam = has_region ? &args.color_cams[body.color_camera] : nullptr;
   const CameraDev* dcam = has_depth ? &args.depth_cams[body.depth_camera] : nullptr;
@@ -667,6 +852,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   const bool do_rcorr = has_region && (args.phases & PH_REGION_CORR);
   const bool do_dcorr = has_depth && (args.phases & PH_DEPTH_CORR);
   if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
+  if (tid >= 32 && tid < 44 && ccam) sh.cw2c[tid - 32] = ccam->w2c[tid - 32];
+  if (tid >= 64 && tid < 76 && dcam) sh.dw2c[tid - 64] = dcam->w2c[tid - 64];
   const bool need_lut = LUT_SMEM && do_rcorr;
   const unsigned lut_bytes = LUT_SMEM ? unsigned(16 * 16 * 16 * sizeof(float2)) : 0u;
   if (tid == 0) {
@@ -674,6 +861,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     MbarInit(&sh.depth_bar, 1);
   }
   __syncthreads();
+  if (warp == 0) PoseProductsWarp(ccam != nullptr, dcam != nullptr, sh);
   if (need_lut && tid == 0) {
     const unsigned bytes = unsigned(body.rp.n_bins * body.rp.n_bins * body.rp.n_bins) * sizeof(float2);
     MbarExpectTx(&sh.lut_bar, bytes);
@@ -736,19 +924,33 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     const int n_groups = groups_per_row * ctile.h;
     const int bs = body.rp.bitshift, nb = body.rp.n_bins;
     uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
-    for (int g = tid; g < n_groups; g += T) {
-      const int r = g / groups_per_row, c = g - r * groups_per_row;
-      const unsigned* src = reinterpret_cast<const unsigned*>(ccam->image + size_t(ctile.y0 + r) * ccam->pitch +
-                                                              size_t(ctile.x0 + 4 * c) * 3u);
-      const unsigned w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
-      auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
-        return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
-      };
-      const unsigned i0 = bin(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-      const unsigned i1 = bin(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
-      const unsigned i2 = bin((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
-      const unsigned i3 = bin((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
-      out[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+    auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
+      return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
+    };
+    for (int g0 = tid; g0 < n_groups; g0 += 4 * T) {  // 12 independent word loads in flight per thread
+      unsigned w[4][3];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int g = g0 + u * T;
+        if (g < n_groups) {
+          const int r = g / groups_per_row, c = g - r * groups_per_row;
+          const unsigned* src = reinterpret_cast<const unsigned*>(ccam->image + size_t(ctile.y0 + r) * ccam->pitch +
+                                                                  size_t(ctile.x0 + 4 * c) * 3u);
+          w[u][0] = __ldg(src); w[u][1] = __ldg(src + 1); w[u][2] = __ldg(src + 2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int g = g0 + u * T;
+        if (g < n_groups) {
+          const unsigned w0 = w[u][0], w1 = w[u][1], w2 = w[u][2];
+          const unsigned i0 = bin(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+          const unsigned i1 = bin(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+          const unsigned i2 = bin((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+          const unsigned i3 = bin((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+          out[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+        }
+      }
     }
     __syncthreads();
   }
@@ -790,20 +992,17 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   }
 
   bool lut_ready = !need_lut;
+  M3TB_STAMP();  // prologue done
 
   for (int corr = args.corr_begin; corr < args.corr_end; ++corr) {
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr || do_dcorr) {
       int v0, v1;
-      {
-        float b2c_r[12], b2c_d[12];
-        if (do_rcorr) PoseMul(ccam->w2c, sh.pose, b2c_r);
-        if (do_dcorr) PoseMul(dcam->w2c, sh.pose, b2c_d);
-        ClosestViews<T>(do_rcorr ? rmodel : nullptr, b2c_r, do_dcorr ? dmodel : nullptr, b2c_d, sh, v0, v1);
-      }
+      ClosestViews<T>(do_rcorr ? rmodel : nullptr, sh.rb2c, do_dcorr ? dmodel : nullptr, sh.db2c, sh, v0, v1);
+      M3TB_STAMP();  // closest views
       if (do_rcorr) {
         RegionIter rit;
-        MakeRegionIter(body.rp, *ccam, sh.pose, corr, rit);
+        MakeRegionIter(body.rp, *ccam, sh.rb2c, corr, rit);
         view_r = v0;
         n_lines = AdaptiveCount(body.rp.n_lines_max, body.rp.use_adaptive_coverage, body.rp.reference_contour_length,
                                 __ldg(rmodel->view_scalars + view_r), rmodel->max_view_scalar, rmodel->n_points);
@@ -820,9 +1019,10 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
           }
         }
       }
+      M3TB_STAMP();  // region lines (thread 0's own line)
       if (do_dcorr) {
         DepthIter dit;
-        MakeDepthIter(body.dp, *dcam, sh.pose, corr, dit);
+        MakeDepthIter(body.dp, *dcam, sh.db2c, sh.dc2b, corr, dit);
         view_d = v1;
         n_points = AdaptiveCount(body.dp.n_points_max, body.dp.use_adaptive_coverage, body.dp.reference_surface_area,
                                  __ldg(dmodel->view_scalars + view_d), dmodel->max_view_scalar, dmodel->n_points);
@@ -841,6 +1041,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
       }
     }
 
+    M3TB_STAMP();  // depth points (thread 0's own point)
     // ---------------- n_update x (CalculateGradientAndHessian + CalculateOptimization) ---------
     for (int upd = 0; upd < args.n_update; ++upd) {
       const int opt_iteration = args.opt_base + upd;
@@ -849,56 +1050,72 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
       for (int k = 0; k < 27; ++k) acc[k] = 0.0f;
       if (has_region && (args.phases & PH_REGION_GH)) {
         RegionIter rit;
-        MakeRegionIter(body.rp, *ccam, sh.pose, corr, rit);
+        MakeRegionIter(body.rp, *ccam, sh.rb2c, corr, rit);
 #pragma unroll
         for (int k = 0; k < K; ++k) RegionGradient(rit, body.rp, L[k], opt_iteration, acc);
       }
       if (has_depth && (args.phases & PH_DEPTH_GH)) {
         DepthIter dit;
-        MakeDepthIter(body.dp, *dcam, sh.pose, corr, dit);
+        MakeDepthIter(body.dp, *dcam, sh.db2c, sh.dc2b, corr, dit);
 #pragma unroll
         for (int k = 0; k < K; ++k) DepthGradient(dit, P[k], acc);
       }
-      // warp-shuffle reduction of the 27 partial sums, then one hop through shared memory
+      // Warp reduction by recursive halving: the 27 sums are padded to 32; at each of the 5 butterfly steps a
+      // lane keeps one half of its values and hands the other half to its partner, so 31 shuffle+add pairs per
+      // lane replace the 135 of a value-by-value tree, and lane l ends up with the warp total of value kSlot(l).
+      {
+        float v[32];
 #pragma unroll
-      for (int k = 0; k < 27; ++k) {
-        float v = acc[k];
+        for (int k = 0; k < 32; ++k) v[k] = k < 27 ? acc[k] : 0.0f;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
-        if (lane == 0) sh.red[warp][k] = v;
+        for (int half = 16; half >= 1; half >>= 1) {
+          const bool upper = (lane & half) != 0;
+#pragma unroll
+          for (int k = 0; k < half; ++k) {
+            const float send = upper ? v[k] : v[k + half];
+            const float keep = upper ? v[k + half] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+          }
+        }
+        // value index held by this lane: bit b of the index is set iff lane bit b is set (same bit, same weight)
+        sh.red[warp][lane] = v[0];
       }
+      M3TB_STAMP();  // accumulate + warp reduce
       __syncthreads();
+      M3TB_STAMP();  // all warps arrived
       if (warp == 0) {
-        if (lane < 27) {
-          float v = sh.red[0][lane];
+        // Branch-free on purpose: a divergent branch here would leave the warp split when it reaches the
+        // full-mask shuffles of the solve (the compiler then runs their slow divergent path). Lanes >= 27
+        // shadow lane 26 and redundantly store the same values to the same addresses.
+        const int l = lane < 27 ? lane : 26;
+        float v = sh.red[0][l];
 #pragma unroll
-          for (int w = 1; w < kW; ++w) v += sh.red[w][lane];
-          if (args.phases & PH_STORE_GH) {
-            if (args.phases & PH_REGION_GH) args.gh_region[27 * body_id + lane] = v;
-            if (args.phases & PH_DEPTH_GH) args.gh_depth[27 * body_id + lane] = v;
-          }
-          if (args.phases & PH_LOAD_GH)  // Link::CalculateGradientAndHessian (link.cpp:184-193): region, then depth
-            v = 0.0f + args.gh_region[27 * body_id + lane] + args.gh_depth[27 * body_id + lane];
-          if (args.phases & PH_SOLVE) {
-            // Optimizer: b = J^T g, a(lower) = -J^T H J with J = I6, a.diagonal() += tikhonov (optimizer.cpp:144-159)
-            if (lane < 6) {
-              sh.b[lane] = 0.0f + v;
-            } else {
-              int i, j;
-              TriInv(lane - 6, i, j);
-              float val = 0.0f - v;
-              if (i == j) val += (i < 3) ? body.tikhonov_rotation : body.tikhonov_translation;
-              sh.a[i * 6 + j] = val;
-              sh.a[j * 6 + i] = val;
-            }
-          }
+        for (int w = 1; w < kW; ++w) v += sh.red[w][l];
+        if (args.phases & PH_STORE_GH) {
+          if (args.phases & PH_REGION_GH) args.gh_region[27 * body_id + l] = v;
+          if (args.phases & PH_DEPTH_GH) args.gh_depth[27 * body_id + l] = v;
         }
+        if (args.phases & PH_LOAD_GH)  // Link::CalculateGradientAndHessian (link.cpp:184-193): region, then depth
+          v = 0.0f + args.gh_region[27 * body_id + l] + args.gh_depth[27 * body_id + l];
         if (args.phases & PH_SOLVE) {
+          // Optimizer: b = J^T g, a(lower) = -J^T H J with J = I6, a.diagonal() += tikhonov (optimizer.cpp:144-159)
+          int i, j;
+          TriInv(l >= 6 ? l - 6 : 0, i, j);
+          float aval = 0.0f - v;
+          if (i == j) aval += (i < 3) ? body.tikhonov_rotation : body.tikhonov_translation;
+          const bool is_b = l < 6;
+          float* p1 = is_b ? &sh.b[l] : &sh.a[i * 6 + j];
+          float* p2 = is_b ? &sh.b[l] : &sh.a[j * 6 + i];
+          const float val = is_b ? 0.0f + v : aval;
+          *p1 = val;
+          *p2 = val;
           __syncwarp();
-          SolveAndUpdateWarp(sh);
+          M3TB_STAMP();  // cross-warp sum + normal equations
+          SolveAndUpdateWarp(sh, ccam, dcam, stamp_ptr, stamp_i);
         }
       }
       __syncthreads();
+      M3TB_STAMP();  // solve + pose update
     }
   }
 
@@ -1001,12 +1218,15 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   float* hist_b = args.hist_b + size_t(body_id) * args.stride;
   float2* lut = args.lut + size_t(body_id) * args.stride;
   for (int k = tid; k < nbins3; k += kBlockThreads) { mem_f[k] = 0.0f; mem_b[k] = 0.0f; }  // ClearMemory
-  if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
-  __syncthreads();
   const CameraDev& cam = args.color_cams[body.color_camera];
+  if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
+  if (tid >= 32 && tid < 44) sh.cw2c[tid - 32] = cam.w2c[tid - 32];
+  __syncthreads();
   const ModelDev& model = args.region_models[body.region_model];
+  if (warp == 0) PoseProductsWarp(true, false, sh);
+  __syncthreads();
   RegionIter it;
-  MakeRegionIter(rp, cam, sh.pose, 0, it);
+  MakeRegionIter(rp, cam, sh.rb2c, 0, it);
   int view, unused;
   ClosestViews<kBlockThreads>(&model, it.b2c, nullptr, it.b2c, sh, view, unused);
   int n_lines = AdaptiveCount(rp.n_lines_max, rp.use_adaptive_coverage, rp.reference_contour_length,

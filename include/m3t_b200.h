@@ -244,6 +244,11 @@ int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int
 /* Index of the closest view chosen by the last *correspondences call (GetClosestView). */
 int m3tb_get_closest_views(m3tb_ctx* ctx, int body, int* region_view, int* depth_view);
 
+/* Profiling aid (no reference counterpart): clock64() stamps taken by thread 0 of body `body` at the phase
+ * boundaries of the last fused launch. Only available when the context was created with M3TB_TIMING=1 in the
+ * environment. */
+int m3tb_debug_phase_clocks(m3tb_ctx* ctx, int body, long long* out, int capacity);
+
 #ifdef __cplusplus
 }
 #endif

@@ -582,9 +582,9 @@ void ExpSkew(const float* w, int exp_mode, float* out) {
     // closed form, same expression as the CUDA path (csrc/m3t_b200_math.cuh ExpSkew)
     float t2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
     float a, b;
-    if (t2 < 1e-8f) {
-      a = 1.0f - t2 / 6.0f;
-      b = 0.5f - t2 / 24.0f;
+    if (t2 < 0.01f) {
+      a = 1.0f + t2 * (-1.0f / 6.0f + t2 * (1.0f / 120.0f + t2 * (-1.0f / 5040.0f)));
+      b = 0.5f + t2 * (-1.0f / 24.0f + t2 * (1.0f / 720.0f + t2 * (-1.0f / 40320.0f)));
     } else {
       float t = std::sqrt(t2);
       float sh = std::sin(0.5f * t);
