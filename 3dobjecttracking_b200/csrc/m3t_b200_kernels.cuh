@@ -596,9 +596,11 @@ __device__ __forceinline__ void DepthGradient(const DepthIter& it, const PointSt
     for (int r = 0; r <= c; ++r) acc[6 + Tri(c, r)] -= v[r] * v[c];
 }
 
+// All 32 lanes of warp 0 take the stamp and store it to the same shared-memory slot: warp-uniform control flow,
+// so the instrumentation cannot split the warp in front of the full-mask collectives of the solve.
 #define M3TB_STAMP()                                                              \
   do {                                                                            \
-    if (stamp_ptr && tid == 0 && stamp_i < kPhaseSlots) stamp_ptr[stamp_i++] = clock64(); \
+    if (stamp_ptr && (tid >> 5) == 0 && stamp_i < kPhaseSlots) g_stamps[stamp_i++] = clock64(); \
   } while (0)
 
 // ---------------------------------------------------------------------------------------------
@@ -680,7 +682,7 @@ __device__ __forceinline__ void PoseProductsWarp(bool has_color, bool has_depth,
 // latency is fully exposed): one division per lane per elimination step, shuffles instead of unrolled copies.
 // Returns true if the pose was updated.
 __device__ __forceinline__ bool SolveAndUpdateWarp(Shared& sh, const CameraDev* ccam, const CameraDev* dcam,
-                                                   long long* stamp_ptr, int& stamp_i) {
+                                                   long long* stamp_ptr, long long* g_stamps, int& stamp_i) {
   const int tid = threadIdx.x;
   constexpr int n = 6;
   constexpr unsigned kFull = 0xffffffffu;
@@ -841,6 +843,9 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   const float2* lut_g = args.lut + size_t(body_id) * args.lut_stride;
   const float2* lut_s = reinterpret_cast<const float2*>(dyn);
 
+  // profiling aid: stamps go to shared memory (cheap) and are flushed at the end of the kernel
+  __shared__ long long g_stamps_storage[kPhaseSlots];
+  long long* g_stamps = g_stamps_storage;
   long long* stamp_ptr = args.phase_clock ? args.phase_clock + size_t(body_id) * kPhaseSlots : nullptr;
   int stamp_i = 0;
   M3TB_STAMP();
@@ -1111,7 +1116,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
           *p2 = val;
           __syncwarp();
           M3TB_STAMP();  // cross-warp sum + normal equations
-          SolveAndUpdateWarp(sh, ccam, dcam, stamp_ptr, stamp_i);
+          SolveAndUpdateWarp(sh, ccam, dcam, stamp_ptr, g_stamps, stamp_i);
         }
       }
       __syncthreads();
@@ -1156,6 +1161,8 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     }
     if (tid == 0) { counts[1] = n_points; counts[3] = view_d; }
   }
+  if (stamp_ptr && tid == 0)
+    for (int k = 0; k < kPhaseSlots; ++k) stamp_ptr[k] = k < stamp_i ? g_stamps[k] : 0;
   if (need_lut && !lut_ready) MbarWait(&sh.lut_bar, 0);  // never leave with a bulk copy in flight
   if (!depth_ready) MbarWait(&sh.depth_bar, 0);
 }
