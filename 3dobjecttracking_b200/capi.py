@@ -70,7 +70,7 @@ SYMBOLS = [
     "m3tb_start_modalities", "m3tb_calculate_results", "m3tb_region_correspondences",
     "m3tb_region_gradient_hessian", "m3tb_depth_correspondences", "m3tb_depth_gradient_hessian",
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
-    "m3tb_debug_phase_clocks",
+    "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes",
 ]
 
 _lib = None
@@ -317,6 +317,12 @@ class Context:
         n = C.c_int(0)
         self._ck(self.L.m3tb_get_depth_points(self.h, body, out.ctypes.data_as(C.c_void_p), capacity, C.byref(n)))
         return out[:min(n.value, capacity)]
+
+    def last_ingest_bytes(self):
+        v = C.c_ulonglong(0)
+        self.L.m3tb_last_ingest_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        self._ck(self.L.m3tb_last_ingest_bytes(self.h, C.byref(v)))
+        return int(v.value)
 
     def phase_clocks(self, body, n=128):
         out = np.zeros(n, np.int64)

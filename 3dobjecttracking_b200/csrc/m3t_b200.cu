@@ -60,6 +60,10 @@ struct m3tb_ctx {
   int* d_counts = nullptr;
   float *d_gh_region = nullptr, *d_gh_depth = nullptr;
   size_t max_dyn_smem = 0;
+  RoiRecord* d_roi = nullptr;             // [max_bodies][2]
+  unsigned long long* d_ingest_bytes = nullptr;
+  bool ingest_pending = false;            // a pinned frame was handed over since the last k_ingest launch
+  bool roi_ingest = true;                 // M3TB_NO_ROI_INGEST=1 forces full-frame copies
   long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
 };
@@ -195,6 +199,26 @@ int ValidateBodies(m3tb_ctx* ctx) {
   return M3TB_OK;
 }
 
+// Frame ingest for pinned host frames: fetch every body's ROI (k_ingest) before the first consumer of the new frame.
+int LaunchIngestIfPending(m3tb_ctx* ctx) {
+  if (!ctx->ingest_pending) return M3TB_OK;
+  IngestArgs a;
+  a.bodies = ctx->d_bodies;
+  a.poses = ctx->d_poses;
+  a.color_cams = ctx->d_ccams;
+  a.depth_cams = ctx->d_dcams;
+  a.region_models = ctx->d_rmodels;
+  a.depth_models = ctx->d_dmodels;
+  a.roi = ctx->d_roi;
+  a.bytes = ctx->d_ingest_bytes;
+  CU(cudaMemsetAsync(ctx->d_ingest_bytes, 0, sizeof(unsigned long long), ctx->stream));
+  k_ingest<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  ctx->ingest_pending = false;
+  return M3TB_OK;
+}
+
 int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update, int opt_base,
                 unsigned phases) {
   int rc = ValidateBodies(ctx);
@@ -202,6 +226,8 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   rc = EnsureState(ctx);
   if (rc) return rc;
   rc = SyncTables(ctx);
+  if (rc) return rc;
+  rc = LaunchIngestIfPending(ctx);
   if (rc) return rc;
   TrackArgs a;
   a.bodies = ctx->d_bodies;
@@ -226,6 +252,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   a.opt_base = opt_base;
   a.phases = phases;
   a.phase_clock = ctx->d_phase_clock;
+  a.roi = ctx->d_roi;
   // thread <-> line mapping: T threads per body, K lines and K points per thread (state in registers)
   const int items = std::max(ctx->line_cap, ctx->point_cap);
   bool lut_smem = true;  // normalised LUT staged in shared memory when every region body has <= 16 bins (32 KB)
@@ -261,6 +288,8 @@ int LaunchHistogram(m3tb_ctx* ctx, int mode) {
   if (rc) return rc;
   rc = SyncTables(ctx);
   if (rc) return rc;
+  rc = LaunchIngestIfPending(ctx);
+  if (rc) return rc;
   if (!ctx->hist_stride) return M3TB_OK;  // no region modality anywhere
   HistArgs a;
   a.bodies = ctx->d_bodies;
@@ -274,6 +303,7 @@ int LaunchHistogram(m3tb_ctx* ctx, int mode) {
   a.lut = ctx->d_lut;
   a.stride = ctx->hist_stride;
   a.mode = mode;
+  a.roi = ctx->d_roi;
   k_histogram<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
@@ -376,13 +406,37 @@ int EnsureImage(m3tb_ctx* ctx, bool color, int cam) {
   return M3TB_OK;
 }
 
-int Upload(m3tb_ctx* ctx, bool color, int cam, const void* src, size_t pitch, cudaMemcpyKind kind) {
+// Device-visible alias of a pinned (page-locked, mapped) host pointer, or null for pageable / foreign memory.
+const uint8_t* PinnedAlias(m3tb_ctx* ctx, const void* host) {
+  if (!ctx->roi_ingest) return nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer) return nullptr;
+  return static_cast<const uint8_t*>(attr.devicePointer);
+}
+
+// Camera::UpdateImage. Pinned host frames are NOT copied here: the camera records the frame (zero-copy alias) and
+// the next consumer launch first runs k_ingest, which fetches only each body's ROI. The caller keeps the frame
+// unchanged until the work that uses it has completed (m3tb_synchronize / m3tb_get_poses), exactly as for any
+// asynchronous copy from pinned memory. Pageable frames and device frames are copied in full.
+int Upload(m3tb_ctx* ctx, bool color, int cam, const void* src, size_t pitch, cudaMemcpyKind kind,
+           const uint8_t* pinned_alias) {
   if (cam < 0 || cam >= ctx->max_cameras || !src) return Fail(ctx, M3TB_ERR_INVALID, "bad upload arguments");
   int rc = EnsureImage(ctx, color, cam);
   if (rc) return rc;
   CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[cam];
   const size_t row = size_t(c.width) * (color ? 3 : 2);
   if (pitch < row) return Fail(ctx, M3TB_ERR_INVALID, "pitch smaller than a row");
+  c.generation = (c.generation + 1) & 0x3fffffff;
+  ctx->cams_dirty = true;
+  if (pinned_alias) {
+    c.host_src = pinned_alias;
+    c.host_pitch = unsigned(pitch);
+    ctx->ingest_pending = true;
+    return M3TB_OK;
+  }
+  c.host_src = nullptr;
+  c.host_pitch = 0;
   CU(cudaMemcpy2DAsync(const_cast<uint8_t*>(c.image), c.pitch, src, pitch, row, c.height, kind, ctx->stream));
   return M3TB_OK;
 }
@@ -399,6 +453,18 @@ int UploadBatch(m3tb_ctx* ctx, bool color, int first, int count, const void* src
     pooled = pooled && pool.base && c.image == pool.base + pool.frame_bytes * (first + k);
   }
   const uint8_t* s = static_cast<const uint8_t*>(src);
+  if (const uint8_t* alias = PinnedAlias(ctx, src)) {
+    for (int k = 0; k < count; ++k) {
+      int rc = Upload(ctx, color, first + k, s + frame_stride * k, pitch, cudaMemcpyHostToDevice, alias + frame_stride * k);
+      if (rc) return rc;
+    }
+    return M3TB_OK;
+  }
+  for (int k = 0; k < count; ++k) {
+    CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[first + k];
+    c.host_src = nullptr; c.host_pitch = 0; c.generation = (c.generation + 1) & 0x3fffffff;
+  }
+  ctx->cams_dirty = true;
   if (pooled && frame_stride == pitch * size_t(pool.height)) {
     const size_t row = size_t(pool.width) * (color ? 3 : 2);
     uint8_t* dst = pool.base + pool.frame_bytes * first;
@@ -411,7 +477,7 @@ int UploadBatch(m3tb_ctx* ctx, bool color, int first, int count, const void* src
     return M3TB_OK;
   }
   for (int k = 0; k < count; ++k) {
-    int rc = Upload(ctx, color, first + k, s + frame_stride * k, pitch, cudaMemcpyHostToDevice);
+    int rc = Upload(ctx, color, first + k, s + frame_stride * k, pitch, cudaMemcpyHostToDevice, nullptr);
     if (rc) return rc;
   }
   return M3TB_OK;
@@ -497,6 +563,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->private_color.assign(max_cameras, nullptr);
   ctx->private_depth.assign(max_cameras, nullptr);
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
+  if (const char* e = std::getenv("M3TB_NO_ROI_INGEST")) ctx->roi_ingest = !(e[0] == '1');
   const char* timing_env = std::getenv("M3TB_TIMING");
   const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {
@@ -513,7 +580,10 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
     CU(cudaMemset(ctx->d_poses, 0, sizeof(float) * 12 * max_bodies));
     CU(cudaMemset(ctx->d_counts, 0, sizeof(int) * 4 * max_bodies));
     CU(cudaMemset(ctx->d_gh_region, 0, sizeof(float) * 27 * max_bodies));
-    CU(cudaMemset(ctx->d_gh_depth, 0, sizeof(float) * 27 * max_bodies));
+    CU(cudaMalloc(&ctx->d_roi, sizeof(RoiRecord) * 2 * max_bodies));
+    CU(cudaMemset(ctx->d_roi, 0xff, sizeof(RoiRecord) * 2 * max_bodies));  // generation -1: nothing ingested yet
+    CU(cudaMalloc(&ctx->d_ingest_bytes, sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_ingest_bytes, 0, sizeof(unsigned long long)));
     if (want_timing) {
       CU(cudaMalloc(&ctx->d_phase_clock, sizeof(long long) * kPhaseSlots * max_bodies));
       CU(cudaMemset(ctx->d_phase_clock, 0, sizeof(long long) * kPhaseSlots * max_bodies));
@@ -543,7 +613,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_dmodels); cudaFree(ctx->d_poses); cudaFree(ctx->d_counts); cudaFree(ctx->d_gh_region);
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
-  cudaFree(ctx->d_phase_clock);
+  cudaFree(ctx->d_phase_clock); cudaFree(ctx->d_roi); cudaFree(ctx->d_ingest_bytes);
   delete ctx;
   return M3TB_OK;
 }
@@ -591,19 +661,19 @@ int m3tb_set_depth_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrins
 
 int m3tb_upload_color(m3tb_ctx* ctx, int cam, const uint8_t* bgr, size_t pitch) {
   CHECK_CTX();
-  return Upload(ctx, true, cam, bgr, pitch, cudaMemcpyHostToDevice);
+  return Upload(ctx, true, cam, bgr, pitch, cudaMemcpyHostToDevice, PinnedAlias(ctx, bgr));
 }
 int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitch) {
   CHECK_CTX();
-  return Upload(ctx, false, cam, depth, pitch, cudaMemcpyHostToDevice);
+  return Upload(ctx, false, cam, depth, pitch, cudaMemcpyHostToDevice, PinnedAlias(ctx, depth));
 }
 int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch) {
   CHECK_CTX();
-  return Upload(ctx, true, cam, dev_bgr, pitch, cudaMemcpyDeviceToDevice);
+  return Upload(ctx, true, cam, dev_bgr, pitch, cudaMemcpyDeviceToDevice, nullptr);
 }
 int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch) {
   CHECK_CTX();
-  return Upload(ctx, false, cam, dev_depth, pitch, cudaMemcpyDeviceToDevice);
+  return Upload(ctx, false, cam, dev_depth, pitch, cudaMemcpyDeviceToDevice, nullptr);
 }
 int m3tb_upload_color_batch(m3tb_ctx* ctx, int first_cam, int count, const uint8_t* bgr, size_t frame_stride,
                             size_t pitch) {
@@ -906,6 +976,14 @@ int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int
     }
   }
   if (n_out) *n_out = counts[1];
+  return M3TB_OK;
+}
+
+int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes) {
+  CHECK_CTX();
+  if (!bytes) return Fail(ctx, M3TB_ERR_INVALID, "null output");
+  CU(cudaMemcpyAsync(bytes, ctx->d_ingest_bytes, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
   return M3TB_OK;
 }
 

@@ -42,9 +42,25 @@ struct CameraDev {
   int width, height;
   float w2c[12];
   float depth_scale;
-  const uint8_t* image;  // BGR8 or U16
+  const uint8_t* image;  // BGR8 or U16, device copy (complete, or valid only inside each body's ROI, see FrameView)
   unsigned pitch;        // bytes
+  const uint8_t* host_src;  // device-visible alias of the caller's pinned frame (zero-copy ROI ingest), or null
+  unsigned host_pitch;
+  int generation;        // bumped by every upload; k_ingest refreshes a body's ROI when it differs from the ROI's
   int set;
+};
+
+// How one body sees one camera frame. The device copy is valid inside [x0,x1) x [y0,y1); everything else is read
+// straight from the caller's pinned frame over PCIe (always correct, just slower), so the ROI is purely a transfer
+// optimisation. Without a pinned source the rectangle is the whole frame.
+struct FrameView {
+  const uint8_t* dev;
+  const uint8_t* host;
+  unsigned dev_pitch, host_pitch;
+  int x0, y0, x1, y1;
+};
+struct RoiRecord {  // per body, per camera kind
+  int x0, y0, x1, y1, generation, pad0, pad1, pad2;
 };
 
 struct ModelDev {
@@ -108,6 +124,7 @@ struct TrackArgs {
   int iteration, corr_begin, corr_end, n_update, opt_base;
   unsigned phases;
   int tile_bytes;               // dynamic shared memory available for the colour / depth ROI tiles (0: no tiling)
+  RoiRecord* roi;               // [n_bodies][2]: colour, depth
   long long* phase_clock;       // optional [n_bodies][kPhaseSlots] clock64() stamps of thread 0 (profiling aid), or null
 };
 

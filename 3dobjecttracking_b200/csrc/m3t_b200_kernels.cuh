@@ -196,22 +196,35 @@ __device__ __forceinline__ void MakeRegionIter(const RegionParamsDev& rp, const 
   it.variance = sd * sd;
 }
 
-// Histogram bin index of pixel (x, y): from the shared-memory tile when inside it, else straight from the frame
+__device__ __forceinline__ FrameView MakeFrameView(const CameraDev& cam, const RoiRecord& r) {
+  FrameView f;
+  f.dev = cam.image; f.dev_pitch = cam.pitch;
+  f.host = cam.host_src; f.host_pitch = cam.host_pitch;
+  if (cam.host_src) { f.x0 = r.x0; f.y0 = r.y0; f.x1 = r.x1; f.y1 = r.y1; }
+  else { f.x0 = 0; f.y0 = 0; f.x1 = cam.width; f.y1 = cam.height; }
+  return f;
+}
+__device__ __forceinline__ const uint8_t* FramePtr(const FrameView& f, int x, int y, unsigned bytes_per_pixel) {
+  const bool in_roi = x >= f.x0 && x < f.x1 && y >= f.y0 && y < f.y1;
+  return in_roi ? f.dev + size_t(unsigned(y)) * f.dev_pitch + bytes_per_pixel * unsigned(x)
+                : f.host + size_t(unsigned(y)) * f.host_pitch + bytes_per_pixel * unsigned(x);
+}
+
+// Histogram bin index of pixel (x, y): from the shared-memory tile when inside it, else from the frame
 // (same integer result either way, so tiling never changes a line).
-__device__ __forceinline__ int PixelBin(const Tile& t, const uint16_t* tile, const uint8_t* __restrict__ img,
-                                        unsigned pitch, int bs, int nb, int x, int y) {
+__device__ __forceinline__ int PixelBin(const Tile& t, const uint16_t* tile, const FrameView& f, int bs, int nb, int x,
+                                        int y) {
   const unsigned tx = unsigned(x - t.x0), ty = unsigned(y - t.y0);
   if (tx < unsigned(t.w) && ty < unsigned(t.h)) return tile[ty * unsigned(t.pitch) + tx];
-  const uint8_t* px = img + size_t(unsigned(y)) * pitch + 3u * unsigned(x);
+  const uint8_t* px = FramePtr(f, x, y, 3u);
   // ColorHistograms::GetProbabilities index (color_histograms.cpp:97-99), BGR memory order
   return (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
 }
 
-__device__ __forceinline__ unsigned DepthAt(const Tile& t, const uint16_t* tile, const uint8_t* __restrict__ img,
-                                            unsigned pitch, int x, int y) {
+__device__ __forceinline__ unsigned DepthAt(const Tile& t, const uint16_t* tile, const FrameView& f, int x, int y) {
   const unsigned tx = unsigned(x - t.x0), ty = unsigned(y - t.y0);
   if (tx < unsigned(t.w) && ty < unsigned(t.h)) return tile[ty * unsigned(t.pitch) + tx];
-  return __ldg(reinterpret_cast<const uint16_t*>(img + size_t(unsigned(y)) * pitch) + x);
+  return __ldg(reinterpret_cast<const uint16_t*>(FramePtr(f, x, y, 2u)));
 }
 
 struct LineState {  // RegionModality::DataLine (region_modality.h:150-165), the fields the math uses
@@ -267,7 +280,7 @@ __device__ __forceinline__ void GatherFast(int scale, int base, float minor_f, f
 // Generic (rare) gather: any sample may lie outside the tile. Kept out of line so that the hot loop stays small.
 template <bool LUT_SMEM>
 __device__ __noinline__ void GatherSlow(int scale, int bs, int nb, bool horizontal, int major, float minor_f, float step,
-                                        const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
+                                        const FrameView& frame, const Tile& tile,
                                         const uint16_t* tile_px, const float2* __restrict__ lut_g, const float2* lut_s,
                                         float* sf, float* sb) {
 #pragma unroll 1
@@ -276,7 +289,7 @@ __device__ __noinline__ void GatherSlow(int scale, int bs, int nb, bool horizont
 #pragma unroll 1
     for (int k = 0; k < scale; ++k) {
       const int minor = int(minor_f);
-      const int idx = PixelBin(tile, tile_px, img, pitch, bs, nb, horizontal ? major : minor, horizontal ? minor : major);
+      const int idx = PixelBin(tile, tile_px, frame, bs, nb, horizontal ? major : minor, horizontal ? minor : major);
       const float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);
       pf *= l.x;
       pb *= l.y;
@@ -290,7 +303,7 @@ __device__ __noinline__ void GatherSlow(int scale, int bs, int nb, bool horizont
 
 template <bool LUT_SMEM>
 __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionParamsDev& rp, const float4 p0,
-                                           const float4 p1, const uint8_t* __restrict__ img, unsigned pitch,
+                                           const float4 p1, const FrameView& frame,
                                            const Tile& tile, const uint16_t* tile_px,
                                            const float2* __restrict__ lut_g, const float2* lut_s, LineState& L) {
   L.valid = false;
@@ -354,7 +367,7 @@ __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionPar
       }
     } else {
       float tf[kLineSegments], tb[kLineSegments];
-      GatherSlow<LUT_SMEM>(it.scale, rp.bitshift, rp.n_bins, horizontal, major, minor_f, step, img, pitch, tile, tile_px,
+      GatherSlow<LUT_SMEM>(it.scale, rp.bitshift, rp.n_bins, horizontal, major, minor_f, step, frame, tile, tile_px,
                            lut_g, lut_s, tf, tb);
 #pragma unroll
       for (int s = 0; s < kLineSegments; ++s) { sf[s] = tf[s]; sb[s] = tb[s]; }
@@ -487,12 +500,11 @@ struct PointState {  // DepthModality::DataPoint (depth_modality.h:139-150)
 
 __device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int u_max, int v_min, int v_max, int stride,
                                              float min_depth_value, float max_depth_value, float x, float y, float z,
-                                             const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
-                                             const uint16_t* tile_px, float* r) {
+                                             const FrameView& frame, const Tile& tile, const uint16_t* tile_px, float* r) {
   float best = r[0], bx = r[1], by = r[2], bz = r[3];
   for (int v = v_min; v <= v_max; v += stride) {
     for (int u = u_min; u <= u_max; u += stride) {
-      float depth = float(DepthAt(tile, tile_px, img, pitch, u, v));
+      float depth = float(DepthAt(tile, tile_px, frame, u, v));
       if (depth > min_depth_value && depth < max_depth_value) {
         depth *= it.depth_scale;
         float tx = (float(u) - it.ppu) * depth / it.fu;
@@ -507,8 +519,8 @@ __device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int
 }
 
 __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
-                                           const uint8_t* __restrict__ img, unsigned pitch, const Tile& tile,
-                                           const uint16_t* tile_px, PointState& P) {
+                                           const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
+                                           PointState& P) {
   P.valid = false;
   float x, y, z;
   PoseApply(it.b2c, p0.x, p0.y, p0.z, x, y, z);
@@ -563,7 +575,7 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
     }
   } else {
     float r[4] = {best, bx, by, bz};
-    DepthSearchSlow(it, u_min, u_max, v_min, v_max, stride, min_depth_value, max_depth_value, x, y, z, img, pitch, tile,
+    DepthSearchSlow(it, u_min, u_max, v_min, v_max, stride, min_depth_value, max_depth_value, x, y, z, frame, tile,
                     tile_px, r);
     best = r[0]; bx = r[1]; by = r[2]; bz = r[3];
   }
@@ -812,6 +824,14 @@ __device__ __forceinline__ void RoiRect(const float* b2c, float fu, float fv, fl
   t.x0 = x0; t.y0 = y0; t.w = x1 - x0; t.h = y1 - y0; t.pitch = t.w;
 }
 
+__device__ __forceinline__ void ClipTile(Tile& t, const FrameView& f, int align_x) {
+  if (t.w <= 0) return;
+  int x0 = max(t.x0, (f.x0 + align_x - 1) / align_x * align_x), x1 = min(t.x0 + t.w, f.x1 / align_x * align_x);
+  int y0 = max(t.y0, f.y0), y1 = min(t.y0 + t.h, f.y1);
+  if (x1 <= x0 || y1 <= y0) { t.w = t.h = t.pitch = 0; return; }
+  t.x0 = x0; t.y0 = y0; t.w = x1 - x0; t.h = y1 - y0; t.pitch = t.w;
+}
+
 // shrink symmetric about the centre until the tile fits `budget` bytes (2 bytes per pixel)
 __device__ __forceinline__ void FitTile(Tile& t, int budget, int align_x) {
   while (t.w > 0 && t.h > 0 && t.w * t.h * 2 > budget) {
@@ -856,6 +876,12 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   const ModelDev* dmodel = has_depth ? &args.depth_models[body.depth_model] : nullptr;
   const bool do_rcorr = has_region && (args.phases & PH_REGION_CORR);
   const bool do_dcorr = has_depth && (args.phases & PH_DEPTH_CORR);
+  FrameView cframe, dframe;
+  cframe.dev = cframe.host = dframe.dev = dframe.host = nullptr;
+  cframe.dev_pitch = cframe.host_pitch = dframe.dev_pitch = dframe.host_pitch = 0u;
+  cframe.x0 = cframe.y0 = cframe.x1 = cframe.y1 = dframe.x0 = dframe.y0 = dframe.x1 = dframe.y1 = 0;
+  if (ccam) cframe = MakeFrameView(*ccam, args.roi[2 * body_id + 0]);
+  if (dcam) dframe = MakeFrameView(*dcam, args.roi[2 * body_id + 1]);
   if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
   if (tid >= 32 && tid < 44 && ccam) sh.cw2c[tid - 32] = ccam->w2c[tid - 32];
   if (tid >= 64 && tid < 76 && dcam) sh.dw2c[tid - 64] = dcam->w2c[tid - 64];
@@ -894,6 +920,9 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
         const float reach = (z > 2.0f * dmodel->radius) ? d_max * dcam->fu / (z - dmodel->radius) + 2.0f + 8.0f : 0.0f;
         RoiRect(b2c, dcam->fu, dcam->fv, dcam->ppu, dcam->ppv, dcam->width, dcam->height, dmodel->radius, reach, 8, dt);
       }
+      // tiles are built from the device copy: keep them inside the rectangle where that copy is valid
+      ClipTile(ct, cframe, 4);
+      ClipTile(dt, dframe, 8);
       // split the budget: the depth tile is the smaller one, give it what it asks for up to 40 %
       int budget = args.tile_bytes - 256;
       FitTile(dt, budget * 2 / 5, 8);
@@ -1020,7 +1049,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
           L[k].valid = false;
           if (i < n_lines) {
             float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-            RegionLine<LUT_SMEM>(rit, body.rp, p0, p1, ccam->image, ccam->pitch, ctile, ctile_px, lut_g, lut_s, L[k]);
+            RegionLine<LUT_SMEM>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, lut_g, lut_s, L[k]);
           }
         }
       }
@@ -1040,7 +1069,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
           P[k].valid = false;
           if (i < n_points) {
             float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-            DepthPoint(dit, body.dp, p0, p1, dcam->image, dcam->pitch, dtile, dtile_px, P[k]);
+            DepthPoint(dit, body.dp, p0, p1, dframe, dtile, dtile_px, P[k]);
           }
         }
       }
@@ -1206,7 +1235,107 @@ struct HistArgs {
   float2* lut;
   size_t stride;
   int mode;
+  const RoiRecord* roi;
 };
+
+// ---------------------------------------------------------------------------------------------
+// k_ingest: frame ingest for pinned host frames. One CTA per body: the rectangle of the colour /
+// depth frame this body can touch during a whole tracking cycle (projected bounding sphere + longest
+// correspondence line or widest depth window + a motion margin) is fetched straight from the caller's pinned
+// frame over PCIe into the device copy - ~1/7 of the frame at 0.6 m - and recorded as the body's RoiRecord.
+// Pixels outside it are still reachable (FrameView falls back to the pinned frame), so this never changes a result.
+// ---------------------------------------------------------------------------------------------
+struct IngestArgs {
+  const BodyDev* bodies;
+  const float* poses;
+  const CameraDev* color_cams;
+  const CameraDev* depth_cams;
+  const ModelDev* region_models;
+  const ModelDev* depth_models;
+  RoiRecord* roi;
+  unsigned long long* bytes;  // total bytes fetched by this launch
+};
+
+__device__ __forceinline__ void IngestRect(const CameraDev& cam, const Tile& t, unsigned bpp, unsigned long long* bytes) {
+  if (t.w <= 0 || t.h <= 0) return;
+  const unsigned row_bytes = unsigned(t.w) * bpp;
+  const uint8_t* src0 = cam.host_src + size_t(t.y0) * cam.host_pitch + size_t(t.x0) * bpp;
+  uint8_t* dst0 = const_cast<uint8_t*>(cam.image) + size_t(t.y0) * cam.pitch + size_t(t.x0) * bpp;
+  const bool vec16 = ((reinterpret_cast<size_t>(src0) | cam.host_pitch | row_bytes) & 15u) == 0;  // dst is 16 B aligned by construction
+  if (vec16) {
+    const int per_row = int(row_bytes >> 4);
+    const int total = per_row * t.h;
+    for (int c0 = threadIdx.x; c0 < total; c0 += 4 * blockDim.x) {  // four 16-byte PCIe reads in flight per thread
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < total) {
+          const int r = c / per_row, k = c - r * per_row;
+          v[u] = __ldg(reinterpret_cast<const uint4*>(src0 + size_t(r) * cam.host_pitch) + k);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < total) {
+          const int r = c / per_row, k = c - r * per_row;
+          reinterpret_cast<uint4*>(dst0 + size_t(r) * cam.pitch)[k] = v[u];
+        }
+      }
+    }
+  } else {
+    const int total = int(row_bytes) * t.h;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+      const int r = c / int(row_bytes), k = c - r * int(row_bytes);
+      dst0[size_t(r) * cam.pitch + k] = __ldg(src0 + size_t(r) * cam.host_pitch + k);
+    }
+  }
+  if (threadIdx.x == 0) atomicAdd(bytes, static_cast<unsigned long long>(row_bytes) * t.h);
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
+  const int body_id = blockIdx.x;
+  const BodyDev& body = args.bodies[body_id];
+  if (!body.set) return;
+  __shared__ Tile rect[2];
+  __shared__ int todo[2];
+  if (threadIdx.x == 0) {
+    float pose[12], b2c[12];
+    for (int i = 0; i < 12; ++i) pose[i] = args.poses[12 * body_id + i];
+    for (int which = 0; which < 2; ++which) {
+      todo[which] = 0;
+      const bool present = which == 0 ? body.has_region : body.has_depth;
+      if (!present) continue;
+      const CameraDev& cam = which == 0 ? args.color_cams[body.color_camera] : args.depth_cams[body.depth_camera];
+      RoiRecord& rec = args.roi[2 * body_id + which];
+      if (!cam.host_src || rec.generation == cam.generation) continue;
+      PoseMul(cam.w2c, pose, b2c);
+      Tile t;
+      if (which == 0) {
+        const ModelDev& m = args.region_models[body.region_model];
+        int s_max = 1;
+        for (int c = 0; c < body.rp.n_scales; ++c) s_max = max(s_max, body.rp.scales[c]);
+        const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + 24.0f;
+        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 16, t);
+      } else {
+        const ModelDev& m = args.depth_models[body.depth_model];
+        float d_max = 0.0f;
+        for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
+        const float z = b2c[11];
+        const float reach = (z > 2.0f * m.radius) ? d_max * cam.fu / (z - m.radius) + 2.0f + 16.0f : 0.0f;
+        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 8, t);
+      }
+      rect[which] = t;
+      todo[which] = 1;
+      rec.x0 = t.x0; rec.y0 = t.y0; rec.x1 = t.x0 + t.w; rec.y1 = t.y0 + t.h;
+      rec.generation = cam.generation;
+    }
+  }
+  __syncthreads();
+  if (todo[0]) IngestRect(args.color_cams[body.color_camera], rect[0], 3u, args.bytes);
+  if (todo[1]) IngestRect(args.depth_cams[body.depth_camera], rect[1], 2u, args.bytes);
+}
 
 __device__ __forceinline__ float sgnf_dev(float v) { return v < 0.0f ? -1.0f : (v > 0.0f ? 1.0f : 0.0f); }
 
@@ -1239,8 +1368,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   int n_lines = AdaptiveCount(rp.n_lines_max, rp.use_adaptive_coverage, rp.reference_contour_length,
                               __ldg(model.view_scalars + view), model.max_view_scalar, model.n_points);
   const float4* pts = model.points + size_t(view) * model.n_points * 2;
-  const uint8_t* img = cam.image;
-  const size_t pitch = cam.pitch;
+  const FrameView frame = MakeFrameView(cam, args.roi[2 * body_id + 0]);
   const int bs = rp.bitshift, nb = rp.n_bins;
   for (int i = tid; i < n_lines; i += kBlockThreads) {
     float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
@@ -1281,7 +1409,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     for (int k = 0; k < plf; ++k) {
       int iu = int(u), iv = int(v);
       if (iu < 0 || iu > it.w_m1 || iv < 0 || iv > it.h_m1) break;
-      const uint8_t* px = img + size_t(iv) * pitch + 3 * size_t(iu);
+      const uint8_t* px = FramePtr(frame, iu, iv, 3u);
       int idx = (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
       atomicAdd(mem_f + idx, 1.0f);
       u -= u_step;
@@ -1292,7 +1420,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     for (int k = 0; k < plb; ++k) {
       int iu = int(u), iv = int(v);
       if (iu < 0 || iu > it.w_m1 || iv < 0 || iv > it.h_m1) break;
-      const uint8_t* px = img + size_t(iv) * pitch + 3 * size_t(iu);
+      const uint8_t* px = FramePtr(frame, iu, iv, 3u);
       int idx = (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
       atomicAdd(mem_b + idx, 1.0f);
       u += u_step;

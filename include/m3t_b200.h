@@ -171,9 +171,15 @@ int m3tb_set_color_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrins
                           const float world2camera[12]);
 int m3tb_set_depth_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics,
                           const float world2camera[12], float depth_scale);
-/* Camera::UpdateImage: copy a host cv::Mat-style frame (CV_8UC3 BGR / CV_16UC1) to the device.
- * `pitch` is the host row pitch in bytes. Host memory stays caller-owned; pinned memory makes the
- * copy asynchronous on the context stream. */
+/* Camera::UpdateImage: hand a host cv::Mat-style frame (CV_8UC3 BGR / CV_16UC1) to the device.
+ * `pitch` is the host row pitch in bytes. Host memory stays caller-owned.
+ *  - pageable memory: the whole frame is copied before the call returns control to the stream;
+ *  - pinned (page-locked, mapped) memory: nothing is copied here. The next launch that consumes the frame first
+ *    fetches, straight from the pinned frame over PCIe, only the rectangle each body can touch in this cycle
+ *    (projected bounding sphere + longest correspondence line / widest depth window + motion margin); pixels
+ *    outside it remain readable through the same zero-copy alias, so results never depend on the rectangle.
+ *    The frame must stay unchanged until that work has completed (m3tb_synchronize / m3tb_get_poses), as for any
+ *    asynchronous copy from pinned memory. */
 int m3tb_upload_color(m3tb_ctx* ctx, int cam, const uint8_t* bgr, size_t pitch);
 int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitch);
 /* Same, for frames that already live in device memory (device-resident pipelines, bench `value`). */
@@ -243,6 +249,9 @@ int m3tb_get_region_lines(m3tb_ctx* ctx, int body, m3tb_region_line* lines, int 
 int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int capacity, int* n_out);
 /* Index of the closest view chosen by the last *correspondences call (GetClosestView). */
 int m3tb_get_closest_views(m3tb_ctx* ctx, int body, int* region_view, int* depth_view);
+
+/* Bytes the last frame ingest (pinned-frame ROI fetch) moved host -> device; 0 if frames were copied in full. */
+int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes);
 
 /* Profiling aid (no reference counterpart): clock64() stamps taken by thread 0 of body `body` at the phase
  * boundaries of the last fused launch. Only available when the context was created with M3TB_TIMING=1 in the

@@ -210,3 +210,39 @@ def test_tiles_do_not_change_results(capi, synth, monkeypatch, rot_deg, trans_m)
         poses.append(ctx.get_poses())
         ctx.close()
     assert np.array_equal(poses[0].view(np.uint32), poses[1].view(np.uint32))
+
+
+@pytest.mark.parametrize("rot_deg,trans_m", [(3.0, 0.005), (9.0, 0.03)])
+def test_pinned_roi_ingest_matches_full_upload(capi, synth, rot_deg, trans_m):
+    """Frame ingest: frames handed over in pinned memory are fetched ROI-only (zero-copy, k_ingest)
+    instead of being copied in full. Results must be bit-identical to the full-copy path, also when the pose moves
+    far enough (3 cm ~ 30 px) that samples leave the ROI and are read from the pinned frame directly, and over a
+    whole cycle (StartModalities, tracking step, CalculateResults, next frame)."""
+    import torch
+    wl = synth.make_workload("c2", n_bodies=5, n_divides=4, seed=21, rot_deg=rot_deg, trans_m=trans_m)
+    pin_c = torch.from_numpy(wl.color_frames).pin_memory()
+    pin_d = torch.from_numpy(wl.depth_frames.view(np.uint8).reshape(wl.n_bodies, wl.depth_frames.shape[1], -1)).pin_memory()
+    results = []
+    for pinned in (False, True):
+        ctx = capi.context_from_workload(wl, upload_frames=not pinned)
+        moved = 0
+        out = []
+        for it in range(2):
+            if pinned:  # a new frame pair per iteration (same pixels), handed over from pinned memory
+                ctx.upload_batch_ptr(True, 0, wl.n_bodies, pin_c.data_ptr(), pin_c.stride(0), pin_c.stride(1))
+                ctx.upload_batch_ptr(False, 0, wl.n_bodies, pin_d.data_ptr(), pin_d.stride(0), pin_d.stride(1))
+            if it == 0:
+                ctx.start_modalities(0)
+            ctx.tracking_step(it, wl.n_corr_iterations, wl.n_update_iterations)
+            ctx.calculate_results(it)
+            out.append(ctx.get_poses())
+            if pinned:
+                moved = ctx.last_ingest_bytes()
+        if pinned:
+            full = wl.color_frames[0].nbytes + wl.depth_frames[0].nbytes
+            assert 0 < moved < 0.5 * full * wl.n_bodies, (moved, full * wl.n_bodies)
+        hf, hb = ctx.get_histograms(0, wl.region.n_histogram_bins)
+        results.append((np.stack(out), hf, hb))
+        ctx.close()
+    assert np.array_equal(results[0][0].view(np.uint32), results[1][0].view(np.uint32))
+    assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
