@@ -8,7 +8,7 @@ The package name starts with a digit, so import it with
     .synth  seeded synthetic workloads (BASELINE.json configs)
     ._build in-tree nvcc / g++ builds
 """
-from . import _build, roofline, sharding, synth  # noqa: F401
+from . import _build, model_io, roofline, sharding, synth  # noqa: F401
 
 
 def __getattr__(name):
