@@ -61,5 +61,22 @@ def build_cuda(force=False, verbose=False):
     return out
 
 
+def build_host_example(force=False):
+    """g++ build of the C++ mirror's example driver (examples/run_synthetic_tracker.cpp) against the two in-tree
+    libraries; proves that the header-only host mirror compiles as plain C++17 without CUDA headers."""
+    src = os.path.join(_ROOT, "examples", "run_synthetic_tracker.cpp")
+    hdr = os.path.join(_HERE, "host", "m3t_b200", "m3t_b200.hpp")
+    out = os.path.join(_ROOT, "examples", "run_synthetic_tracker")
+    csrc = os.path.join(_HERE, "csrc")
+    synth = os.path.join(_HERE, "synth")
+    if force or _stale(out, [src, hdr, os.path.join(csrc, "libm3t_b200.so"), os.path.join(synth, "libm3t_synth.so")]):
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-I", os.path.join(_ROOT, "include"), "-I", os.path.join(_HERE, "host"),
+               "-I", synth, src, "-o", out, "-L", csrc, "-L", synth, "-lm3t_b200", "-lm3t_synth",
+               "-Wl,-rpath," + csrc, "-Wl,-rpath," + synth, "-fopenmp"]
+        subprocess.run(cmd, check=True)
+    return out
+
+
 def build_all(force=False, verbose=False):
-    return build_synth(force), build_cuda(force, verbose)
+    a, b = build_synth(force), build_cuda(force, verbose)
+    return a, b, build_host_example(force)

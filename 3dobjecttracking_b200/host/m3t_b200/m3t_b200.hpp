@@ -1,0 +1,604 @@
+// m3t_b200.hpp — header-only C++17 mirror of M3T's object model for the pose-optimisation path, on top of the
+// C ABI of libm3t_b200 (include/m3t_b200.h). It keeps the reference's class and method names, argument meaning and
+// bool-return / std::cerr error convention (DLR-RM/3DObjectTracking M3T/include/m3t/{body,camera,color_histograms,
+// region_model,depth_model,modality,region_modality,depth_modality,link,optimizer,tracker}.h) so that code written
+// against m3t:: reads the same against m3t_b200::, and so that the parity tests read like the reference's tests.
+//
+//   m3t::Modality::{StartModality,CalculateCorrespondences,CalculateGradientAndHessian,CalculateResults}
+//       -> the fine-grained entry points (one batched launch per phase for ALL bodies of the Batch; the adapters
+//          de-duplicate the per-object calls a Tracker fans out, see Batch::Phase)
+//   m3t::Optimizer::CalculateOptimization              -> m3tb_calculate_optimization
+//   m3t::Tracker::ExecuteTrackingStep                  -> m3tb_tracking_step + m3tb_calculate_results (fast path)
+//
+// Everything the reference has outside this path (renderers, detectors, viewers, texture modality, YAML metafiles,
+// kinematic constraints) is out of scope here. Poses use a minimal Transform3fA (row-major 3x4).
+#ifndef M3T_B200_HPP_
+#define M3T_B200_HPP_
+
+#include <array>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "m3t_b200.h"
+
+namespace m3t_b200 {
+
+// ---- common.h ------------------------------------------------------------------------------------------------
+struct Transform3fA {  // the top three rows of m3t::Transform3fA (Eigen::Transform<float,3,Affine>), row-major
+  float m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  static Transform3fA Identity() { return Transform3fA(); }
+  float& operator()(int r, int c) { return m[4 * r + c]; }
+  float operator()(int r, int c) const { return m[4 * r + c]; }
+  const float* data() const { return m; }
+  float* data() { return m; }
+};
+using Intrinsics = m3tb_intrinsics;
+
+inline bool Check(m3tb_ctx* ctx, int status, const char* what) {
+  if (status == M3TB_OK) return true;
+  std::cerr << what << ": " << (ctx ? m3tb_last_error(ctx) : "no context") << " (status " << status << ")" << std::endl;
+  return false;
+}
+
+// ---- the batch = one m3tb context shared by all objects of a tracker ---------------------------------------------
+// A reference Tracker fans every phase out over its modalities / optimizers one object at a time
+// (tracker.cpp:447-489). Here a phase is ONE launch for all bodies; the first object that asks for a phase triggers
+// it, the others find it done (same iteration / corr_iteration / opt_iteration and unchanged poses).
+class Batch {
+ public:
+  Batch(int device, int max_bodies, int max_cameras, int max_models) {
+    if (m3tb_create(device, max_bodies, max_cameras, max_models, &ctx_) != M3TB_OK) {
+      ctx_ = nullptr;
+      std::cerr << "m3t_b200::Batch: no usable sm_100 CUDA device / context creation failed" << std::endl;
+    }
+    max_bodies_ = max_bodies;
+  }
+  ~Batch() {
+    if (ctx_) m3tb_destroy(ctx_);
+  }
+  Batch(const Batch&) = delete;
+  Batch& operator=(const Batch&) = delete;
+  m3tb_ctx* ctx() const { return ctx_; }
+  bool ok() const { return ctx_ != nullptr; }
+
+  enum PhaseKind { kRegionCorr, kDepthCorr, kRegionGH, kDepthGH, kOptimize, kStart, kResults, kNPhases };
+  struct Key {
+    int iteration = -1, corr = -1, opt = -1;
+    long pose_version = -1;
+    bool operator==(const Key& o) const {
+      return iteration == o.iteration && corr == o.corr && opt == o.opt && pose_version == o.pose_version;
+    }
+  };
+  // Returns true if the phase still has to run for this key (and records it as done).
+  bool Claim(PhaseKind k, int iteration, int corr, int opt) {
+    Key key{iteration, corr, opt, pose_version_};
+    if (done_[k] == key) return false;
+    done_[k] = key;
+    return true;
+  }
+  void MarkDone(PhaseKind k, int iteration, int corr, int opt) { done_[k] = Key{iteration, corr, opt, pose_version_}; }
+  void PosesChanged() { ++pose_version_; }
+  int NextBody() { return n_bodies_++; }
+  int NextColorCamera() { return n_color_++; }
+  int NextDepthCamera() { return n_depth_++; }
+  int NextRegionModel() { return n_rmodels_++; }
+  int NextDepthModel() { return n_dmodels_++; }
+  int n_bodies() const { return n_bodies_; }
+
+  std::vector<float> region_g, region_h, depth_g, depth_h;  // last batched gradients / Hessians (all bodies)
+
+ private:
+  m3tb_ctx* ctx_ = nullptr;
+  int max_bodies_ = 0, n_bodies_ = 0, n_color_ = 0, n_depth_ = 0, n_rmodels_ = 0, n_dmodels_ = 0;
+  long pose_version_ = 0;
+  Key done_[kNPhases];
+};
+
+// ---- body.h --------------------------------------------------------------------------------------------------------
+class Body {
+ public:
+  Body(const std::string& name, const std::shared_ptr<Batch>& batch) : name_(name), batch_(batch) {
+    index_ = batch->NextBody();
+  }
+  const std::string& name() const { return name_; }
+  int index() const { return index_; }
+  // Body::set_body2world_pose (body.cpp:85-90)
+  bool set_body2world_pose(const Transform3fA& pose) {
+    body2world_pose_ = pose;
+    batch_->PosesChanged();
+    return Check(batch_->ctx(), m3tb_set_poses(batch_->ctx(), index_, 1, pose.data()), "Body::set_body2world_pose");
+  }
+  // Body::body2world_pose(): reads the pose back from the device (it is updated there by the optimizer)
+  const Transform3fA& body2world_pose() {
+    Check(batch_->ctx(), m3tb_get_poses(batch_->ctx(), index_, 1, body2world_pose_.data()), "Body::body2world_pose");
+    return body2world_pose_;
+  }
+
+ private:
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  int index_ = 0;
+  Transform3fA body2world_pose_;
+};
+
+// ---- camera.h --------------------------------------------------------------------------------------------------------
+class Camera {
+ public:
+  const std::string& name() const { return name_; }
+  const Intrinsics& intrinsics() const { return intrinsics_; }
+  const Transform3fA& world2camera_pose() const { return world2camera_pose_; }
+  int index() const { return index_; }
+  bool set_up() const { return set_up_; }
+
+ protected:
+  Camera(const std::string& name, const std::shared_ptr<Batch>& batch) : name_(name), batch_(batch) {}
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  Intrinsics intrinsics_{};
+  Transform3fA world2camera_pose_;
+  int index_ = 0;
+  bool set_up_ = false;
+};
+
+class ColorCamera : public Camera {
+ public:
+  ColorCamera(const std::string& name, const std::shared_ptr<Batch>& batch, const Intrinsics& intrinsics,
+              const Transform3fA& world2camera_pose)
+      : Camera(name, batch) {
+    intrinsics_ = intrinsics;
+    world2camera_pose_ = world2camera_pose;
+    index_ = batch->NextColorCamera();
+  }
+  bool SetUp() {
+    set_up_ = Check(batch_->ctx(), m3tb_set_color_camera(batch_->ctx(), index_, &intrinsics_, world2camera_pose_.data()),
+                    "ColorCamera::SetUp");
+    return set_up_;
+  }
+  // Camera::UpdateImage with a caller-owned BGR8 frame (cv::Mat::data / step)
+  bool UpdateImage(const uint8_t* bgr, size_t pitch) {
+    if (!set_up_) {
+      std::cerr << "Set up color camera " << name_ << " first" << std::endl;
+      return false;
+    }
+    return Check(batch_->ctx(), m3tb_upload_color(batch_->ctx(), index_, bgr, pitch), "ColorCamera::UpdateImage");
+  }
+};
+
+class DepthCamera : public Camera {
+ public:
+  DepthCamera(const std::string& name, const std::shared_ptr<Batch>& batch, const Intrinsics& intrinsics,
+              const Transform3fA& world2camera_pose, float depth_scale)
+      : Camera(name, batch), depth_scale_(depth_scale) {
+    intrinsics_ = intrinsics;
+    world2camera_pose_ = world2camera_pose;
+    index_ = batch->NextDepthCamera();
+  }
+  float depth_scale() const { return depth_scale_; }
+  bool SetUp() {
+    set_up_ = Check(batch_->ctx(),
+                    m3tb_set_depth_camera(batch_->ctx(), index_, &intrinsics_, world2camera_pose_.data(), depth_scale_),
+                    "DepthCamera::SetUp");
+    return set_up_;
+  }
+  bool UpdateImage(const uint16_t* depth, size_t pitch) {
+    if (!set_up_) {
+      std::cerr << "Set up depth camera " << name_ << " first" << std::endl;
+      return false;
+    }
+    return Check(batch_->ctx(), m3tb_upload_depth(batch_->ctx(), index_, depth, pitch), "DepthCamera::UpdateImage");
+  }
+
+ private:
+  float depth_scale_;
+};
+
+// ---- region_model.h / depth_model.h: views in the reference's DataPoint layout ---------------------------------------
+class Model {
+ public:
+  const std::string& name() const { return name_; }
+  int index() const { return index_; }
+  bool set_up() const { return set_up_; }
+  int n_views() const { return n_views_; }
+  int n_points() const { return n_points_; }
+  // Views as stored by RegionModel/DepthModel::SaveModel: n_views x (n_points x DataPoint), orientations, scalars
+  void SetViews(int n_views, int n_points, const float* orientations, const float* view_scalars, const void* points) {
+    n_views_ = n_views;
+    n_points_ = n_points;
+    orientations_.assign(orientations, orientations + size_t(3) * n_views);
+    scalars_.assign(view_scalars, view_scalars + n_views);
+    const size_t bytes = size_t(n_views) * n_points * point_bytes_;
+    points_.assign(static_cast<const uint8_t*>(points), static_cast<const uint8_t*>(points) + bytes);
+  }
+  // Model::LoadModel for the view block of a .bin (header / body blocks skipped, see 3dobjecttracking_b200/model_io.py)
+  bool LoadViews(const std::string& path, size_t view_block_offset, int n_views, int n_points) {
+    std::ifstream ifs(path, std::ios::in | std::ios::binary);
+    if (!ifs.is_open()) {
+      std::cerr << "Could not open model file " << path << std::endl;
+      return false;
+    }
+    ifs.seekg(std::streamoff(view_block_offset));
+    n_views_ = n_views;
+    n_points_ = n_points;
+    orientations_.resize(size_t(3) * n_views);
+    scalars_.resize(n_views);
+    points_.resize(size_t(n_views) * n_points * point_bytes_);
+    for (int v = 0; v < n_views; ++v) {
+      ifs.read(reinterpret_cast<char*>(points_.data() + size_t(v) * n_points * point_bytes_), std::streamsize(n_points) * point_bytes_);
+      ifs.read(reinterpret_cast<char*>(&orientations_[3 * v]), 12);
+      ifs.read(reinterpret_cast<char*>(&scalars_[v]), 4);
+    }
+    return bool(ifs);
+  }
+
+ protected:
+  Model(const std::string& name, const std::shared_ptr<Batch>& batch, int point_bytes)
+      : name_(name), batch_(batch), point_bytes_(point_bytes) {}
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  int point_bytes_;
+  int index_ = 0, n_views_ = 0, n_points_ = 0;
+  std::vector<float> orientations_, scalars_;
+  std::vector<uint8_t> points_;
+  bool set_up_ = false;
+};
+
+class RegionModel : public Model {
+ public:
+  RegionModel(const std::string& name, const std::shared_ptr<Batch>& batch) : Model(name, batch, M3TB_REGION_POINT_BYTES) {
+    index_ = batch->NextRegionModel();
+  }
+  bool SetUp() {
+    if (n_views_ == 0) {
+      std::cerr << "Region model " << name_ << " has no views" << std::endl;
+      return false;
+    }
+    set_up_ = Check(batch_->ctx(),
+                    m3tb_set_region_model(batch_->ctx(), index_, n_views_, n_points_, orientations_.data(), scalars_.data(),
+                                          points_.data(), 0.002f, 0.05f),
+                    "RegionModel::SetUp");
+    return set_up_;
+  }
+};
+
+class DepthModel : public Model {
+ public:
+  DepthModel(const std::string& name, const std::shared_ptr<Batch>& batch) : Model(name, batch, M3TB_DEPTH_POINT_BYTES) {
+    index_ = batch->NextDepthModel();
+  }
+  bool SetUp() {
+    if (n_views_ == 0) {
+      std::cerr << "Depth model " << name_ << " has no views" << std::endl;
+      return false;
+    }
+    set_up_ = Check(batch_->ctx(),
+                    m3tb_set_depth_model(batch_->ctx(), index_, n_views_, n_points_, orientations_.data(), scalars_.data(),
+                                         points_.data(), 0.002f, 0.05f),
+                    "DepthModel::SetUp");
+    return set_up_;
+  }
+};
+
+// ---- modality.h ----------------------------------------------------------------------------------------------------
+class Modality {
+ public:
+  virtual ~Modality() = default;
+  virtual bool SetUp() = 0;
+  virtual bool StartModality(int iteration, int corr_iteration) = 0;
+  virtual bool CalculateCorrespondences(int iteration, int corr_iteration) = 0;
+  virtual bool CalculateGradientAndHessian(int iteration, int corr_iteration, int opt_iteration) = 0;
+  virtual bool CalculateResults(int iteration) = 0;
+  const std::array<float, 6>& gradient() const { return gradient_; }
+  const std::array<float, 36>& hessian() const { return hessian_; }
+  const std::string& name() const { return name_; }
+  const std::shared_ptr<Body>& body_ptr() const { return body_ptr_; }
+  bool set_up() const { return set_up_; }
+
+ protected:
+  Modality(const std::string& name, const std::shared_ptr<Batch>& batch, const std::shared_ptr<Body>& body_ptr)
+      : name_(name), batch_(batch), body_ptr_(body_ptr) {}
+  bool IsSetup() const {
+    if (!set_up_) std::cerr << "Set up modality " << name_ << " first" << std::endl;
+    return set_up_;
+  }
+  void FetchGH(const std::vector<float>& g, const std::vector<float>& h) {
+    const int b = body_ptr_->index();
+    std::memcpy(gradient_.data(), g.data() + 6 * b, sizeof(float) * 6);
+    std::memcpy(hessian_.data(), h.data() + 36 * b, sizeof(float) * 36);
+  }
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  std::shared_ptr<Body> body_ptr_;
+  std::array<float, 6> gradient_{};
+  std::array<float, 36> hessian_{};
+  bool set_up_ = false;
+  friend class Optimizer;
+};
+
+// ---- region_modality.h --------------------------------------------------------------------------------------------
+class RegionModality : public Modality {
+ public:
+  RegionModality(const std::string& name, const std::shared_ptr<Batch>& batch, const std::shared_ptr<Body>& body_ptr,
+                 const std::shared_ptr<ColorCamera>& color_camera_ptr, const std::shared_ptr<RegionModel>& region_model_ptr)
+      : Modality(name, batch, body_ptr), color_camera_ptr_(color_camera_ptr), region_model_ptr_(region_model_ptr) {
+    m3tb_region_params_default(&params_);
+  }
+  // setters of the reference (region_modality.h:196-260), same names
+  void set_n_lines_max(int v) { params_.n_lines_max = v; set_up_ = false; }
+  void set_min_continuous_distance(float v) { params_.min_continuous_distance = v; set_up_ = false; }
+  void set_function_amplitude(float v) { params_.function_amplitude = v; set_up_ = false; }
+  void set_function_slope(float v) { params_.function_slope = v; set_up_ = false; }
+  void set_learning_rate(float v) { params_.learning_rate = v; set_up_ = false; }
+  void set_n_global_iterations(int v) { params_.n_global_iterations = v; set_up_ = false; }
+  void set_scales(const std::vector<int>& v) {
+    params_.n_scales = int(v.size());
+    for (size_t i = 0; i < v.size() && i < M3TB_MAX_SCHEDULE; ++i) params_.scales[i] = v[i];
+    set_up_ = false;
+  }
+  void set_standard_deviations(const std::vector<float>& v) {
+    params_.n_standard_deviations = int(v.size());
+    for (size_t i = 0; i < v.size() && i < M3TB_MAX_SCHEDULE; ++i) params_.standard_deviations[i] = v[i];
+    set_up_ = false;
+  }
+  void set_n_histogram_bins(int v) { params_.n_histogram_bins = v; set_up_ = false; }
+  void set_learning_rate_f(float v) { params_.learning_rate_f = v; set_up_ = false; }
+  void set_learning_rate_b(float v) { params_.learning_rate_b = v; set_up_ = false; }
+  void set_unconsidered_line_length(float v) { params_.unconsidered_line_length = v; set_up_ = false; }
+  void set_max_considered_line_length(float v) { params_.max_considered_line_length = v; set_up_ = false; }
+  const m3tb_region_params& params() const { return params_; }
+  const std::shared_ptr<ColorCamera>& color_camera_ptr() const { return color_camera_ptr_; }
+  const std::shared_ptr<RegionModel>& region_model_ptr() const { return region_model_ptr_; }
+
+  bool SetUp() override { set_up_ = true; return true; }  // the body's device record is written by Optimizer::SetUp
+  bool StartModality(int iteration, int corr_iteration) override {
+    if (!IsSetup()) return false;
+    (void)corr_iteration;
+    if (!batch_->Claim(Batch::kStart, iteration, 0, 0)) return true;
+    return Check(batch_->ctx(), m3tb_start_modalities(batch_->ctx(), iteration), "RegionModality::StartModality");
+  }
+  bool CalculateCorrespondences(int iteration, int corr_iteration) override {
+    if (!IsSetup()) return false;
+    if (!batch_->Claim(Batch::kRegionCorr, iteration, corr_iteration, 0)) return true;
+    return Check(batch_->ctx(), m3tb_region_correspondences(batch_->ctx(), iteration, corr_iteration),
+                 "RegionModality::CalculateCorrespondences");
+  }
+  bool CalculateGradientAndHessian(int iteration, int corr_iteration, int opt_iteration) override {
+    if (!IsSetup()) return false;
+    if (batch_->Claim(Batch::kRegionGH, iteration, corr_iteration, opt_iteration)) {
+      batch_->region_g.resize(size_t(6) * batch_->n_bodies());
+      batch_->region_h.resize(size_t(36) * batch_->n_bodies());
+      if (!Check(batch_->ctx(),
+                 m3tb_region_gradient_hessian(batch_->ctx(), iteration, corr_iteration, opt_iteration,
+                                              batch_->region_g.data(), batch_->region_h.data()),
+                 "RegionModality::CalculateGradientAndHessian"))
+        return false;
+    }
+    FetchGH(batch_->region_g, batch_->region_h);
+    return true;
+  }
+  bool CalculateResults(int iteration) override {
+    if (!IsSetup()) return false;
+    if (!batch_->Claim(Batch::kResults, iteration, 0, 0)) return true;
+    return Check(batch_->ctx(), m3tb_calculate_results(batch_->ctx(), iteration), "RegionModality::CalculateResults");
+  }
+
+ private:
+  m3tb_region_params params_;
+  std::shared_ptr<ColorCamera> color_camera_ptr_;
+  std::shared_ptr<RegionModel> region_model_ptr_;
+};
+
+// ---- depth_modality.h ----------------------------------------------------------------------------------------------
+class DepthModality : public Modality {
+ public:
+  DepthModality(const std::string& name, const std::shared_ptr<Batch>& batch, const std::shared_ptr<Body>& body_ptr,
+                const std::shared_ptr<DepthCamera>& depth_camera_ptr, const std::shared_ptr<DepthModel>& depth_model_ptr)
+      : Modality(name, batch, body_ptr), depth_camera_ptr_(depth_camera_ptr), depth_model_ptr_(depth_model_ptr) {
+    m3tb_depth_params_default(&params_);
+  }
+  void set_n_points_max(int v) { params_.n_points_max = v; set_up_ = false; }
+  void set_stride_length(float v) { params_.stride_length = v; set_up_ = false; }
+  void set_considered_distances(const std::vector<float>& v) {
+    params_.n_considered_distances = int(v.size());
+    for (size_t i = 0; i < v.size() && i < M3TB_MAX_SCHEDULE; ++i) params_.considered_distances[i] = v[i];
+    set_up_ = false;
+  }
+  void set_standard_deviations(const std::vector<float>& v) {
+    params_.n_standard_deviations = int(v.size());
+    for (size_t i = 0; i < v.size() && i < M3TB_MAX_SCHEDULE; ++i) params_.standard_deviations[i] = v[i];
+    set_up_ = false;
+  }
+  const m3tb_depth_params& params() const { return params_; }
+  const std::shared_ptr<DepthCamera>& depth_camera_ptr() const { return depth_camera_ptr_; }
+  const std::shared_ptr<DepthModel>& depth_model_ptr() const { return depth_model_ptr_; }
+
+  bool SetUp() override { set_up_ = true; return true; }
+  bool StartModality(int, int) override { return IsSetup(); }  // depth_modality.cpp:248-250
+  bool CalculateCorrespondences(int iteration, int corr_iteration) override {
+    if (!IsSetup()) return false;
+    if (!batch_->Claim(Batch::kDepthCorr, iteration, corr_iteration, 0)) return true;
+    return Check(batch_->ctx(), m3tb_depth_correspondences(batch_->ctx(), iteration, corr_iteration),
+                 "DepthModality::CalculateCorrespondences");
+  }
+  bool CalculateGradientAndHessian(int iteration, int corr_iteration, int opt_iteration) override {
+    if (!IsSetup()) return false;
+    if (batch_->Claim(Batch::kDepthGH, iteration, corr_iteration, opt_iteration)) {
+      batch_->depth_g.resize(size_t(6) * batch_->n_bodies());
+      batch_->depth_h.resize(size_t(36) * batch_->n_bodies());
+      if (!Check(batch_->ctx(),
+                 m3tb_depth_gradient_hessian(batch_->ctx(), iteration, corr_iteration, opt_iteration,
+                                             batch_->depth_g.data(), batch_->depth_h.data()),
+                 "DepthModality::CalculateGradientAndHessian"))
+        return false;
+    }
+    FetchGH(batch_->depth_g, batch_->depth_h);
+    return true;
+  }
+  bool CalculateResults(int) override { return IsSetup(); }  // depth_modality.cpp:393
+
+ private:
+  m3tb_depth_params params_;
+  std::shared_ptr<DepthCamera> depth_camera_ptr_;
+  std::shared_ptr<DepthModel> depth_model_ptr_;
+};
+
+// ---- link.h: a root link carrying one body and its modalities ---------------------------------------------------------
+class Link {
+ public:
+  Link(const std::string& name, const std::shared_ptr<Body>& body_ptr) : name_(name), body_ptr_(body_ptr) {}
+  bool AddModality(const std::shared_ptr<Modality>& m) {
+    modality_ptrs_.push_back(m);
+    return true;
+  }
+  const std::string& name() const { return name_; }
+  const std::shared_ptr<Body>& body_ptr() const { return body_ptr_; }
+  const std::vector<std::shared_ptr<Modality>>& modality_ptrs() const { return modality_ptrs_; }
+
+ private:
+  std::string name_;
+  std::shared_ptr<Body> body_ptr_;
+  std::vector<std::shared_ptr<Modality>> modality_ptrs_;
+};
+
+// ---- optimizer.h ----------------------------------------------------------------------------------------------------
+class Optimizer {
+ public:
+  Optimizer(const std::string& name, const std::shared_ptr<Batch>& batch, const std::shared_ptr<Link>& root_link_ptr,
+            float tikhonov_parameter_rotation = 1000.0f, float tikhonov_parameter_translation = 30000.0f)
+      : name_(name), batch_(batch), root_link_ptr_(root_link_ptr) {
+    params_.tikhonov_parameter_rotation = tikhonov_parameter_rotation;
+    params_.tikhonov_parameter_translation = tikhonov_parameter_translation;
+  }
+  void set_tikhonov_parameter_rotation(float v) { params_.tikhonov_parameter_rotation = v; set_up_ = false; }
+  void set_tikhonov_parameter_translation(float v) { params_.tikhonov_parameter_translation = v; set_up_ = false; }
+  const std::string& name() const { return name_; }
+  const std::shared_ptr<Link>& root_link_ptr() const { return root_link_ptr_; }
+  bool set_up() const { return set_up_; }
+
+  // Optimizer::SetUp (optimizer.cpp:22-40): here it also writes the body's device record (modalities + parameters)
+  bool SetUp() {
+    const m3tb_region_params* rp = nullptr;
+    const m3tb_depth_params* dp = nullptr;
+    int rmodel = 0, dmodel = 0, ccam = 0, dcam = 0;
+    if (root_link_ptr_->modality_ptrs().empty()) {
+      std::cerr << "No modalities were assigned to link " << root_link_ptr_->name() << std::endl;
+      return false;
+    }
+    for (auto& m : root_link_ptr_->modality_ptrs()) {
+      if (!m->set_up()) {
+        std::cerr << "Modality " << m->name() << " was not set up" << std::endl;
+        return false;
+      }
+      if (auto r = std::dynamic_pointer_cast<RegionModality>(m)) {
+        rp = &r->params();
+        rmodel = r->region_model_ptr()->index();
+        ccam = r->color_camera_ptr()->index();
+      } else if (auto d = std::dynamic_pointer_cast<DepthModality>(m)) {
+        dp = &d->params();
+        dmodel = d->depth_model_ptr()->index();
+        dcam = d->depth_camera_ptr()->index();
+      }
+    }
+    set_up_ = Check(batch_->ctx(),
+                    m3tb_set_body(batch_->ctx(), root_link_ptr_->body_ptr()->index(), rp, dp, &params_, rmodel, dmodel, ccam, dcam),
+                    "Optimizer::SetUp");
+    return set_up_;
+  }
+  // Optimizer::CalculateOptimization (optimizer.cpp:144-167): batched over all optimizers of the Batch
+  bool CalculateOptimization(int iteration, int corr_iteration, int opt_iteration) {
+    if (!set_up_) {
+      std::cerr << "Set up optimizer " << name_ << " first" << std::endl;
+      return false;
+    }
+    if (!batch_->Claim(Batch::kOptimize, iteration, corr_iteration, opt_iteration)) return true;
+    bool ok = Check(batch_->ctx(), m3tb_calculate_optimization(batch_->ctx(), iteration, corr_iteration, opt_iteration),
+                    "Optimizer::CalculateOptimization");
+    batch_->PosesChanged();
+    // the batched launch updated every body: the other optimizers of this phase must find it done
+    batch_->MarkDone(Batch::kOptimize, iteration, corr_iteration, opt_iteration);
+    return ok;
+  }
+
+ private:
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  std::shared_ptr<Link> root_link_ptr_;
+  m3tb_optimizer_params params_{};
+  bool set_up_ = false;
+};
+
+// ---- tracker.h ------------------------------------------------------------------------------------------------------
+class Tracker {
+ public:
+  Tracker(const std::string& name, const std::shared_ptr<Batch>& batch, int n_corr_iterations = 5, int n_update_iterations = 2)
+      : name_(name), batch_(batch), n_corr_iterations_(n_corr_iterations), n_update_iterations_(n_update_iterations) {}
+  bool AddOptimizer(const std::shared_ptr<Optimizer>& o) {
+    optimizer_ptrs_.push_back(o);
+    for (auto& m : o->root_link_ptr()->modality_ptrs()) modality_ptrs_.push_back(m);
+    return true;
+  }
+  void set_n_corr_iterations(int v) { n_corr_iterations_ = v; }
+  void set_n_update_iterations(int v) { n_update_iterations_ = v; }
+  int n_corr_iterations() const { return n_corr_iterations_; }
+  int n_update_iterations() const { return n_update_iterations_; }
+
+  bool SetUp() {  // Tracker::SetUp: set up all referenced objects (tracker.cpp:884-899 order: modalities, optimizers)
+    for (auto& m : modality_ptrs_)
+      if (!m->SetUp()) return false;
+    for (auto& o : optimizer_ptrs_)
+      if (!o->SetUp()) return false;
+    set_up_ = true;
+    return true;
+  }
+  // Tracker::StartModalities (tracker.cpp:430-445)
+  bool StartModalities(int iteration) {
+    for (auto& m : modality_ptrs_)
+      if (!m->StartModality(iteration, 0)) return false;
+    return true;
+  }
+  // Tracker::ExecuteTrackingStep (tracker.cpp:344-364), fast path: ONE fused launch for the whole
+  // corr x update loop nest of every body + the histogram update
+  bool ExecuteTrackingStep(int iteration) {
+    if (!set_up_) {
+      std::cerr << "Set up tracker " << name_ << " first" << std::endl;
+      return false;
+    }
+    bool ok = Check(batch_->ctx(), m3tb_tracking_step(batch_->ctx(), iteration, n_corr_iterations_, n_update_iterations_),
+                    "Tracker::ExecuteTrackingStep");
+    batch_->PosesChanged();
+    return ok && Check(batch_->ctx(), m3tb_calculate_results(batch_->ctx(), iteration), "Tracker::CalculateResults");
+  }
+  // The same step, phase by phase through the Modality / Optimizer objects exactly as the reference's Tracker fans
+  // them out (tracker.cpp:447-517); used to show that the adapters compose and for step-wise debugging.
+  bool ExecuteTrackingStepObjectWise(int iteration) {
+    for (int corr = 0; corr < n_corr_iterations_; ++corr) {
+      for (auto& m : modality_ptrs_)
+        if (!m->CalculateCorrespondences(iteration, corr)) return false;
+      for (int upd = 0; upd < n_update_iterations_; ++upd) {
+        for (auto& m : modality_ptrs_)
+          if (!m->CalculateGradientAndHessian(iteration, corr, upd)) return false;
+        for (auto& o : optimizer_ptrs_)
+          if (!o->CalculateOptimization(iteration, corr, upd)) return false;
+      }
+    }
+    for (auto& m : modality_ptrs_)
+      if (!m->CalculateResults(iteration)) return false;
+    return true;
+  }
+
+ private:
+  std::string name_;
+  std::shared_ptr<Batch> batch_;
+  int n_corr_iterations_, n_update_iterations_;
+  std::vector<std::shared_ptr<Optimizer>> optimizer_ptrs_;
+  std::vector<std::shared_ptr<Modality>> modality_ptrs_;
+  bool set_up_ = false;
+};
+
+}  // namespace m3t_b200
+#endif  // M3T_B200_HPP_
