@@ -1,0 +1,79 @@
+"""The CUDA path, through the C ABI, on the reference's own test rig (real frame pair, real camera parameters, the
+regenerated template view, see test_reference_goldens.py) against the reference's stored known answers."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+
+import test_reference_goldens as T
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _context(capi, synth, tik=(1000.0, 30000.0)):
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import reference_rig as rr
+    rig, ka = rr.rig(), rr.KA
+    view = np.load(os.path.join(GOLDEN, "triangle_test_view.npz"))
+    nv = view["orientations"].shape[0]
+
+    def model(kind, fl):
+        pts = np.zeros((nv, 200, fl), np.float32)
+        pts[int(view[f"{kind}_view"])] = view[f"{kind}_points"]
+        scal = np.zeros(nv, np.float32)
+        scal[int(view[f"{kind}_view"])] = view[f"{kind}_scalar"]
+        return SimpleNamespace(n_views=nv, n_points=200, orientations=np.ascontiguousarray(view["orientations"]),
+                               view_scalars=scal, points=pts, stride_depth_offset=0.002, max_radius_depth_offset=0.05)
+
+    ctx = capi.Context(0, 1, 1, 1)
+    ctx.set_region_model(0, model("region", 38))
+    ctx.set_depth_model(0, model("depth", 36))
+    cc, dc = ka["color_camera"], ka["depth_camera"]
+    ctx.set_color_camera(0, synth.Intrinsics(cc["fu"], cc["fv"], cc["ppu"], cc["ppv"], cc["width"], cc["height"]), rig["color_w2c"][:3])
+    ctx.set_depth_camera(0, synth.Intrinsics(dc["fu"], dc["fv"], dc["ppu"], dc["ppv"], dc["width"], dc["height"]), rig["depth_w2c"][:3],
+                         dc["depth_scale"])
+    ctx.upload_color(0, rig["color"].reshape(540, -1))
+    ctx.upload_depth(0, rig["depth"])
+    ctx.set_body(0, capi.region_params(), capi.depth_params(), capi.OptimizerParams(*tik), 0, 0, 0, 0)
+    ctx.set_poses(rig["body2world"][:3].astype(np.float32))
+    return ctx, ka, rig
+
+
+def test_cuda_path_reproduces_reference_modality_goldens(capi, synth):
+    ctx, ka, _ = _context(capi, synth)
+    ctx.start_modalities(0)
+    ctx.region_correspondences(0, 0)
+    ctx.depth_correspondences(0, 0)
+    lines, pts = ctx.get_region_lines(0, 200), ctx.get_depth_points(0, 200)
+    assert lines["valid"].sum() == 179 and pts["valid"].sum() == 182
+    g0, H0 = ctx.region_gradient_hessian(0, 0, 0)
+    g1, H1 = ctx.region_gradient_hessian(0, 0, 1)
+    gd, Hd = ctx.depth_gradient_hessian(0, 0, 0)
+    M = lambda n: T._mat(ka, n)
+    assert T._rel_fro(H0[0], M("region_modality_global_hessian")) < 1e-5
+    assert T._rel_fro(H1[0], M("region_modality_local_hessian")) < 1e-5
+    assert T._rel_elem(g0[0], M("region_modality_global_gradient").reshape(6)).max() < 2e-3
+    assert T._rel_elem(g1[0], M("region_modality_local_gradient").reshape(6)).max() < 2e-4
+    assert T._rel_fro(Hd[0], M("depth_modality_hessian")) < 2e-5
+    assert T._rel_elem(gd[0], M("depth_modality_gradient").reshape(6)).max() < 1e-3
+    for golden, ours in ((M("region_modality_global_hessian"), H0[0]), (M("region_modality_local_gradient").reshape(6), g1[0]),
+                         (M("depth_modality_hessian"), Hd[0]), (M("depth_modality_gradient").reshape(6), gd[0])):
+        assert T._reference_comparator(golden, ours) < 1e-3   # CompareToLoadedMatrix, the reference's tolerance
+    ctx.close()
+
+
+def test_cuda_path_reproduces_reference_optimizer_golden(capi, synth):
+    """OptimizerTest.Optimize through the fused entry point: one correspondence iteration with one update."""
+    ctx, ka, rig = _context(capi, synth, tik=(5000.0, 500000.0))
+    ctx.start_modalities(0)
+    ctx.corr_iteration(0, 0, 1)
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3] = ctx.get_poses()[0]
+    golden = T._mat(ka, "optimizer_triangle_pose")
+    assert T._reference_comparator(golden, pose) < 1e-5
+    assert np.abs(pose[:3] - golden[:3]).max() < 1e-5
+    assert np.abs(pose[:3, :3] - golden[:3, :3]).max() < 1e-6
+    ctx.close()
