@@ -44,8 +44,8 @@ struct Shared {
   float a[36];                   // normal matrix, full symmetric
   float b[6];
   float x[6];
-  float best_dot[2][kMaxWarps];
-  int best_idx[2][kMaxWarps];
+  float best_dot[2][2][kMaxWarps];  // [call parity][model][warp]
+  int best_idx[2][2][kMaxWarps];
   unsigned long long lut_bar;    // mbarrier of the LUT bulk copy
 };
 
@@ -110,7 +110,7 @@ __device__ __forceinline__ void ArgmaxMerge(float& best, int& idx, float ob, int
 
 template <int T>
 __device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelDev* m1, const float* b2c1, Shared& sh,
-                             int& view0, int& view1) {
+                             int parity, int& view0, int& view1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kW = T / 32;
   float best[2] = {-1.0f, -1.0f};
@@ -141,27 +141,33 @@ __device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelD
         if (v < nv[s] && dot > best[s]) { best[s] = dot; idx[s] = v; }
       }
   }
+  // warp arg-max (xor butterfly: every lane ends with the warp's result), one shared-memory hop, then the same
+  // butterfly over the per-warp results inside every warp: one __syncthreads per call; the buffers alternate
+  // with the call parity so that the next call cannot overwrite values a slow warp is still reading.
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
-      float ob = __shfl_down_sync(0xffffffffu, best[s], off);
-      int oi = __shfl_down_sync(0xffffffffu, idx[s], off);
+      float ob = __shfl_xor_sync(0xffffffffu, best[s], off);
+      int oi = __shfl_xor_sync(0xffffffffu, idx[s], off);
       ArgmaxMerge(best[s], idx[s], ob, oi);
     }
-    if (lane == 0) { sh.best_dot[s][warp] = best[s]; sh.best_idx[s][warp] = idx[s]; }
+    if (lane == 0) { sh.best_dot[parity][s][warp] = best[s]; sh.best_idx[parity][s][warp] = idx[s]; }
   }
   __syncthreads();
   int out[2] = {0, 0};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    float rb = sh.best_dot[s][0];
-    int ri = sh.best_idx[s][0];
+    float rb = lane < kW ? sh.best_dot[parity][s][lane] : -1.0f;
+    int ri = lane < kW ? sh.best_idx[parity][s][lane] : 0x7fffffff;
 #pragma unroll
-    for (int w = 1; w < kW; ++w) ArgmaxMerge(rb, ri, sh.best_dot[s][w], sh.best_idx[s][w]);
+    for (int off = 16; off > 0; off >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, rb, off);
+      int oi = __shfl_xor_sync(0xffffffffu, ri, off);
+      ArgmaxMerge(rb, ri, ob, oi);
+    }
     out[s] = (ri == 0x7fffffff || !nonzero[s]) ? 0 : ri;
   }
-  __syncthreads();  // best_* are reused by the next call
   view0 = out[0];
   view1 = out[1];
 }
@@ -565,6 +571,10 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
         float depth = float(trow[u]);
         if (depth > min_depth_value && depth < max_depth_value) {
           depth *= it.depth_scale;
+          // exact early-out: d2 = (dx*dx + dy*dy) + dz*dz >= dz*dz under round-to-nearest, so dz*dz >= best means
+          // the strict test d2 < best below cannot succeed; skips the two divisions for most non-surface samples
+          const float dz0 = depth - z;
+          if (dz0 * dz0 >= best) continue;
           float tx = (float(u) - it.ppu) * depth / it.fu;
           float ty = vy * depth / it.fv;
           float dx = tx - x, dy = ty - y, dz = depth - z;
@@ -1032,7 +1042,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr || do_dcorr) {
       int v0, v1;
-      ClosestViews<T>(do_rcorr ? rmodel : nullptr, sh.rb2c, do_dcorr ? dmodel : nullptr, sh.db2c, sh, v0, v1);
+      ClosestViews<T>(do_rcorr ? rmodel : nullptr, sh.rb2c, do_dcorr ? dmodel : nullptr, sh.db2c, sh, corr & 1, v0, v1);
       M3TB_STAMP();  // closest views
       if (do_rcorr) {
         RegionIter rit;
@@ -1364,7 +1374,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   RegionIter it;
   MakeRegionIter(rp, cam, sh.rb2c, 0, it);
   int view, unused;
-  ClosestViews<kBlockThreads>(&model, it.b2c, nullptr, it.b2c, sh, view, unused);
+  ClosestViews<kBlockThreads>(&model, it.b2c, nullptr, it.b2c, sh, 0, view, unused);
   int n_lines = AdaptiveCount(rp.n_lines_max, rp.use_adaptive_coverage, rp.reference_contour_length,
                               __ldg(model.view_scalars + view), model.max_view_scalar, model.n_points);
   const float4* pts = model.points + size_t(view) * model.n_points * 2;
