@@ -37,6 +37,7 @@ struct Shared {
   float db2c[12];                // depth-camera body2camera   (depth_modality.cpp:642-643)
   float dc2b[12];                // its inverse                (depth_modality.cpp:644)
   float cw2c[12], dw2c[12];      // world2camera of the two cameras (copied once per launch)
+  float view_o[2][4];            // R^T normalize(t) of rb2c / db2c, [3] = 1 if |t| > 0 (GetClosestView query)
   Tile ctile, dtile;
   unsigned long long depth_bar;  // mbarrier of the depth-tile bulk copies
   float pose[12];                // body2world (Body::body2world_pose)
@@ -44,7 +45,7 @@ struct Shared {
   float a[36];                   // normal matrix, full symmetric
   float b[6];
   float x[6];
-  float best_dot[2][2][kMaxWarps];  // [call parity][model][warp]
+  unsigned best_key[2][2][kMaxWarps];  // [call parity][model][warp]
   int best_idx[2][2][kMaxWarps];
   unsigned long long lut_bar;    // mbarrier of the LUT bulk copy
 };
@@ -108,19 +109,36 @@ __device__ __forceinline__ void ArgmaxMerge(float& best, int& idx, float ob, int
   if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
 }
 
+// float -> unsigned key with the same ordering (finite values)
+__device__ __forceinline__ unsigned SortableKey(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+// warp arg-max with "first maximum wins": REDUX.MAX on the key, then REDUX.MIN of the index among the lanes holding it
+__device__ __forceinline__ void WarpArgmax(unsigned& key, int& idx) {
+  const unsigned kmax = __reduce_max_sync(0xffffffffu, key);
+  const unsigned cand = key == kmax ? unsigned(idx) : 0x7fffffffu;
+  idx = int(__reduce_min_sync(0xffffffffu, cand));
+  key = kmax;
+}
+
 template <int T>
-__device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelDev* m1, const float* b2c1, Shared& sh,
-                             int parity, int& view0, int& view1) {
+__device__ void ClosestViews(const ModelDev* m0, const ModelDev* m1, Shared& sh, int parity, int& view0, int& view1) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int kW = T / 32;
   float best[2] = {-1.0f, -1.0f};
   int idx[2] = {0x7fffffff, 0x7fffffff};
-  float o[2][3] = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
-  bool nonzero[2] = {false, false};
+  float o[2][3];
+  bool nonzero[2];
   int nv[2] = {0, 0};
   const float4* ori[2] = {nullptr, nullptr};
-  if (m0) { nonzero[0] = ViewOrientation(b2c0, o[0][0], o[0][1], o[0][2]); nv[0] = nonzero[0] ? m0->n_views : 0; ori[0] = m0->orientations4; }
-  if (m1) { nonzero[1] = ViewOrientation(b2c1, o[1][0], o[1][1], o[1][2]); nv[1] = nonzero[1] ? m1->n_views : 0; ori[1] = m1->orientations4; }
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    o[s][0] = sh.view_o[s][0]; o[s][1] = sh.view_o[s][1]; o[s][2] = sh.view_o[s][2];
+    nonzero[s] = sh.view_o[s][3] != 0.0f;
+  }
+  if (m0) { nv[0] = nonzero[0] ? m0->n_views : 0; ori[0] = m0->orientations4; }
+  if (m1) { nv[1] = nonzero[1] ? m1->n_views : 0; ori[1] = m1->orientations4; }
   const int nv_max = max(nv[0], nv[1]);
   // both models share one pass: eight independent 16-byte loads in flight per thread
   for (int v0 = tid; v0 < nv_max; v0 += 4 * T) {
@@ -141,32 +159,24 @@ __device__ void ClosestViews(const ModelDev* m0, const float* b2c0, const ModelD
         if (v < nv[s] && dot > best[s]) { best[s] = dot; idx[s] = v; }
       }
   }
-  // warp arg-max (xor butterfly: every lane ends with the warp's result), one shared-memory hop, then the same
-  // butterfly over the per-warp results inside every warp: one __syncthreads per call; the buffers alternate
-  // with the call parity so that the next call cannot overwrite values a slow warp is still reading.
+  // warp arg-max (REDUX), one shared-memory hop, the same arg-max over the per-warp results inside every warp:
+  // one __syncthreads per call; the buffers alternate with the call parity so that the next call cannot overwrite
+  // values a slow warp is still reading.
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, best[s], off);
-      int oi = __shfl_xor_sync(0xffffffffu, idx[s], off);
-      ArgmaxMerge(best[s], idx[s], ob, oi);
-    }
-    if (lane == 0) { sh.best_dot[parity][s][warp] = best[s]; sh.best_idx[parity][s][warp] = idx[s]; }
+    unsigned key = SortableKey(best[s]);
+    WarpArgmax(key, idx[s]);
+    if (lane == 0) { sh.best_key[parity][s][warp] = key; sh.best_idx[parity][s][warp] = idx[s]; }
   }
   __syncthreads();
   int out[2] = {0, 0};
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    float rb = lane < kW ? sh.best_dot[parity][s][lane] : -1.0f;
+    unsigned key = lane < kW ? sh.best_key[parity][s][lane] : 0u;
     int ri = lane < kW ? sh.best_idx[parity][s][lane] : 0x7fffffff;
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      float ob = __shfl_xor_sync(0xffffffffu, rb, off);
-      int oi = __shfl_xor_sync(0xffffffffu, ri, off);
-      ArgmaxMerge(rb, ri, ob, oi);
-    }
-    out[s] = (ri == 0x7fffffff || !nonzero[s]) ? 0 : ri;
+    WarpArgmax(key, ri);
+    // nothing beat the initial -1 (or |t| = 0): the reference leaves / returns views_[0]
+    out[s] = (ri == 0x7fffffff || !nonzero[s] || key <= SortableKey(-1.0f)) ? 0 : ri;
   }
   view0 = out[0];
   view1 = out[1];
@@ -676,6 +686,12 @@ __device__ __forceinline__ void PoseProductsWarp(bool has_color, bool has_depth,
     if (lane >= 12 && lane < 24 && has_depth) sh.db2c[e] = out;
   }
   __syncwarp();
+  // GetClosestView query vectors (region_model.cpp:112-120): lanes 0 / 1 handle the colour / depth camera
+  if (lane < 2 && (lane == 0 ? has_color : has_depth)) {
+    float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+    const bool nz = ViewOrientation(lane == 0 ? sh.rb2c : sh.db2c, o0, o1, o2);
+    sh.view_o[lane][0] = o0; sh.view_o[lane][1] = o1; sh.view_o[lane][2] = o2; sh.view_o[lane][3] = nz ? 1.0f : 0.0f;
+  }
   if (has_depth) {
     const float* M = sh.db2c;
     auto m = [&](int r, int c) { return M[4 * r + c]; };
@@ -1042,7 +1058,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr || do_dcorr) {
       int v0, v1;
-      ClosestViews<T>(do_rcorr ? rmodel : nullptr, sh.rb2c, do_dcorr ? dmodel : nullptr, sh.db2c, sh, corr & 1, v0, v1);
+      ClosestViews<T>(do_rcorr ? rmodel : nullptr, do_dcorr ? dmodel : nullptr, sh, corr & 1, v0, v1);
       M3TB_STAMP();  // closest views
       if (do_rcorr) {
         RegionIter rit;
@@ -1374,7 +1390,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   RegionIter it;
   MakeRegionIter(rp, cam, sh.rb2c, 0, it);
   int view, unused;
-  ClosestViews<kBlockThreads>(&model, it.b2c, nullptr, it.b2c, sh, 0, view, unused);
+  ClosestViews<kBlockThreads>(&model, nullptr, sh, 0, view, unused);
   int n_lines = AdaptiveCount(rp.n_lines_max, rp.use_adaptive_coverage, rp.reference_contour_length,
                               __ldg(model.view_scalars + view), model.max_view_scalar, model.n_points);
   const float4* pts = model.points + size_t(view) * model.n_points * 2;
