@@ -1271,6 +1271,10 @@ struct HistArgs {
 // frame over PCIe into the device copy - ~1/7 of the frame at 0.6 m - and recorded as the body's RoiRecord.
 // Pixels outside it are still reachable (FrameView falls back to the pinned frame), so this never changes a result.
 // ---------------------------------------------------------------------------------------------
+// pixels of pose motion (since the ROI was fetched) that stay inside the device copy; beyond it samples are served
+// from the pinned frame directly (correct, slower)
+constexpr float kIngestMotionMarginPx = 12.0f;
+
 struct IngestArgs {
   const BodyDev* bodies;
   const float* poses;
@@ -1342,14 +1346,14 @@ __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
         const ModelDev& m = args.region_models[body.region_model];
         int s_max = 1;
         for (int c = 0; c < body.rp.n_scales; ++c) s_max = max(s_max, body.rp.scales[c]);
-        const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + 24.0f;
+        const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + kIngestMotionMarginPx;
         RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 16, t);
       } else {
         const ModelDev& m = args.depth_models[body.depth_model];
         float d_max = 0.0f;
         for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
         const float z = b2c[11];
-        const float reach = (z > 2.0f * m.radius) ? d_max * cam.fu / (z - m.radius) + 2.0f + 16.0f : 0.0f;
+        const float reach = (z > 2.0f * m.radius) ? d_max * cam.fu / (z - m.radius) + 2.0f + kIngestMotionMarginPx : 0.0f;
         RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 8, t);
       }
       rect[which] = t;
