@@ -201,6 +201,7 @@ class Workload:
     start_body2world: np.ndarray            # [nb,3,4]
     seed: int = 0
     notes: dict = field(default_factory=dict)
+    structures: list | None = None          # [StructureSpec] (kinematic structures, config 5); None = rigid bodies
 
     @property
     def lines_per_body(self):
@@ -209,6 +210,69 @@ class Workload:
     @property
     def points_per_body(self):
         return self.depth.n_points_max if self.depth else 0
+
+
+@dataclass
+class LinkSpec:
+    """One m3t::Link (link.h:150-156). body: index into the workload's bodies or -1; parent: index into the
+    structure's link list (links are listed in Optimizer::ReferencedLinks() order, parent < own index) or -1."""
+    body: int
+    parent: int
+    body2joint: np.ndarray = None           # [3,4]
+    joint2parent: np.ndarray = None         # [3,4]
+    free_directions: tuple = (1, 1, 1, 1, 1, 1)
+    fixed_body2joint_pose: bool = True
+    link2world: np.ndarray = None           # [3,4], links without a body only
+
+
+@dataclass
+class ConstraintSpec:
+    """m3t::Constraint (constraint.h:109-112), or m3t::SoftConstraint when `soft` (soft_constraint.h:128-136)."""
+    link1: int
+    link2: int
+    body12joint1: np.ndarray = None
+    body22joint2: np.ndarray = None
+    directions: tuple = (0, 0, 0, 0, 0, 0)
+    soft: bool = False
+    max_distance_rotation: float = 0.0
+    max_distance_translation: float = 0.0
+    standard_deviation_rotation: float = 0.01
+    standard_deviation_translation: float = 0.001
+
+
+@dataclass
+class StructureSpec:
+    """One m3t::Optimizer with its link tree and constraints."""
+    links: list
+    constraints: list = field(default_factory=list)
+    tikhonov_rotation: float = 1000.0
+    tikhonov_translation: float = 30000.0
+
+    @property
+    def dof(self):
+        return sum(int(sum(1 for d in l.free_directions if d)) for l in self.links)
+
+    @property
+    def n_constraint_rows(self):
+        return sum(int(sum(1 for d in c.directions if d)) for c in self.constraints if not c.soft)
+
+
+def identity_pose():
+    p = np.zeros((3, 4), np.float32)
+    p[:, :3] = np.eye(3, dtype=np.float32)
+    return p
+
+
+def translation_pose(x=0.0, y=0.0, z=0.0):
+    p = identity_pose()
+    p[:, 3] = (x, y, z)
+    return p
+
+
+def rotation_pose(axis, deg):
+    p = identity_pose()
+    p[:, :3] = _rot(axis, deg)
+    return p
 
 
 PRESETS = {
@@ -237,6 +301,88 @@ def _rot(axis, deg):
     return np.array([[c + x * x * Cc, x * y * Cc - z * s, x * z * Cc + y * s],
                      [y * x * Cc + z * s, c + y * y * Cc, y * z * Cc - x * s],
                      [z * x * Cc - y * s, z * y * Cc + x * s, c + z * z * Cc]])
+
+
+def make_chain_workload(n_chains=2, n_links=8, n_lines=300, n_points=300, variant="projected", n_divides=4, seed=0,
+                        rot_deg=3.0, trans_m=0.005, joint_deg=3.0, color_sigma=10.0, first_chain=0, frames=True,
+                        models=None, soft=False) -> Workload:
+    """BASELINE.json configs[4] shape: n_chains instances of an n_links serial chain, RTB-shape
+    parameters (examples/evaluate_rtb_dataset.cpp:27-66), chain geometry of examples/optimization_time.cpp.
+
+    variant "projected" (optimization_time.cpp:48-56): root link with 6 DoF, every further link is the child of the
+    previous one with joint2parent = Tx(0.01) and one revolute DoF about x -> 6 + (n_links-1) unknowns.
+    variant "constrained" (optimization_time.cpp:32-46): every link is a 6-DoF child of the root and consecutive
+    links are tied by a Constraint with body12joint1 = Tx(-0.01), directions (0,1,1,1,1,1) -> 6 n_links unknowns + 5
+    (n_links-1) constraint rows. soft=True uses SoftConstraints instead of Constraints in the constrained variant.
+    Bodies are numbered chain * n_links + link. Every link is observed in its own RGB-D pair by the same camera pair
+    (deviation from "one pair per instance": the links of this chain geometry overlap in space, rendering them into
+    one frame would make the silhouettes meaningless; the arithmetic of the path is unaffected)."""
+    nb = n_chains * n_links
+    region = RegionSettings(n_lines_max=n_lines, scales=(9, 7, 5, 2), standard_deviations=(25.0, 15.0, 10.0)) if n_lines else None
+    depth = DepthSettings(n_points_max=n_points, stride_length=0.008, considered_distances=(0.1, 0.08, 0.05),
+                          standard_deviations=(0.05, 0.03, 0.02)) if n_points else None
+    ci, di = default_color_intrinsics(False), default_depth_intrinsics()
+    c_w2c = np.zeros((3, 4), np.float32)
+    c_w2c[:, :3] = _rot((0.2, 1.0, 0.1), 4.0)
+    c_w2c[:, 3] = (0.01, -0.02, 0.03)
+    d_rel = np.zeros((3, 4), np.float32)
+    d_rel[:, :3] = _rot((1.0, 0.3, -0.2), 0.6)
+    d_rel[:, 3] = (-0.015, 0.001, 0.002)
+    d_w2c = pose_mul(d_rel, c_w2c)
+    c_c2w = pose_inv(c_w2c)
+    if models is not None:
+        region_model, depth_model = models
+    else:
+        region_model = generate_region_model(n_divides, max(n_lines, 1), 0.8, seed) if region else None
+        depth_model = generate_depth_model(n_divides, max(n_points, 1), 0.8, seed) if depth else None
+    gt = np.zeros((nb, 3, 4), np.float32)
+    start = np.zeros((nb, 3, 4), np.float32)
+    pitch = (3 * ci.width + 15) // 16 * 16
+    color = np.zeros((nb, ci.height, pitch), np.uint8) if (region and frames) else None
+    dframes = np.zeros((nb, di.height, di.width), np.uint16) if (depth and frames) else None
+    offset = translation_pose(0.01)
+    structures = []
+    for c in range(n_chains):
+        gc = first_chain + c
+        rng = np.random.default_rng([seed, 77, gc])
+        q_gt = rng.uniform(-12.0, 12.0, n_links)
+        q_start = q_gt + rng.uniform(-joint_deg, joint_deg, n_links)
+        root_gt = pose_mul(c_c2w, ground_truth_pose(seed, 100000 + gc, ci, 200.0, 0.6, 0.8))
+        root_start = perturb_pose(seed, 100000 + gc, rot_deg, trans_m, root_gt)
+        links, constraints = [], []
+        for j in range(n_links):
+            b = c * n_links + j
+            if j == 0:
+                gt[b], start[b] = root_gt, root_start
+                links.append(LinkSpec(body=b, parent=-1, body2joint=identity_pose(), joint2parent=identity_pose()))
+                continue
+            gt[b] = pose_mul(pose_mul(gt[b - 1], offset), rotation_pose((1, 0, 0), q_gt[j]))
+            start[b] = pose_mul(pose_mul(start[b - 1], offset), rotation_pose((1, 0, 0), q_start[j]))
+            if variant == "projected":
+                links.append(LinkSpec(body=b, parent=j - 1, body2joint=identity_pose(),
+                                      joint2parent=pose_mul(offset, rotation_pose((1, 0, 0), q_start[j])),
+                                      free_directions=(1, 0, 0, 0, 0, 0)))
+            else:
+                links.append(LinkSpec(body=b, parent=0, body2joint=identity_pose(),
+                                      joint2parent=pose_mul(pose_inv(start[c * n_links]), start[b])))
+                constraints.append(ConstraintSpec(link1=j - 1, link2=j, body12joint1=translation_pose(-0.01),
+                                                  body22joint2=identity_pose(), directions=(0, 1, 1, 1, 1, 1), soft=soft))
+        structures.append(StructureSpec(links=links, constraints=constraints, tikhonov_rotation=100.0,
+                                        tikhonov_translation=1000.0))
+        for j in range(n_links):
+            b = c * n_links + j
+            gb = gc * n_links + j
+            if color is not None:
+                render_color(ci, pose_mul(c_w2c, gt[b]), seed * 1000003 + 500000 + gb, sigma=color_sigma, out=color[b])
+            if dframes is not None:
+                render_depth(di, pose_mul(d_w2c, gt[b]), seed * 1000003 + 500000 + gb, depth_scale=0.001, out=dframes[b])
+    return Workload(name="c5", n_bodies=nb, region=region, depth=depth, tikhonov_rotation=100.0,
+                    tikhonov_translation=1000.0, n_corr_iterations=6, n_update_iterations=2, color_intrinsics=ci,
+                    depth_intrinsics=di, color_world2camera=c_w2c, depth_world2camera=d_w2c, depth_scale=0.001,
+                    region_model=region_model, depth_model=depth_model, color_frames=color, depth_frames=dframes,
+                    gt_body2world=gt, start_body2world=start, seed=seed,
+                    notes=dict(n_divides=n_divides, variant=variant, n_links=n_links, n_chains=n_chains, soft=soft,
+                               first_body=first_chain * n_links), structures=structures)
 
 
 def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divides=4, seed=0, rot_deg=3.0,

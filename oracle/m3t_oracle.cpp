@@ -1107,3 +1107,461 @@ void orc_tracking_step(orc_body* bodies, int n_bodies, int iteration, int corr_b
 }
 
 }  // extern "C"
+
+// =============================================================================================
+// Kinematic structures: Link tree, Constraint, SoftConstraint, Optimizer over DoF + nc unknowns.
+// The reference has no known answers for this part (parity unpinned, see the header); float summation order of the
+// small Eigen products is taken as left-to-right.
+// =============================================================================================
+namespace {
+
+constexpr int kMaxDof = 96;  // 16 links x 6
+
+inline void Skew3(const float* v, float* m /*3x3 row-major*/) {  // Vector2Skewsymmetric (common.h:62-71)
+  m[0] = 0.0f; m[1] = -v[2]; m[2] = v[1];
+  m[3] = v[2]; m[4] = 0.0f; m[5] = -v[0];
+  m[6] = -v[1]; m[7] = v[0]; m[8] = 0.0f;
+}
+inline void Mul3(const float* a, const float* b, float* o) {
+  float r[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) r[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+  std::memcpy(o, r, sizeof(r));
+}
+
+// Link::Adjoint (link.cpp:341-348): [[R, 0], [skew(t) R, R]], row-major 6x6
+void Adjoint(const float* pose, int rotation_mode, float* m) {
+  float r[9], s[9], sr[9];
+  PoseRotation(pose, rotation_mode, r);
+  float t[3] = {T_(pose, 0), T_(pose, 1), T_(pose, 2)};
+  Skew3(t, s);
+  Mul3(s, r, sr);
+  for (int k = 0; k < 36; ++k) m[k] = 0.0f;
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      m[6 * i + j] = r[3 * i + j];
+      m[6 * (i + 3) + j] = sr[3 * i + j];
+      m[6 * (i + 3) + j + 3] = r[3 * i + j];
+    }
+}
+
+int LinkDof(const orc_link& l) {
+  int n = 0;
+  for (int d = 0; d < 6; ++d) n += l.free_directions[d] ? 1 : 0;
+  return n;
+}
+int FirstIndex(const orc_structure* s, int link) {
+  int n = 0;
+  for (int i = 0; i < link; ++i) n += LinkDof(s->links[i]);
+  return n;
+}
+int NRows(const int32_t* directions) {
+  int n = 0;
+  for (int d = 0; d < 6; ++d) n += directions[d] ? 1 : 0;
+  return n;
+}
+
+// Eigen::Quaternionf(Matrix3f) (quaternionbase_assign_impl<..,3,3>) followed by AngleAxisf = Quaternionf.
+void AngleAxisFromMatrix(const float* m /*row-major 3x3*/, float* angle, float* axis) {
+  auto M = [&](int i, int j) { return m[3 * i + j]; };
+  float q[4];  // x, y, z, w
+  float t = M(0, 0) + M(1, 1) + M(2, 2);
+  if (t > 0.0f) {
+    t = std::sqrt(t + 1.0f);
+    q[3] = 0.5f * t;
+    t = 0.5f / t;
+    q[0] = (M(2, 1) - M(1, 2)) * t;
+    q[1] = (M(0, 2) - M(2, 0)) * t;
+    q[2] = (M(1, 0) - M(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (M(1, 1) > M(0, 0)) i = 1;
+    if (M(2, 2) > M(i, i)) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = std::sqrt(M(i, i) - M(j, j) - M(k, k) + 1.0f);
+    q[i] = 0.5f * t;
+    t = 0.5f / t;
+    q[3] = (M(k, j) - M(j, k)) * t;
+    q[j] = (M(j, i) + M(i, j)) * t;
+    q[k] = (M(k, i) + M(i, k)) * t;
+  }
+  float n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (n < std::numeric_limits<float>::epsilon()) {  // stableNorm(): scaled to avoid underflow
+    double sx = q[0], sy = q[1], sz = q[2];
+    n = float(std::sqrt(sx * sx + sy * sy + sz * sz));
+  }
+  if (n != 0.0f) {
+    *angle = 2.0f * std::atan2(n, std::fabs(q[3]));
+    if (q[3] < 0.0f) n = -n;
+    axis[0] = q[0] / n; axis[1] = q[1] / n; axis[2] = q[2] / n;
+  } else {
+    *angle = 0.0f;
+    axis[0] = 1.0f; axis[1] = 0.0f; axis[2] = 0.0f;
+  }
+}
+
+float Xcotx(float x) {  // common.h:73-77
+  if (std::tan(x) <= std::numeric_limits<float>::min()) return 1.0f;
+  if (std::tan(x) >= std::numeric_limits<float>::max()) return 0.0f;
+  return float(double(x) / std::tan(double(x)));
+}
+
+struct JointGeometry {
+  float body22joint1[12], joint22joint1[12];
+  float angle, axis[3];
+  float rotation_vector[3], translation_vector[3];
+};
+
+// the "required poses" block shared by Constraint (constraint.cpp:88-92) and SoftConstraint (soft_constraint.cpp:120-124)
+void CalcJointGeometry(const float* body12joint1, const float* body22joint2, const float* link1_2world,
+                       const float* link2_2world, int rotation_mode, JointGeometry* jg) {
+  float inv1[12], tmp[12], inv22[12], rot[9];
+  PoseInverse(link1_2world, inv1);
+  PoseMul(body12joint1, inv1, tmp);
+  PoseMul(tmp, link2_2world, jg->body22joint1);
+  PoseInverse(body22joint2, inv22);
+  PoseMul(jg->body22joint1, inv22, jg->joint22joint1);
+  PoseRotation(jg->joint22joint1, rotation_mode, rot);
+  AngleAxisFromMatrix(rot, &jg->angle, jg->axis);
+  for (int i = 0; i < 3; ++i) {
+    jg->rotation_vector[i] = jg->angle * jg->axis[i];
+    jg->translation_vector[i] = T_(jg->joint22joint1, i);
+  }
+}
+
+// Constraint::UnprojectedConstraintJacobian (constraint.cpp:205-274) for the selected directions: rows[nr][6]
+int UnprojectedJacobian(const JointGeometry& jg, const float* body2joint1, const int32_t* directions, int rotation_mode,
+                        bool rotation_rows, bool translation_rows, float* rows) {
+  float inv_j[12], body2joint2[12], inv_b[12], r1[9];
+  PoseInverse(jg.joint22joint1, inv_j);
+  PoseMul(inv_j, body2joint1, body2joint2);
+  PoseInverse(body2joint2, inv_b);
+  float jt[3] = {T_(inv_b, 0), T_(inv_b, 1), T_(inv_b, 2)};  // joint22body_translation
+  PoseRotation(body2joint1, rotation_mode, r1);
+  float angle_half = 0.5f * jg.angle;
+  float xc = Xcotx(angle_half);
+  float sk[9], var[9];
+  Skew3(jg.axis, sk);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      var[3 * i + j] = (xc * (i == j ? 1.0f : 0.0f) - angle_half * sk[3 * i + j]) + ((1.0f - xc) * jg.axis[i]) * jg.axis[j];
+  int idx = 0;
+  for (int d = 0; d < 6; ++d) {
+    if (!directions[d]) continue;
+    if (d < 3 && !rotation_rows) continue;
+    if (d >= 3 && !translation_rows) continue;
+    float* row = rows + 6 * idx;
+    for (int k = 0; k < 6; ++k) row[k] = 0.0f;
+    if (d < 3) {
+      for (int j = 0; j < 3; ++j)
+        row[j] = var[3 * d] * r1[j] + var[3 * d + 1] * r1[3 + j] + var[3 * d + 2] * r1[6 + j];
+    } else {
+      const float* rr = r1 + 3 * (d - 3);
+      row[0] = jt[1] * rr[2] - jt[2] * rr[1];
+      row[1] = jt[2] * rr[0] - jt[0] * rr[2];
+      row[2] = jt[0] * rr[1] - jt[1] * rr[0];
+      row[3] = rr[0]; row[4] = rr[1]; row[5] = rr[2];
+    }
+    idx++;
+  }
+  return idx;
+}
+
+void StructureJacobians(const orc_structure* s, int rotation_mode, int dof, float* jac /*[n_links][6][dof]*/) {
+  int first = 0;
+  for (int l = 0; l < s->n_links; ++l) {
+    const orc_link& link = s->links[l];
+    float* J = jac + size_t(l) * 6 * dof;
+    if (link.parent >= 0) {
+      float prod[12], parent2body[12], ad[36];
+      PoseMul(link.joint2parent, link.body2joint, prod);
+      PoseInverse(prod, parent2body);
+      Adjoint(parent2body, rotation_mode, ad);
+      const float* Jp = jac + size_t(link.parent) * 6 * dof;
+      for (int i = 0; i < 6; ++i)
+        for (int c = 0; c < dof; ++c) {
+          float acc = 0.0f;
+          for (int k = 0; k < 6; ++k) acc += ad[6 * i + k] * Jp[size_t(k) * dof + c];
+          J[size_t(i) * dof + c] = acc;
+        }
+    } else {
+      for (int k = 0; k < 6 * dof; ++k) J[k] = 0.0f;
+    }
+    float joint2body[12], adj[36];
+    PoseInverse(link.body2joint, joint2body);
+    Adjoint(joint2body, rotation_mode, adj);
+    int idx = first;
+    for (int d = 0; d < 6; ++d)
+      if (link.free_directions[d]) {
+        for (int i = 0; i < 6; ++i) J[size_t(i) * dof + idx] = adj[6 * i + d];
+        idx++;
+      }
+    first = idx;
+  }
+}
+
+// Link::UpdatePoses for every link in pre-order (optimizer.cpp:334-346, link.cpp:205-241)
+void StructureUpdatePoses(orc_structure* s, const float* theta, int exp_mode, float* link2world) {
+  int idx = 0;
+  for (int l = 0; l < s->n_links; ++l) {
+    orc_link& link = s->links[l];
+    float th[6];
+    for (int d = 0; d < 6; ++d) th[d] = link.free_directions[d] ? theta[idx++] : 0.0f;
+    float e[9];
+    ExpSkew(th, exp_mode, e);
+    float var[12] = {e[0], e[1], e[2], th[3], e[3], e[4], e[5], th[4], e[6], e[7], e[8], th[5]};
+    float* l2w = link2world + 12 * l;
+    float tmp[12], tmp2[12];
+    if (link.parent >= 0) {
+      if (link.fixed_body2joint_pose) {
+        PoseMul(link.joint2parent, var, tmp);
+        std::memcpy(link.joint2parent, tmp, sizeof(tmp));
+      } else {
+        PoseMul(var, link.body2joint, tmp);
+        std::memcpy(link.body2joint, tmp, sizeof(tmp));
+      }
+      PoseMul(link2world + 12 * link.parent, link.joint2parent, tmp);
+      PoseMul(tmp, link.body2joint, l2w);
+    } else {
+      float inv[12];
+      PoseInverse(link.body2joint, inv);
+      PoseMul(l2w, inv, tmp);
+      PoseMul(tmp, var, tmp2);
+      PoseMul(tmp2, link.body2joint, l2w);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_structure_dof(const orc_structure* s) { return FirstIndex(s, s->n_links); }
+int orc_structure_n_constraint_rows(const orc_structure* s) {
+  int n = 0;
+  for (int c = 0; c < s->n_constraints; ++c) n += NRows(s->constraints[c].directions);
+  return n;
+}
+void orc_angle_axis(const float r[9], float* angle, float axis[3]) { AngleAxisFromMatrix(r, angle, axis); }
+float orc_xcotx(float x) { return Xcotx(x); }
+
+void orc_structure_jacobians(const orc_structure* s, int rotation_mode, float* jacobians) {
+  StructureJacobians(s, rotation_mode, orc_structure_dof(s), jacobians);
+}
+
+int orc_constraint_residual_jacobian(const orc_structure* s, int constraint, const float* link2world,
+                                     const float* jacobians, int rotation_mode, float* residual, float* jacobian) {
+  const orc_constraint& c = s->constraints[constraint];
+  const int dof = orc_structure_dof(s);
+  JointGeometry jg;
+  CalcJointGeometry(c.body12joint1, c.body22joint2, link2world + 12 * c.link1, link2world + 12 * c.link2, rotation_mode, &jg);
+  int idx = 0;
+  for (int d = 0; d < 6; ++d)  // Constraint::Residual (constraint.cpp:176-203)
+    if (c.directions[d]) residual[idx++] = d < 3 ? jg.rotation_vector[d] : jg.translation_vector[d - 3];
+  float u2[36], u1[36];
+  const int nr = UnprojectedJacobian(jg, jg.body22joint1, c.directions, rotation_mode, true, true, u2);
+  UnprojectedJacobian(jg, c.body12joint1, c.directions, rotation_mode, true, true, u1);
+  const float* J2 = jacobians + size_t(c.link2) * 6 * dof;
+  const float* J1 = jacobians + size_t(c.link1) * 6 * dof;
+  for (int r = 0; r < nr; ++r)
+    for (int col = 0; col < dof; ++col) {
+      float a2 = 0.0f, a1 = 0.0f;
+      for (int k = 0; k < 6; ++k) a2 += u2[6 * r + k] * J2[size_t(k) * dof + col];
+      for (int k = 0; k < 6; ++k) a1 += u1[6 * r + k] * J1[size_t(k) * dof + col];
+      jacobian[size_t(r) * dof + col] = a2 - a1;
+    }
+  return nr;
+}
+
+// SoftConstraint::AddGradientsAndHessiansToLink (soft_constraint.cpp:220-270)
+static void SoftAddToLink(const orc_soft_constraint& c, const JointGeometry& jg, const float* body2joint1, float sign,
+                          int rotation_mode, float* g, float* H) {
+  float grad[6] = {0, 0, 0, 0, 0, 0}, hess[36];
+  for (int k = 0; k < 36; ++k) hess[k] = 0.0f;
+  for (int part = 0; part < 2; ++part) {
+    const int32_t* dirs = c.directions;
+    int n = 0;
+    float vec[3];
+    for (int d = 0; d < 3; ++d)
+      if (dirs[d + 3 * part]) vec[n++] = part == 0 ? jg.rotation_vector[d] : jg.translation_vector[d];
+    if (!n) continue;
+    const float max_d = part == 0 ? c.max_distance_rotation : c.max_distance_translation;
+    const float sd = part == 0 ? c.standard_deviation_rotation : c.standard_deviation_translation;
+    float sq = 0.0f;
+    for (int i = 0; i < n; ++i) sq += vec[i] * vec[i];
+    const float dist = std::sqrt(sq);
+    if (!(dist > max_d)) continue;
+    float rows[18];
+    UnprojectedJacobian(jg, body2joint1, dirs, rotation_mode, part == 0, part == 1, rows);
+    float unit[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) unit[i] = vec[i];
+    if (sq > 0.0f)
+      for (int i = 0; i < n; ++i) unit[i] = vec[i] / dist;
+    const float inv_var = 1.0f / (sd * sd);
+    // gradient -= (sign / sd^2) * J^T * (vec - unit * max_d)
+    float e[3];
+    for (int i = 0; i < n; ++i) e[i] = vec[i] - unit[i] * max_d;
+    for (int k = 0; k < 6; ++k) {
+      float acc = 0.0f;
+      for (int i = 0; i < n; ++i) acc += rows[6 * i + k] * e[i];
+      grad[k] -= (sign * inv_var) * acc;
+    }
+    // hessian -= (1 / sd^2) * J^T * (I - (max_d / dist) * (I - unit unit^T)) * J
+    float w[9];
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < n; ++j) {
+        const float id = i == j ? 1.0f : 0.0f;
+        w[3 * i + j] = id - (max_d / dist) * (id - unit[i] * unit[j]);
+      }
+    for (int a = 0; a < 6; ++a)
+      for (int b = 0; b < 6; ++b) {
+        float acc = 0.0f;
+        for (int i = 0; i < n; ++i) {
+          float jw = 0.0f;
+          for (int k = 0; k < n; ++k) jw += rows[6 * k + a] * w[3 * k + i];
+          acc += jw * rows[6 * i + b];
+        }
+        hess[6 * a + b] -= inv_var * acc;
+      }
+  }
+  for (int k = 0; k < 6; ++k) g[k] += grad[k];      // Link::AddToGradientAndHessian (link.cpp:195-203)
+  for (int k = 0; k < 36; ++k) H[k] += hess[k];
+}
+
+void orc_soft_constraint_add(const orc_structure* s, int soft_constraint, const float* link2world, int rotation_mode,
+                             float* g, float* H) {
+  const orc_soft_constraint& c = s->soft_constraints[soft_constraint];
+  JointGeometry jg;
+  CalcJointGeometry(c.body12joint1, c.body22joint2, link2world + 12 * c.link1, link2world + 12 * c.link2, rotation_mode, &jg);
+  SoftAddToLink(c, jg, c.body12joint1, -1.0f, rotation_mode, g + 6 * c.link1, H + 36 * c.link1);
+  SoftAddToLink(c, jg, jg.body22joint1, 1.0f, rotation_mode, g + 6 * c.link2, H + 36 * c.link2);
+}
+
+int orc_optimize_structure(orc_structure* s, const float* g_in, const float* H_in, int rotation_mode, int exp_mode,
+                           float* link2world, float* theta_out) {
+  const int dof = orc_structure_dof(s);
+  const int nc = orc_structure_n_constraint_rows(s);
+  const int n = dof + nc;
+  if (dof > kMaxDof || n > kMaxN || n < 1) return -1;
+  const int nl = s->n_links;
+  std::vector<float> jac(size_t(nl) * 6 * dof), g(g_in, g_in + size_t(nl) * 6), H(H_in, H_in + size_t(nl) * 36);
+  // CalculateDataLinks (optimizer.cpp:283-299): Jacobians + modality sums (given), then the soft constraints
+  StructureJacobians(s, rotation_mode, dof, jac.data());
+  for (int c = 0; c < s->n_soft_constraints; ++c) orc_soft_constraint_add(s, c, link2world, rotation_mode, g.data(), H.data());
+  std::vector<float> a(size_t(n) * n, 0.0f), b(n, 0.0f), theta(n, 0.0f);
+  // AddProjectedGradientsAndHessians (optimizer.cpp:308-320)
+  for (int l = 0; l < nl; ++l) {
+    const float* J = jac.data() + size_t(l) * 6 * dof;
+    const float* gl = g.data() + 6 * l;
+    const float* Hl = H.data() + 36 * l;
+    for (int i = 0; i < dof; ++i) {
+      float acc = 0.0f;
+      for (int k = 0; k < 6; ++k) acc += J[size_t(k) * dof + i] * gl[k];
+      b[i] += acc;
+      float jh[6];
+      for (int q = 0; q < 6; ++q) {
+        float t = 0.0f;
+        for (int k = 0; k < 6; ++k) t += J[size_t(k) * dof + i] * Hl[6 * k + q];
+        jh[q] = t;
+      }
+      for (int j = 0; j <= i; ++j) {
+        float t = 0.0f;
+        for (int q = 0; q < 6; ++q) t += jh[q] * J[size_t(q) * dof + j];
+        a[size_t(i) * n + j] -= t;
+      }
+    }
+  }
+  // AddResidualsAndConstraintJacobians (optimizer.cpp:322-332)
+  int idx = dof;
+  std::vector<float> res(6), cj(size_t(6) * std::max(dof, 1));
+  for (int c = 0; c < s->n_constraints; ++c) {
+    const int nr = orc_constraint_residual_jacobian(s, c, link2world, jac.data(), rotation_mode, res.data(), cj.data());
+    for (int r = 0; r < nr; ++r) {
+      b[idx + r] = res[r];
+      for (int col = 0; col < dof; ++col) a[size_t(idx + r) * n + col] = -cj[size_t(r) * dof + col];
+    }
+    idx += nr;
+  }
+  // tikhonov_vector_ (optimizer.cpp:236-252)
+  int di = 0;
+  for (int l = 0; l < nl; ++l)
+    for (int d = 0; d < 6; ++d)
+      if (s->links[l].free_directions[d]) {
+        a[size_t(di) * n + di] += d < 3 ? s->tikhonov_rotation : s->tikhonov_translation;
+        di++;
+      }
+  LdltSolve(n, a.data(), b.data(), theta.data());
+  if (theta_out) std::memcpy(theta_out, theta.data(), sizeof(float) * n);
+  for (int i = 0; i < n; ++i)
+    if (std::isnan(theta[i])) return 0;  // optimizer.cpp:165
+  StructureUpdatePoses(s, theta.data(), exp_mode, link2world);
+  return 1;
+}
+
+void orc_structure_consistent_poses(orc_structure* s, int exp_mode, float* link2world) {
+  std::vector<float> theta(size_t(std::max(1, orc_structure_dof(s))), 0.0f);
+  StructureUpdatePoses(s, theta.data(), exp_mode, link2world);
+}
+
+void orc_tracking_step_structures(orc_body* bodies, orc_structure* structures, int n_structures, int iteration,
+                                  int corr_begin, int corr_end, int n_update, int rotation_mode, int exp_mode,
+                                  int n_threads, float* bodyless_link2world, int max_links) {
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
+  for (int si = 0; si < n_structures; ++si) {
+    orc_structure* s = &structures[si];
+    const int nl = s->n_links;
+    std::vector<float> l2w(size_t(nl) * 12), g(size_t(nl) * 6), H(size_t(nl) * 36);
+    auto gather = [&]() {
+      for (int l = 0; l < nl; ++l) {
+        const int bi = s->links[l].body;
+        const float* src = bi >= 0 ? bodies[bi].body2world : bodyless_link2world + (size_t(si) * max_links + l) * 12;
+        std::memcpy(&l2w[12 * l], src, 12 * sizeof(float));
+      }
+    };
+    auto scatter = [&]() {
+      for (int l = 0; l < nl; ++l) {
+        const int bi = s->links[l].body;
+        float* dst = bi >= 0 ? bodies[bi].body2world : bodyless_link2world + (size_t(si) * max_links + l) * 12;
+        std::memcpy(dst, &l2w[12 * l], 12 * sizeof(float));
+      }
+    };
+    for (int corr = corr_begin; corr < corr_end; ++corr) {
+      for (int l = 0; l < nl; ++l) {
+        if (s->links[l].body < 0) continue;
+        orc_body* b = &bodies[s->links[l].body];
+        if (b->region)
+          b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, nullptr, b->histogram_f,
+                                                  b->histogram_b, b->body2world, iteration, b->first_iteration, corr,
+                                                  rotation_mode, b->lines, &b->region_view);
+        if (b->depth)
+          b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
+                                                  b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);
+      }
+      for (int upd = 0; upd < n_update; ++upd) {
+        std::fill(g.begin(), g.end(), 0.0f);
+        std::fill(H.begin(), H.end(), 0.0f);
+        for (int l = 0; l < nl; ++l) {
+          if (s->links[l].body < 0) continue;
+          orc_body* b = &bodies[s->links[l].body];
+          float gm[6], Hm[36];
+          if (b->region) {
+            orc_region_gradient_hessian(b->region, b->color, b->body2world, b->lines, b->n_lines, corr, upd,
+                                        rotation_mode, gm, Hm);
+            for (int i = 0; i < 6; ++i) g[6 * l + i] += gm[i];
+            for (int i = 0; i < 36; ++i) H[36 * l + i] += Hm[i];
+          }
+          if (b->depth) {
+            orc_depth_gradient_hessian(b->depth, b->depth_frame, b->body2world, b->points, b->n_points, corr, gm, Hm);
+            for (int i = 0; i < 6; ++i) g[6 * l + i] += gm[i];
+            for (int i = 0; i < 36; ++i) H[36 * l + i] += Hm[i];
+          }
+        }
+        gather();
+        orc_optimize_structure(s, g.data(), H.data(), rotation_mode, exp_mode, l2w.data(), nullptr);
+        scatter();
+      }
+    }
+  }
+}
+
+}  // extern "C"

@@ -96,6 +96,31 @@ class Body(C.Structure):
                 ("n_points", C.c_int32), ("region_view", C.c_int32), ("depth_view", C.c_int32)]
 
 
+class Link(C.Structure):
+    _fields_ = [("body", C.c_int32), ("parent", C.c_int32), ("body2joint", C.c_float * 12),
+                ("joint2parent", C.c_float * 12), ("free_directions", C.c_int32 * 6),
+                ("fixed_body2joint_pose", C.c_int32)]
+
+
+class Constraint(C.Structure):
+    _fields_ = [("link1", C.c_int32), ("link2", C.c_int32), ("body12joint1", C.c_float * 12),
+                ("body22joint2", C.c_float * 12), ("directions", C.c_int32 * 6)]
+
+
+class SoftConstraint(C.Structure):
+    _fields_ = [("link1", C.c_int32), ("link2", C.c_int32), ("body12joint1", C.c_float * 12),
+                ("body22joint2", C.c_float * 12), ("directions", C.c_int32 * 6),
+                ("max_distance_rotation", C.c_float), ("max_distance_translation", C.c_float),
+                ("standard_deviation_rotation", C.c_float), ("standard_deviation_translation", C.c_float)]
+
+
+class Structure(C.Structure):
+    _fields_ = [("links", C.POINTER(Link)), ("n_links", C.c_int32), ("constraints", C.POINTER(Constraint)),
+                ("n_constraints", C.c_int32), ("soft_constraints", C.POINTER(SoftConstraint)),
+                ("n_soft_constraints", C.c_int32), ("tikhonov_rotation", C.c_float),
+                ("tikhonov_translation", C.c_float)]
+
+
 _libs = {}
 
 
@@ -150,6 +175,23 @@ def lib(native=False):
                                     C.c_int, C.POINTER(C.c_double)]
     L.orc_calculate_results.argtypes = [C.POINTER(Body), C.c_int, C.c_int, C.c_int, C.c_int]
     L.orc_max_threads.restype = C.c_int
+    sp = C.POINTER(Structure)
+    L.orc_structure_dof.argtypes = [sp]
+    L.orc_structure_dof.restype = C.c_int
+    L.orc_structure_n_constraint_rows.argtypes = [sp]
+    L.orc_structure_n_constraint_rows.restype = C.c_int
+    L.orc_angle_axis.argtypes = [fp, fp, fp]
+    L.orc_xcotx.argtypes = [C.c_float]
+    L.orc_xcotx.restype = C.c_float
+    L.orc_structure_jacobians.argtypes = [sp, C.c_int, fp]
+    L.orc_constraint_residual_jacobian.argtypes = [sp, C.c_int, fp, fp, C.c_int, fp, fp]
+    L.orc_constraint_residual_jacobian.restype = C.c_int
+    L.orc_soft_constraint_add.argtypes = [sp, C.c_int, fp, C.c_int, fp, fp]
+    L.orc_optimize_structure.argtypes = [sp, fp, fp, C.c_int, C.c_int, fp, fp]
+    L.orc_optimize_structure.restype = C.c_int
+    L.orc_structure_consistent_poses.argtypes = [sp, C.c_int, fp]
+    L.orc_tracking_step_structures.argtypes = [C.POINTER(Body), sp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                               C.c_int, C.c_int, C.c_int, fp, C.c_int]
     _libs[key] = L
     return L
 
@@ -209,6 +251,59 @@ def make_model(m) -> Model:
     return om
 
 
+class OracleStructure:
+    """ctypes image of one synth.StructureSpec (kept alive together with its arrays)."""
+
+    def __init__(self, spec):
+        self.spec = spec
+        nl = len(spec.links)
+        hard = [c for c in spec.constraints if not c.soft]
+        soft = [c for c in spec.constraints if c.soft]
+        self.links = (Link * nl)()
+        self.constraints = (Constraint * max(1, len(hard)))()
+        self.soft = (SoftConstraint * max(1, len(soft)))()
+        for i, l in enumerate(spec.links):
+            L_ = self.links[i]
+            L_.body, L_.parent = l.body, l.parent
+            L_.body2joint[:] = f32(l.body2joint).reshape(12).tolist()
+            L_.joint2parent[:] = f32(l.joint2parent).reshape(12).tolist()
+            L_.free_directions[:] = [int(bool(d)) for d in l.free_directions]
+            L_.fixed_body2joint_pose = int(l.fixed_body2joint_pose)
+        for arr, items in ((self.constraints, hard), (self.soft, soft)):
+            for i, c in enumerate(items):
+                K = arr[i]
+                K.link1, K.link2 = c.link1, c.link2
+                K.body12joint1[:] = f32(c.body12joint1).reshape(12).tolist()
+                K.body22joint2[:] = f32(c.body22joint2).reshape(12).tolist()
+                K.directions[:] = [int(bool(d)) for d in c.directions]
+                if c.soft:
+                    K.max_distance_rotation, K.max_distance_translation = c.max_distance_rotation, c.max_distance_translation
+                    K.standard_deviation_rotation = c.standard_deviation_rotation
+                    K.standard_deviation_translation = c.standard_deviation_translation
+        self.n_hard, self.n_soft = len(hard), len(soft)
+
+    def fill(self, S: Structure):
+        S.links = C.cast(self.links, C.POINTER(Link))
+        S.n_links = len(self.spec.links)
+        S.constraints = C.cast(self.constraints, C.POINTER(Constraint))
+        S.n_constraints = self.n_hard
+        S.soft_constraints = C.cast(self.soft, C.POINTER(SoftConstraint))
+        S.n_soft_constraints = self.n_soft
+        S.tikhonov_rotation, S.tikhonov_translation = self.spec.tikhonov_rotation, self.spec.tikhonov_translation
+
+    def as_struct(self) -> Structure:
+        S = Structure()
+        self.fill(S)
+        return S
+
+    def joint_poses(self):
+        """(body2joint[n_links,3,4], joint2parent[n_links,3,4]) as they stand after the last update."""
+        nl = len(self.spec.links)
+        b2j = np.array([list(self.links[i].body2joint) for i in range(nl)], np.float32).reshape(nl, 3, 4)
+        j2p = np.array([list(self.links[i].joint2parent) for i in range(nl)], np.float32).reshape(nl, 3, 4)
+        return b2j, j2p
+
+
 def _intr(i) -> Intrinsics:
     return Intrinsics(i.fu, i.fv, i.ppu, i.ppv, i.width, i.height)
 
@@ -261,6 +356,18 @@ class OracleTracker:
             B.tikhonov_rotation = wl.tikhonov_rotation
             B.tikhonov_translation = wl.tikhonov_translation
         self.set_poses(wl.start_body2world)
+        self.structures = None
+        if getattr(wl, "structures", None):
+            self.structure_objs = [OracleStructure(sp) for sp in wl.structures]
+            self.structures = (Structure * len(self.structure_objs))()
+            for i, so in enumerate(self.structure_objs):
+                so.fill(self.structures[i])
+            self.max_links = max(len(sp.links) for sp in wl.structures)
+            self.bodyless = np.zeros((len(wl.structures), self.max_links, 12), np.float32)
+            for i, sp in enumerate(wl.structures):
+                for j, l in enumerate(sp.links):
+                    if l.body < 0:
+                        self.bodyless[i, j] = f32(l.link2world if l.link2world is not None else np.eye(4)[:3]).reshape(12)
 
     def set_poses(self, poses):
         p = f32(poses).reshape(self.wl.n_bodies, 12)
@@ -280,6 +387,11 @@ class OracleTracker:
         n_update = self.wl.n_update_iterations if n_update is None else n_update
         first = 0 if first is None else first
         count = self.wl.n_bodies - first if count is None else count
+        if self.structures is not None:  # one Optimizer per kinematic structure
+            self.L.orc_tracking_step_structures(self.bodies, self.structures, len(self.structure_objs), iteration,
+                                                corr_begin, n_corr, n_update, self.rotation_mode, self.exp_mode,
+                                                self.n_threads, ptr(self.bodyless), self.max_links)
+            return [0.0, 0.0, 0.0, 0.0]
         phases = (C.c_double * 4)()
         base = C.cast(C.byref(self.bodies, first * C.sizeof(Body)), C.POINTER(Body))
         self.L.orc_tracking_step(base, count, iteration, corr_begin, n_corr, n_update, self.rotation_mode,
