@@ -52,6 +52,21 @@ class OptimizerParams(C.Structure):
     _fields_ = [("tikhonov_parameter_rotation", C.c_float), ("tikhonov_parameter_translation", C.c_float)]
 
 
+class Link(C.Structure):
+    """m3tb_link (m3t::Link, link.h:150-156)."""
+    _fields_ = [("body", C.c_int32), ("parent", C.c_int32), ("body2joint", C.c_float * 12),
+                ("joint2parent", C.c_float * 12), ("link2world", C.c_float * 12), ("free_directions", C.c_int32 * 6),
+                ("fixed_body2joint_pose", C.c_int32)]
+
+
+class Constraint(C.Structure):
+    """m3tb_constraint (m3t::Constraint / m3t::SoftConstraint)."""
+    _fields_ = [("link1", C.c_int32), ("link2", C.c_int32), ("body12joint1", C.c_float * 12),
+                ("body22joint2", C.c_float * 12), ("directions", C.c_int32 * 6), ("soft", C.c_int32),
+                ("max_distance_rotation", C.c_float), ("max_distance_translation", C.c_float),
+                ("standard_deviation_rotation", C.c_float), ("standard_deviation_translation", C.c_float)]
+
+
 REGION_LINE_DTYPE = np.dtype([("model_index", "<i4"), ("valid", "<i4"), ("center_f_body", "<f4", 3),
                               ("center_u", "<f4"), ("center_v", "<f4"), ("normal_u", "<f4"), ("normal_v", "<f4"),
                               ("delta_r", "<f4"), ("normal_component_to_scale", "<f4"), ("distribution", "<f4", 12),
@@ -70,7 +85,9 @@ SYMBOLS = [
     "m3tb_start_modalities", "m3tb_calculate_results", "m3tb_region_correspondences",
     "m3tb_region_gradient_hessian", "m3tb_depth_correspondences", "m3tb_depth_gradient_hessian",
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
-    "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes",
+    "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes", "m3tb_set_structure", "m3tb_clear_structures",
+    "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
+    "m3tb_set_gradient_hessian",
 ]
 
 _lib = None
@@ -123,6 +140,13 @@ def lib():
     L.m3tb_get_region_lines.argtypes = [vp, ci, vp, ci, C.POINTER(ci)]
     L.m3tb_get_depth_points.argtypes = [vp, ci, vp, ci, C.POINTER(ci)]
     L.m3tb_get_closest_views.argtypes = [vp, ci, C.POINTER(ci), C.POINTER(ci)]
+    L.m3tb_set_structure.argtypes = [vp, ci, C.POINTER(Link), ci, C.POINTER(Constraint), ci, C.POINTER(OptimizerParams)]
+    L.m3tb_clear_structures.argtypes = [vp]
+    L.m3tb_n_structures.argtypes = [vp]
+    L.m3tb_calculate_consistent_poses.argtypes = [vp]
+    L.m3tb_get_link_poses.argtypes = [vp, ci, fp, fp, fp]
+    L.m3tb_get_structure_theta.argtypes = [vp, ci, fp, ci, C.POINTER(ci), C.POINTER(ci)]
+    L.m3tb_set_gradient_hessian.argtypes = [vp, ci, fp, fp]
     _lib = L
     return L
 
@@ -306,6 +330,63 @@ class Context:
     def calculate_optimization(self, iteration, corr, opt):
         self._ck(self.L.m3tb_calculate_optimization(self.h, iteration, corr, opt))
 
+    # -- kinematic structures (Optimizer with Link tree / Constraints / SoftConstraints) --
+    def set_structure(self, index, spec, body_offset=0):
+        """spec: synth.StructureSpec (links in pre-order). body_offset is subtracted from the link body indices
+        (a context that holds bodies [first, first+count) of a workload)."""
+        nl = len(spec.links)
+        links = (Link * nl)()
+        for i, l in enumerate(spec.links):
+            K = links[i]
+            K.body = l.body - body_offset if l.body >= 0 else -1
+            K.parent = l.parent
+            K.body2joint[:] = np.asarray(l.body2joint, np.float32).reshape(12).tolist()
+            K.joint2parent[:] = np.asarray(l.joint2parent, np.float32).reshape(12).tolist()
+            l2w = l.link2world if l.link2world is not None else np.eye(4, dtype=np.float32)[:3]
+            K.link2world[:] = np.asarray(l2w, np.float32).reshape(12).tolist()
+            K.free_directions[:] = [int(bool(d)) for d in l.free_directions]
+            K.fixed_body2joint_pose = int(l.fixed_body2joint_pose)
+        nc = len(spec.constraints)
+        cons = (Constraint * max(nc, 1))()
+        for i, c in enumerate(spec.constraints):
+            K = cons[i]
+            K.link1, K.link2 = c.link1, c.link2
+            K.body12joint1[:] = np.asarray(c.body12joint1, np.float32).reshape(12).tolist()
+            K.body22joint2[:] = np.asarray(c.body22joint2, np.float32).reshape(12).tolist()
+            K.directions[:] = [int(bool(d)) for d in c.directions]
+            K.soft = int(c.soft)
+            K.max_distance_rotation, K.max_distance_translation = c.max_distance_rotation, c.max_distance_translation
+            K.standard_deviation_rotation = c.standard_deviation_rotation
+            K.standard_deviation_translation = c.standard_deviation_translation
+        op = OptimizerParams(spec.tikhonov_rotation, spec.tikhonov_translation)
+        self._ck(self.L.m3tb_set_structure(self.h, index, links, nl, cons, nc, C.byref(op)))
+
+    def set_gradient_hessian(self, modality, g, H):
+        g = np.ascontiguousarray(g, np.float32)
+        H = np.ascontiguousarray(H, np.float32)
+        self._ck(self.L.m3tb_set_gradient_hessian(self.h, modality, _p(g), _p(H)))
+
+    def clear_structures(self):
+        self._ck(self.L.m3tb_clear_structures(self.h))
+
+    def n_structures(self):
+        return self.L.m3tb_n_structures(self.h)
+
+    def calculate_consistent_poses(self):
+        self._ck(self.L.m3tb_calculate_consistent_poses(self.h))
+
+    def get_link_poses(self, structure, n_links):
+        """(body2joint, joint2parent, link2world), each [n_links, 3, 4]."""
+        out = [np.zeros((n_links, 3, 4), np.float32) for _ in range(3)]
+        self._ck(self.L.m3tb_get_link_poses(self.h, structure, _p(out[0]), _p(out[1]), _p(out[2])))
+        return tuple(out)
+
+    def get_structure_theta(self, structure, capacity=128):
+        th = np.zeros(capacity, np.float32)
+        n, upd = C.c_int(0), C.c_int(0)
+        self._ck(self.L.m3tb_get_structure_theta(self.h, structure, _p(th), capacity, C.byref(n), C.byref(upd)))
+        return th[:n.value], bool(upd.value)
+
     def get_region_lines(self, body, capacity):
         out = np.zeros(capacity, REGION_LINE_DTYPE)
         n = C.c_int(0)
@@ -361,5 +442,13 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
     for b in range(count):
         ctx.set_body(b, rp, dp, op, 0, 0, b, b)
     ctx.set_poses(wl.start_body2world[first:first + count])
+    if getattr(wl, "structures", None):  # structures whose bodies all lie inside [first, first+count)
+        k = 0
+        for sp in wl.structures:
+            ids = [l.body for l in sp.links if l.body >= 0]
+            if ids and (min(ids) < first or max(ids) >= first + count):
+                continue
+            ctx.set_structure(k, sp, body_offset=first)
+            k += 1
     ctx.synchronize()
     return ctx

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "m3t_b200_kernels.cuh"
+#include "m3t_b200_structures.cuh"
 
 using namespace m3tb;
 
@@ -20,6 +21,14 @@ struct ImagePool {
   size_t frame_bytes = 0;
   unsigned pitch = 0;
   int width = 0, height = 0, capacity = 0;
+};
+
+// One m3t::Optimizer with more than a single free root link (host image; flattened into the device tables on demand)
+struct StructureHost {
+  std::vector<LinkDev> links;
+  std::vector<ConstraintDev> constraints;
+  float tikhonov_rotation = 1000.0f, tikhonov_translation = 30000.0f;
+  bool set = false;
 };
 
 struct ModelAlloc {
@@ -66,6 +75,21 @@ struct m3tb_ctx {
   bool roi_ingest = true;                 // M3TB_NO_ROI_INGEST=1 forces full-frame copies
   long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
+
+  // kinematic structures (empty: every body is its own rigid-body optimiser inside k_track)
+  std::vector<StructureHost> structures;
+  bool structures_dirty = false;
+  int n_struct_launch = 0;                 // user structures + one implicit structure per unreferenced body
+  std::vector<int> struct_first_link;      // per launched structure
+  std::vector<StructureDev> h_structures;
+  StructureDev* d_structures = nullptr;
+  LinkDev* d_links = nullptr;
+  ConstraintDev* d_constraints = nullptr;
+  int cap_structures = 0, cap_links = 0, cap_constraints = 0;
+  float* d_gh_link = nullptr;
+  float* d_theta = nullptr;
+  int* d_struct_status = nullptr;
+  size_t struct_smem = 0;
 };
 
 namespace {
@@ -245,6 +269,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   a.counts = ctx->d_counts;
   a.gh_region = ctx->d_gh_region;
   a.gh_depth = ctx->d_gh_depth;
+  a.gh_link = ctx->d_gh_link;
   a.iteration = iteration;
   a.corr_begin = corr_begin;
   a.corr_end = corr_end;
@@ -280,6 +305,162 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
 #undef M3TB_LAUNCH
   CU(cudaGetLastError());
   ctx->launches++;
+  return M3TB_OK;
+}
+
+
+// ---- kinematic structures -------------------------------------------------------------------------------------
+bool HasStructures(const m3tb_ctx* ctx) {
+  for (const auto& s : ctx->structures)
+    if (s.set) return true;
+  return false;
+}
+
+// The joint poses live on the device while tracking runs; bring them back before the host tables are edited.
+int PullLinks(m3tb_ctx* ctx) {
+  if (ctx->structures_dirty || !ctx->d_links || ctx->n_struct_launch == 0) return M3TB_OK;
+  int total = 0;
+  for (const auto& s : ctx->structures) total += int(s.links.size());
+  if (total == 0) return M3TB_OK;
+  std::vector<LinkDev> tmp(total);
+  CU(cudaMemcpyAsync(tmp.data(), ctx->d_links, sizeof(LinkDev) * total, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  int o = 0;
+  for (auto& s : ctx->structures)
+    for (auto& l : s.links) l = tmp[o++];
+  return M3TB_OK;
+}
+
+// Flatten the user structures, append one implicit single-link structure (free root link, body2joint = identity:
+// the rigid-body optimiser) per body that no structure references, upload.
+int SyncStructures(m3tb_ctx* ctx) {
+  if (!ctx->structures_dirty) return M3TB_OK;
+  std::vector<LinkDev> links;
+  std::vector<ConstraintDev> cons;
+  std::vector<StructureDev> sts;
+  std::vector<char> used(ctx->n_bodies, 0);
+  ctx->struct_first_link.clear();
+  size_t smem = 0;
+  auto push = [&](const std::vector<LinkDev>& L, const std::vector<ConstraintDev>& C, float lr, float lt) {
+    StructureDev d;
+    d.first_link = int(links.size());
+    d.n_links = int(L.size());
+    d.first_constraint = int(cons.size());
+    d.n_constraints = int(C.size());
+    d.dof = 0;
+    for (const auto& l : L) d.dof += l.dof;
+    d.n_rows = 0;
+    for (const auto& c : C) d.n_rows += c.soft ? 0 : c.n_rows;
+    d.tikhonov_rotation = lr;
+    d.tikhonov_translation = lt;
+    ctx->struct_first_link.push_back(d.first_link);
+    links.insert(links.end(), L.begin(), L.end());
+    cons.insert(cons.end(), C.begin(), C.end());
+    sts.push_back(d);
+    smem = std::max(smem, StructSmemFloats(d.n_links, d.dof, d.dof + d.n_rows, d.n_constraints) * sizeof(float));
+  };
+  for (size_t si = 0; si < ctx->structures.size(); ++si) {
+    const StructureHost& s = ctx->structures[si];
+    if (!s.set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "structure " + std::to_string(si) + " not set (structure ids must be dense)");
+    for (const auto& l : s.links) {
+      if (l.body >= ctx->n_bodies) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "structure references a body that is not set");
+      if (l.body >= 0) {
+        if (used[l.body]) return Fail(ctx, M3TB_ERR_INVALID, "body " + std::to_string(l.body) + " is referenced by two links");
+        used[l.body] = 1;
+      }
+    }
+    push(s.links, s.constraints, s.tikhonov_rotation, s.tikhonov_translation);
+  }
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    if (used[b]) continue;
+    LinkDev l;
+    std::memset(&l, 0, sizeof(l));
+    l.body = b; l.parent = -1; l.first_index = 0; l.dof = 6; l.fixed_body2joint = 1;
+    for (int d = 0; d < 6; ++d) l.free_directions[d] = 1;
+    for (int k = 0; k < 3; ++k) l.body2joint[5 * k] = l.joint2parent[5 * k] = l.link2world[5 * k] = 1.0f;
+    push(std::vector<LinkDev>{l}, std::vector<ConstraintDev>{}, ctx->h_bodies[b].tikhonov_rotation,
+         ctx->h_bodies[b].tikhonov_translation);
+  }
+  const int ns = int(sts.size()), nl = int(links.size()), nc = int(std::max<size_t>(cons.size(), 1));
+  if (ns > ctx->cap_structures) {
+    cudaFree(ctx->d_structures); cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
+    CU(cudaMalloc(&ctx->d_structures, sizeof(StructureDev) * ns));
+    CU(cudaMalloc(&ctx->d_theta, sizeof(float) * kMaxSystem * ns));
+    CU(cudaMalloc(&ctx->d_struct_status, sizeof(int) * ns));
+    ctx->cap_structures = ns;
+  }
+  if (nl > ctx->cap_links) {
+    cudaFree(ctx->d_links);
+    CU(cudaMalloc(&ctx->d_links, sizeof(LinkDev) * nl));
+    ctx->cap_links = nl;
+  }
+  if (nc > ctx->cap_constraints) {
+    cudaFree(ctx->d_constraints);
+    CU(cudaMalloc(&ctx->d_constraints, sizeof(ConstraintDev) * nc));
+    ctx->cap_constraints = nc;
+  }
+  CU(cudaMemsetAsync(ctx->d_theta, 0, sizeof(float) * kMaxSystem * ns, ctx->stream));
+  CU(cudaMemsetAsync(ctx->d_struct_status, 0, sizeof(int) * ns, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_structures, sts.data(), sizeof(StructureDev) * ns, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_links, links.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
+  if (!cons.empty())
+    CU(cudaMemcpyAsync(ctx->d_constraints, cons.data(), sizeof(ConstraintDev) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
+  ctx->h_structures = sts;
+  ctx->n_struct_launch = ns;
+  ctx->struct_smem = smem;
+  ctx->structures_dirty = false;
+  return M3TB_OK;
+}
+
+// Optimizer::CalculateOptimization (mode 0) / CalculateConsistentPoses (mode 1) for every structure
+int LaunchStructure(m3tb_ctx* ctx, int mode, bool from_modalities) {
+  if (ctx->n_bodies == 0) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "no body set");
+  int rc = SyncStructures(ctx);
+  if (rc) return rc;
+  StructArgs a;
+  a.structures = ctx->d_structures;
+  a.links = ctx->d_links;
+  a.constraints = ctx->d_constraints;
+  a.poses = ctx->d_poses;
+  a.gh_link = from_modalities ? nullptr : ctx->d_gh_link;
+  a.gh_region = ctx->d_gh_region;
+  a.gh_depth = ctx->d_gh_depth;
+  a.mode = mode;
+  a.theta_out = ctx->d_theta;
+  a.status = ctx->d_struct_status;
+  if (ctx->struct_smem > 48 * 1024)
+    CU(cudaFuncSetAttribute(k_structure, cudaFuncAttributeMaxDynamicSharedMemorySize, int(ctx->struct_smem)));
+  k_structure<<<ctx->n_struct_launch, kStructThreads, ctx->struct_smem, ctx->stream>>>(a);
+  CU(cudaGetLastError());
+  ctx->launches++;
+  return M3TB_OK;
+}
+
+// Tracker::ExecuteTrackingStep's loop nest (tracker.cpp:344-361) when the optimisers are kinematic structures: the
+// per-body work stays in k_track (correspondences, gradient / Hessian -> gh_link), every
+// Optimizer::CalculateOptimization is one k_structure launch over all structures.
+int StructureStep(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update) {
+  for (int corr = corr_begin; corr < corr_end; ++corr) {
+    if (n_update == 0) {
+      int rc = LaunchTrack(ctx, iteration, corr, corr + 1, 0, 0, PH_REGION_CORR | PH_DEPTH_CORR | PH_STORE_REGION | PH_STORE_DEPTH);
+      if (rc) return rc;
+      continue;
+    }
+    int rc = LaunchTrack(ctx, iteration, corr, corr + 1, 1, 0,
+                         PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_STORE_LINK_GH | PH_STORE_REGION |
+                             PH_STORE_DEPTH);
+    if (rc) return rc;
+    rc = LaunchStructure(ctx, 0, false);
+    if (rc) return rc;
+    for (int upd = 1; upd < n_update; ++upd) {
+      rc = LaunchTrack(ctx, iteration, corr, corr + 1, 1, upd,
+                       PH_LOAD_REGION | PH_LOAD_DEPTH | PH_REGION_GH | PH_DEPTH_GH | PH_STORE_LINK_GH);
+      if (rc) return rc;
+      rc = LaunchStructure(ctx, 0, false);
+      if (rc) return rc;
+    }
+  }
   return M3TB_OK;
 }
 
@@ -580,6 +761,9 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
     CU(cudaMemset(ctx->d_poses, 0, sizeof(float) * 12 * max_bodies));
     CU(cudaMemset(ctx->d_counts, 0, sizeof(int) * 4 * max_bodies));
     CU(cudaMemset(ctx->d_gh_region, 0, sizeof(float) * 27 * max_bodies));
+    CU(cudaMemset(ctx->d_gh_depth, 0, sizeof(float) * 27 * max_bodies));
+    CU(cudaMalloc(&ctx->d_gh_link, sizeof(float) * 27 * max_bodies));
+    CU(cudaMemset(ctx->d_gh_link, 0, sizeof(float) * 27 * max_bodies));
     CU(cudaMalloc(&ctx->d_roi, sizeof(RoiRecord) * 2 * max_bodies));
     CU(cudaMemset(ctx->d_roi, 0xff, sizeof(RoiRecord) * 2 * max_bodies));  // generation -1: nothing ingested yet
     CU(cudaMalloc(&ctx->d_ingest_bytes, sizeof(unsigned long long)));
@@ -614,6 +798,8 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
   cudaFree(ctx->d_phase_clock); cudaFree(ctx->d_roi); cudaFree(ctx->d_ingest_bytes);
+  cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_constraints); cudaFree(ctx->d_gh_link);
+  cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
   delete ctx;
   return M3TB_OK;
 }
@@ -787,6 +973,11 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
   }
   B.set = 1;
   ctx->h_bodies[body] = B;
+  if (!ctx->structures.empty()) {  // the implicit one-link structures follow the body table
+    int prc = PullLinks(ctx);
+    if (prc) return prc;
+    ctx->structures_dirty = true;
+  }
   ctx->n_bodies = std::max(ctx->n_bodies, body + 1);
   ctx->bodies_dirty = true;
   return M3TB_OK;
@@ -845,6 +1036,7 @@ int m3tb_get_histograms(m3tb_ctx* ctx, int body, float* histogram_f, float* hist
 int m3tb_tracking_step(m3tb_ctx* ctx, int iteration, int n_corr_iterations, int n_update_iterations) {
   CHECK_CTX();
   if (n_corr_iterations < 0 || n_update_iterations < 0) return Fail(ctx, M3TB_ERR_INVALID, "negative iteration count");
+  if (HasStructures(ctx)) return StructureStep(ctx, iteration, 0, n_corr_iterations, n_update_iterations);
   return LaunchTrack(ctx, iteration, 0, n_corr_iterations, n_update_iterations, 0,
                      PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_SOLVE | PH_STORE_REGION |
                          PH_STORE_DEPTH);
@@ -853,6 +1045,7 @@ int m3tb_tracking_step(m3tb_ctx* ctx, int iteration, int n_corr_iterations, int 
 int m3tb_corr_iteration(m3tb_ctx* ctx, int iteration, int corr_iteration, int n_update_iterations) {
   CHECK_CTX();
   if (corr_iteration < 0 || n_update_iterations < 0) return Fail(ctx, M3TB_ERR_INVALID, "negative iteration count");
+  if (HasStructures(ctx)) return StructureStep(ctx, iteration, corr_iteration, corr_iteration + 1, n_update_iterations);
   return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, n_update_iterations, 0,
                      PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_SOLVE | PH_STORE_REGION |
                          PH_STORE_DEPTH);
@@ -917,7 +1110,153 @@ int m3tb_depth_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration
 
 int m3tb_calculate_optimization(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration) {
   CHECK_CTX();
+  if (HasStructures(ctx)) return LaunchStructure(ctx, 0, true);
   return LaunchTrack(ctx, iteration, corr_iteration, corr_iteration + 1, 1, opt_iteration, PH_LOAD_GH | PH_SOLVE);
+}
+
+int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int n_links,
+                       const m3tb_constraint* constraints, int n_constraints, const m3tb_optimizer_params* optimizer) {
+  CHECK_CTX();
+  if (structure < 0 || structure > int(ctx->structures.size()) || structure >= ctx->max_bodies)
+    return Fail(ctx, M3TB_ERR_INVALID, "structure ids must be dense (0..n)");
+  if (!links || n_links < 1 || n_links > kMaxLinks) return Fail(ctx, M3TB_ERR_INVALID, "a structure has 1..16 links");
+  if (n_constraints < 0 || n_constraints > kMaxStructConstraints || (n_constraints > 0 && !constraints))
+    return Fail(ctx, M3TB_ERR_INVALID, "a structure has at most 32 constraints");
+  StructureHost h;
+  int dof = 0, rows = 0;
+  for (int i = 0; i < n_links; ++i) {
+    const m3tb_link& in = links[i];
+    if ((i == 0) != (in.parent < 0) || in.parent >= i)
+      return Fail(ctx, M3TB_ERR_INVALID, "links must be listed in pre-order: link 0 is the root, parent < own index");
+    if (in.body < -1 || in.body >= ctx->max_bodies) return Fail(ctx, M3TB_ERR_INVALID, "link body index out of range");
+    LinkDev l;
+    std::memset(&l, 0, sizeof(l));
+    l.body = in.body;
+    l.parent = in.parent;
+    l.first_index = dof;
+    for (int d = 0; d < 6; ++d) {
+      l.free_directions[d] = in.free_directions[d] ? 1 : 0;
+      l.dof += l.free_directions[d];
+    }
+    dof += l.dof;
+    l.fixed_body2joint = in.fixed_body2joint_pose ? 1 : 0;
+    std::memcpy(l.body2joint, in.body2joint, sizeof(l.body2joint));
+    std::memcpy(l.joint2parent, in.joint2parent, sizeof(l.joint2parent));
+    std::memcpy(l.link2world, in.link2world, sizeof(l.link2world));
+    h.links.push_back(l);
+  }
+  for (int c = 0; c < n_constraints; ++c) {
+    const m3tb_constraint& in = constraints[c];
+    if (in.link1 < 0 || in.link1 >= n_links || in.link2 < 0 || in.link2 >= n_links)
+      return Fail(ctx, M3TB_ERR_INVALID, "constraint link index out of range");
+    ConstraintDev k;
+    std::memset(&k, 0, sizeof(k));
+    k.link1 = in.link1; k.link2 = in.link2;
+    k.soft = in.soft ? 1 : 0;
+    for (int d = 0; d < 6; ++d) {
+      k.directions[d] = in.directions[d] ? 1 : 0;
+      k.n_rows += k.directions[d];
+    }
+    if (!k.soft) { k.first_row = rows; rows += k.n_rows; }
+    std::memcpy(k.body12joint1, in.body12joint1, sizeof(k.body12joint1));
+    std::memcpy(k.body22joint2, in.body22joint2, sizeof(k.body22joint2));
+    k.max_distance_rotation = in.max_distance_rotation;
+    k.max_distance_translation = in.max_distance_translation;
+    k.sd_rotation = in.standard_deviation_rotation;
+    k.sd_translation = in.standard_deviation_translation;
+    if (k.soft && !(k.sd_rotation > 0.0f && k.sd_translation > 0.0f))
+      return Fail(ctx, M3TB_ERR_INVALID, "soft constraint standard deviations must be positive");
+    h.constraints.push_back(k);
+  }
+  if (dof < 1) return Fail(ctx, M3TB_ERR_INVALID, "a structure needs at least one free direction");
+  if (dof > kMaxStructDof || dof + rows > kMaxSystem)
+    return Fail(ctx, M3TB_ERR_UNSUPPORTED, "more than 96 degrees of freedom or 128 unknowns + constraint rows");
+  m3tb_optimizer_params dflt;
+  m3tb_optimizer_params_default(&dflt);
+  const m3tb_optimizer_params& op = optimizer ? *optimizer : dflt;
+  h.tikhonov_rotation = op.tikhonov_parameter_rotation;
+  h.tikhonov_translation = op.tikhonov_parameter_translation;
+  h.set = true;
+  int rc = PullLinks(ctx);
+  if (rc) return rc;
+  if (structure == int(ctx->structures.size())) ctx->structures.push_back(h);
+  else ctx->structures[structure] = h;
+  ctx->structures_dirty = true;
+  return M3TB_OK;
+}
+
+int m3tb_set_gradient_hessian(m3tb_ctx* ctx, int modality, const float* gradients, const float* hessians) {
+  CHECK_CTX();
+  if ((modality != 0 && modality != 1) || !gradients || !hessians || ctx->n_bodies == 0)
+    return Fail(ctx, M3TB_ERR_INVALID, "bad gradient / hessian arguments");
+  std::vector<float> h(size_t(27) * ctx->n_bodies);
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    for (int i = 0; i < 6; ++i) h[27 * b + i] = gradients[6 * b + i];
+    for (int i = 0; i < 6; ++i)
+      for (int j = 0; j <= i; ++j) h[27 * b + 6 + Tri(i, j)] = hessians[36 * b + 6 * i + j];
+  }
+  CU(cudaMemcpyAsync(modality == 0 ? ctx->d_gh_region : ctx->d_gh_depth, h.data(), h.size() * sizeof(float),
+                     cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
+int m3tb_clear_structures(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->structures.clear();
+  ctx->structures_dirty = true;
+  ctx->n_struct_launch = 0;
+  return M3TB_OK;
+}
+
+int m3tb_n_structures(const m3tb_ctx* ctx) { return ctx ? int(ctx->structures.size()) : 0; }
+
+int m3tb_calculate_consistent_poses(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  if (!HasStructures(ctx)) return M3TB_OK;  // a free root link with body2joint = identity keeps its pose
+  int rc = SyncTables(ctx);
+  if (rc) return rc;
+  return LaunchStructure(ctx, 1, false);
+}
+
+int m3tb_get_link_poses(m3tb_ctx* ctx, int structure, float* body2joint, float* joint2parent, float* link2world) {
+  CHECK_CTX();
+  if (structure < 0 || structure >= int(ctx->structures.size())) return Fail(ctx, M3TB_ERR_INVALID, "structure index out of range");
+  int rc = PullLinks(ctx);
+  if (rc) return rc;
+  const StructureHost& s = ctx->structures[structure];
+  std::vector<float> poses;
+  if (link2world) {
+    poses.resize(size_t(12) * std::max(ctx->n_bodies, 1));
+    CU(cudaMemcpyAsync(poses.data(), ctx->d_poses, sizeof(float) * 12 * ctx->n_bodies, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+  }
+  for (size_t i = 0; i < s.links.size(); ++i) {
+    const LinkDev& l = s.links[i];
+    if (body2joint) std::memcpy(body2joint + 12 * i, l.body2joint, sizeof(float) * 12);
+    if (joint2parent) std::memcpy(joint2parent + 12 * i, l.joint2parent, sizeof(float) * 12);
+    if (link2world) std::memcpy(link2world + 12 * i, l.body >= 0 ? poses.data() + 12 * l.body : l.link2world, sizeof(float) * 12);
+  }
+  return M3TB_OK;
+}
+
+int m3tb_get_structure_theta(m3tb_ctx* ctx, int structure, float* theta, int capacity, int* n_out, int* updated) {
+  CHECK_CTX();
+  if (structure < 0 || structure >= ctx->n_struct_launch || ctx->structures_dirty)
+    return Fail(ctx, M3TB_ERR_INVALID, "structure index out of range / no optimisation ran yet");
+  const StructureDev& d = ctx->h_structures[structure];
+  const int n = d.dof + d.n_rows;
+  if (n_out) *n_out = n;
+  if (theta) {
+    if (capacity < n) return Fail(ctx, M3TB_ERR_INVALID, "theta buffer too small");
+    CU(cudaMemcpyAsync(theta, ctx->d_theta + size_t(structure) * kMaxSystem, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  int st = 0;
+  CU(cudaMemcpyAsync(&st, ctx->d_struct_status + structure, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (updated) *updated = st;
+  return M3TB_OK;
 }
 
 int m3tb_get_region_lines(m3tb_ctx* ctx, int body, m3tb_region_line* lines, int capacity, int* n_out) {

@@ -34,7 +34,8 @@ enum DepthField { DF_CBX = 0, DF_CBY, DF_CBZ, DF_NX, DF_NY, DF_NZ, DF_YX, DF_YY,
 enum Phase : unsigned {
   PH_REGION_CORR = 1u, PH_DEPTH_CORR = 2u, PH_REGION_GH = 4u, PH_DEPTH_GH = 8u, PH_SOLVE = 16u,
   PH_LOAD_REGION = 32u, PH_LOAD_DEPTH = 64u, PH_STORE_REGION = 128u, PH_STORE_DEPTH = 256u,
-  PH_STORE_GH = 512u, PH_LOAD_GH = 1024u
+  PH_STORE_GH = 512u, PH_LOAD_GH = 1024u,
+  PH_STORE_LINK_GH = 2048u  // sum over the body's modalities -> gh_link (input of k_structure)
 };
 
 struct CameraDev {
@@ -121,6 +122,7 @@ struct TrackArgs {
   int* counts;                  // [n_bodies][4]: n_lines, n_points, region_view, depth_view
   float* gh_region;             // [n_bodies][27]: g[6], H lower [21]
   float* gh_depth;              // [n_bodies][27]
+  float* gh_link;               // [n_bodies][27]: Link::CalculateGradientAndHessian (region + depth)
   int iteration, corr_begin, corr_end, n_update, opt_base;
   unsigned phases;
   int tile_bytes;               // dynamic shared memory available for the colour / depth ROI tiles (0: no tiling)

@@ -1155,6 +1155,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
           if (args.phases & PH_REGION_GH) args.gh_region[27 * body_id + l] = v;
           if (args.phases & PH_DEPTH_GH) args.gh_depth[27 * body_id + l] = v;
         }
+        if (args.phases & PH_STORE_LINK_GH) args.gh_link[27 * body_id + l] = v;
         if (args.phases & PH_LOAD_GH)  // Link::CalculateGradientAndHessian (link.cpp:184-193): region, then depth
           v = 0.0f + args.gh_region[27 * body_id + l] + args.gh_depth[27 * body_id + l];
         if (args.phases & PH_SOLVE) {

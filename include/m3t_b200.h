@@ -111,6 +111,32 @@ typedef struct m3tb_optimizer_params {
   float tikhonov_parameter_translation; /* 30000 */
 } m3tb_optimizer_params;
 
+/* One m3t::Link of a kinematic structure (M3T/include/m3t/link.h:150-156). */
+typedef struct m3tb_link {
+  int32_t body;                  /* body index of Link::body_ptr(), or -1 for a link without body */
+  int32_t parent;                /* index of the parent link inside the structure's list, -1 for the root link */
+  float body2joint[12];          /* Link::body2joint_pose(), row-major 3x4 */
+  float joint2parent[12];        /* Link::joint2parent_pose() */
+  float link2world[12];          /* Link::link2world_pose_ of a link without body (ignored when body >= 0) */
+  int32_t free_directions[6];    /* Link::free_directions(): rot x,y,z, trans x,y,z */
+  int32_t fixed_body2joint_pose; /* Link::fixed_body2joint_pose(), default 1 */
+} m3tb_link;
+
+/* m3t::Constraint (M3T/include/m3t/constraint.h:109-112) or, with soft != 0, m3t::SoftConstraint
+ * (M3T/include/m3t/soft_constraint.h:128-136). link1 / link2 index the structure's link list. */
+typedef struct m3tb_constraint {
+  int32_t link1, link2;
+  float body12joint1[12], body22joint2[12];
+  int32_t directions[6];         /* constraint_directions(): rot x,y,z, trans x,y,z */
+  int32_t soft;
+  float max_distance_rotation, max_distance_translation;             /* soft only, defaults 0 / 0 */
+  float standard_deviation_rotation, standard_deviation_translation; /* soft only, defaults 0.01 / 0.001 */
+} m3tb_constraint;
+
+#define M3TB_MAX_LINKS 16         /* links per structure */
+#define M3TB_MAX_SYSTEM 128       /* degrees of freedom + constraint rows of one structure */
+#define M3TB_MAX_CONSTRAINTS 32   /* constraints + soft constraints per structure */
+
 /* Per-line state kept between CalculateCorrespondences and CalculateGradientAndHessian
  * (RegionModality::DataLine, region_modality.h:150-165) - debug / parity read-back only. */
 typedef struct m3tb_region_line {
@@ -242,6 +268,34 @@ int m3tb_depth_gradient_hessian(m3tb_ctx* ctx, int iteration, int corr_iteration
  * Hessians left on the device by the two calls above (Link::CalculateGradientAndHessian sums them,
  * link.cpp:184-193), then Link::UpdatePoses (link.cpp:205-241). */
 int m3tb_calculate_optimization(m3tb_ctx* ctx, int iteration, int corr_iteration, int opt_iteration);
+
+/* ---- kinematic structures (BASELINE config 5) --------------------------------------
+ * One structure = one m3t::Optimizer with the Link tree below its root link, its Constraints and SoftConstraints
+ * (Optimizer::Optimizer / AddConstraint / AddSoftConstraint + SetUp, M3T/src/optimizer.cpp:12-64). Links are listed in
+ * Optimizer::ReferencedLinks() order (pre-order, optimizer.cpp:254-260), i.e. parent < own index; that is also the
+ * order of the unknowns (DefineJacobians, optimizer.cpp:217-227). Structure ids are dense (0..n-1). Bodies that no
+ * structure references keep the rigid-body optimiser of m3tb_set_body (one root link, body2joint = identity).
+ * As soon as one structure exists, m3tb_tracking_step / m3tb_corr_iteration / m3tb_calculate_optimization run
+ * Optimizer::CalculateOptimization per structure: Link::CalculateJacobian (link.cpp:159-182), SoftConstraint::
+ * AddGradientsAndHessiansToLinks (soft_constraint.cpp:113-131), Constraint::CalculateResidualAndConstraintJacobian
+ * (constraint.cpp:81-103), the (DoF + nc)^2 LDLT (optimizer.cpp:144-167) and Link::UpdatePoses (link.cpp:205-241).
+ * Like Optimizer::SetUp, setting a structure makes the poses consistent (UpdatePoses with theta = 0). */
+int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int n_links,
+                       const m3tb_constraint* constraints, int n_constraints, const m3tb_optimizer_params* optimizer);
+int m3tb_clear_structures(m3tb_ctx* ctx);
+int m3tb_n_structures(const m3tb_ctx* ctx);
+/* Optimizer::CalculateConsistentPoses (optimizer.cpp:133-142) for every structure. */
+int m3tb_calculate_consistent_poses(m3tb_ctx* ctx);
+/* Link::body2joint_pose / joint2parent_pose / link2world_pose of every link of one structure after the last update,
+ * each [n_links][12]; any pointer may be NULL. */
+int m3tb_get_link_poses(m3tb_ctx* ctx, int structure, float* body2joint, float* joint2parent, float* link2world);
+/* theta of the last CalculateOptimization of one structure ([DoF + nc], debug / parity); *n_out = DoF + nc;
+ * *updated = 0 when the NaN guard (optimizer.cpp:165) skipped the update. */
+int m3tb_get_structure_theta(m3tb_ctx* ctx, int structure, float* theta, int capacity, int* n_out, int* updated);
+/* Overwrites the gradient / Hessian a modality left on the device (what Modality::gradient() / hessian() return,
+ * modality.h:132-137): modality 0 = region, 1 = depth; gradients[n_bodies][6], hessians[n_bodies][36] (symmetric).
+ * For adapters that compute a modality elsewhere and for the parity tests of m3tb_calculate_optimization. */
+int m3tb_set_gradient_hessian(m3tb_ctx* ctx, int modality, const float* gradients, const float* hessians);
 
 /* ---- parity read-back of the per-line / per-point state (data_lines_, data_points_) ----------- */
 /* `lines` must hold n_lines_max records; *n_out receives how many model points were processed. */
