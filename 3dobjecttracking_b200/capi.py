@@ -87,7 +87,7 @@ SYMBOLS = [
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
     "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes", "m3tb_set_structure", "m3tb_clear_structures",
     "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
-    "m3tb_set_gradient_hessian",
+    "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def lib():
     L.m3tb_clear_structures.argtypes = [vp]
     L.m3tb_n_structures.argtypes = [vp]
     L.m3tb_calculate_consistent_poses.argtypes = [vp]
+    L.m3tb_reset_joint_poses.argtypes = [vp]
     L.m3tb_get_link_poses.argtypes = [vp, ci, fp, fp, fp]
     L.m3tb_get_structure_theta.argtypes = [vp, ci, fp, ci, C.POINTER(ci), C.POINTER(ci)]
     L.m3tb_set_gradient_hessian.argtypes = [vp, ci, fp, fp]
@@ -371,6 +372,9 @@ class Context:
 
     def n_structures(self):
         return self.L.m3tb_n_structures(self.h)
+
+    def reset_joint_poses(self):
+        self._ck(self.L.m3tb_reset_joint_poses(self.h))
 
     def calculate_consistent_poses(self):
         self._ck(self.L.m3tb_calculate_consistent_poses(self.h))

@@ -3,6 +3,7 @@
 #include "m3t_b200.h"
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,6 +85,10 @@ struct m3tb_ctx {
   std::vector<StructureDev> h_structures;
   StructureDev* d_structures = nullptr;
   LinkDev* d_links = nullptr;
+  LinkDev* d_links_default = nullptr;      // Link::default_body2joint_pose_ / default_joint2parent_pose_
+  int n_links_total = 0;
+  bool defaults_valid = false;
+  std::vector<LinkDev> h_links_default;
   ConstraintDev* d_constraints = nullptr;
   int cap_structures = 0, cap_links = 0, cap_constraints = 0;
   float* d_gh_link = nullptr;
@@ -390,8 +395,9 @@ int SyncStructures(m3tb_ctx* ctx) {
     ctx->cap_structures = ns;
   }
   if (nl > ctx->cap_links) {
-    cudaFree(ctx->d_links);
+    cudaFree(ctx->d_links); cudaFree(ctx->d_links_default);
     CU(cudaMalloc(&ctx->d_links, sizeof(LinkDev) * nl));
+    CU(cudaMalloc(&ctx->d_links_default, sizeof(LinkDev) * nl));
     ctx->cap_links = nl;
   }
   if (nc > ctx->cap_constraints) {
@@ -403,6 +409,18 @@ int SyncStructures(m3tb_ctx* ctx) {
   CU(cudaMemsetAsync(ctx->d_struct_status, 0, sizeof(int) * ns, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_structures, sts.data(), sizeof(StructureDev) * ns, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_links, links.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
+  if (!ctx->defaults_valid) {  // the first upload after m3tb_set_structure defines the defaults
+    CU(cudaMemcpyAsync(ctx->d_links_default, links.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h_links_default = links;
+    ctx->defaults_valid = true;
+  } else if (int(ctx->h_links_default.size()) != nl) {  // the body table grew: implicit links were appended
+    std::vector<LinkDev> d = links;
+    for (size_t k = 0; k < std::min(d.size(), ctx->h_links_default.size()); ++k) d[k] = ctx->h_links_default[k];
+    CU(cudaMemcpyAsync(ctx->d_links_default, d.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->h_links_default = d;
+  }
+  ctx->n_links_total = nl;
   if (!cons.empty())
     CU(cudaMemcpyAsync(ctx->d_constraints, cons.data(), sizeof(ConstraintDev) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
@@ -798,7 +816,8 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
   cudaFree(ctx->d_phase_clock); cudaFree(ctx->d_roi); cudaFree(ctx->d_ingest_bytes);
-  cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_constraints); cudaFree(ctx->d_gh_link);
+  cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_links_default); cudaFree(ctx->d_constraints);
+  cudaFree(ctx->d_gh_link);
   cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
   delete ctx;
   return M3TB_OK;
@@ -1182,6 +1201,7 @@ int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int
   if (structure == int(ctx->structures.size())) ctx->structures.push_back(h);
   else ctx->structures[structure] = h;
   ctx->structures_dirty = true;
+  ctx->defaults_valid = false;  // set_joint2parent_pose / set_body2joint_pose also set the defaults (link.cpp:131-139)
   return M3TB_OK;
 }
 
@@ -1206,11 +1226,26 @@ int m3tb_clear_structures(m3tb_ctx* ctx) {
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->structures.clear();
   ctx->structures_dirty = true;
+  ctx->defaults_valid = false;
   ctx->n_struct_launch = 0;
   return M3TB_OK;
 }
 
 int m3tb_n_structures(const m3tb_ctx* ctx) { return ctx ? int(ctx->structures.size()) : 0; }
+
+int m3tb_reset_joint_poses(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  if (!HasStructures(ctx)) return M3TB_OK;
+  int rc = SyncStructures(ctx);
+  if (rc) return rc;
+  // only the joint poses are reset; link2world of body-less links is state, like Link::link2world_pose_
+  LinkDev* d = ctx->d_links;
+  const LinkDev* s = ctx->d_links_default;
+  CU(cudaMemcpy2DAsync(reinterpret_cast<char*>(d) + offsetof(LinkDev, body2joint), sizeof(LinkDev),
+                       reinterpret_cast<const char*>(s) + offsetof(LinkDev, body2joint), sizeof(LinkDev),
+                       sizeof(float) * 24, ctx->n_links_total, cudaMemcpyDeviceToDevice, ctx->stream));
+  return M3TB_OK;
+}
 
 int m3tb_calculate_consistent_poses(m3tb_ctx* ctx) {
   CHECK_CTX();

@@ -15,6 +15,7 @@
 #ifndef M3T_B200_HPP_
 #define M3T_B200_HPP_
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <cstdio>
@@ -89,13 +90,14 @@ class Batch {
   int NextDepthCamera() { return n_depth_++; }
   int NextRegionModel() { return n_rmodels_++; }
   int NextDepthModel() { return n_dmodels_++; }
+  int NextStructure() { return n_structures_++; }
   int n_bodies() const { return n_bodies_; }
 
   std::vector<float> region_g, region_h, depth_g, depth_h;  // last batched gradients / Hessians (all bodies)
 
  private:
   m3tb_ctx* ctx_ = nullptr;
-  int max_bodies_ = 0, n_bodies_ = 0, n_color_ = 0, n_depth_ = 0, n_rmodels_ = 0, n_dmodels_ = 0;
+  int max_bodies_ = 0, n_bodies_ = 0, n_color_ = 0, n_depth_ = 0, n_rmodels_ = 0, n_dmodels_ = 0, n_structures_ = 0;
   long pose_version_ = 0;
   Key done_[kNPhases];
 };
@@ -447,22 +449,148 @@ class DepthModality : public Modality {
   std::shared_ptr<DepthModel> depth_model_ptr_;
 };
 
-// ---- link.h: a root link carrying one body and its modalities ---------------------------------------------------------
+// ---- link.h: one node of a kinematic tree (M3T/include/m3t/link.h) ---------------------------------------------------------
 class Link {
  public:
-  Link(const std::string& name, const std::shared_ptr<Body>& body_ptr) : name_(name), body_ptr_(body_ptr) {}
+  // body_ptr may be null (a link that only carries a joint, e.g. a fixed base)
+  Link(const std::string& name, const std::shared_ptr<Body>& body_ptr = nullptr,
+       const Transform3fA& body2joint_pose = Transform3fA::Identity(),
+       const Transform3fA& joint2parent_pose = Transform3fA::Identity(),
+       const Transform3fA& link2world_pose = Transform3fA::Identity(),
+       const std::array<bool, 6>& free_directions = {true, true, true, true, true, true},
+       bool fixed_body2joint_pose = true)
+      : name_(name), body_ptr_(body_ptr), body2joint_pose_(body2joint_pose), joint2parent_pose_(joint2parent_pose),
+        link2world_pose_(link2world_pose), free_directions_(free_directions), fixed_body2joint_pose_(fixed_body2joint_pose) {}
   bool AddModality(const std::shared_ptr<Modality>& m) {
     modality_ptrs_.push_back(m);
+    set_up_ = false;
     return true;
+  }
+  bool AddChildLink(const std::shared_ptr<Link>& l) {
+    for (auto& c : child_link_ptrs_)
+      if (c->name() == l->name()) {
+        std::cerr << "Child link " << l->name() << " already exists" << std::endl;
+        return false;
+      }
+    child_link_ptrs_.push_back(l);
+    set_up_ = false;
+    return true;
+  }
+  void set_body2joint_pose(const Transform3fA& p) { body2joint_pose_ = p; }
+  void set_joint2parent_pose(const Transform3fA& p) { joint2parent_pose_ = p; }
+  void set_link2world_pose(const Transform3fA& p) { link2world_pose_ = p; }
+  void set_free_directions(const std::array<bool, 6>& f) { free_directions_ = f; set_up_ = false; }
+  void set_fixed_body2joint_pose(bool v) { fixed_body2joint_pose_ = v; }
+  // Link::SetUp (link.cpp:37-58): a link needs a body whenever it has modalities
+  bool SetUp() {
+    set_up_ = false;
+    if (!modality_ptrs_.empty() && !body_ptr_) {
+      std::cerr << "Link " << name_ << " has modalities but no body" << std::endl;
+      return false;
+    }
+    for (auto& m : modality_ptrs_)
+      if (m->body_ptr() != body_ptr_) {
+        std::cerr << "Modality " << m->name() << " does not reference the body of link " << name_ << std::endl;
+        return false;
+      }
+    set_up_ = true;
+    return true;
+  }
+  int DegreesOfFreedom() const {
+    int n = 0;
+    for (bool f : free_directions_) n += f ? 1 : 0;
+    return n;
   }
   const std::string& name() const { return name_; }
   const std::shared_ptr<Body>& body_ptr() const { return body_ptr_; }
   const std::vector<std::shared_ptr<Modality>>& modality_ptrs() const { return modality_ptrs_; }
+  const std::vector<std::shared_ptr<Link>>& child_link_ptrs() const { return child_link_ptrs_; }
+  // the three poses are refreshed from the device by Optimizer::FetchLinkPoses()
+  const Transform3fA& body2joint_pose() const { return body2joint_pose_; }
+  const Transform3fA& joint2parent_pose() const { return joint2parent_pose_; }
+  const Transform3fA& link2world_pose() const { return link2world_pose_; }
+  const std::array<bool, 6>& free_directions() const { return free_directions_; }
+  bool fixed_body2joint_pose() const { return fixed_body2joint_pose_; }
+  bool set_up() const { return set_up_; }
 
  private:
+  friend class Optimizer;
   std::string name_;
   std::shared_ptr<Body> body_ptr_;
   std::vector<std::shared_ptr<Modality>> modality_ptrs_;
+  std::vector<std::shared_ptr<Link>> child_link_ptrs_;
+  Transform3fA body2joint_pose_, joint2parent_pose_, link2world_pose_;
+  std::array<bool, 6> free_directions_;
+  bool fixed_body2joint_pose_ = true;
+  bool set_up_ = true;  // a link without children / modalities changes needs no explicit SetUp (rigid-body applications)
+};
+
+// ---- constraint.h / soft_constraint.h -----------------------------------------------------------------------------------
+class Constraint {
+ public:
+  Constraint(const std::string& name, const std::shared_ptr<Link>& link1_ptr, const std::shared_ptr<Link>& link2_ptr,
+             const Transform3fA& body12joint1_pose = Transform3fA::Identity(),
+             const Transform3fA& body22joint2_pose = Transform3fA::Identity(),
+             const std::array<bool, 6>& constraint_directions = {false, false, false, false, false, false})
+      : name_(name), link1_ptr_(link1_ptr), link2_ptr_(link2_ptr), body12joint1_pose_(body12joint1_pose),
+        body22joint2_pose_(body22joint2_pose), constraint_directions_(constraint_directions) {}
+  virtual ~Constraint() = default;
+  void set_body12joint1_pose(const Transform3fA& p) { body12joint1_pose_ = p; }
+  void set_body22joint2_pose(const Transform3fA& p) { body22joint2_pose_ = p; }
+  void set_constraint_directions(const std::array<bool, 6>& d) { constraint_directions_ = d; }
+  bool SetUp() {  // constraint.cpp:24-41
+    set_up_ = false;
+    if (!link1_ptr_ || !link2_ptr_) {
+      std::cerr << "Constraint " << name_ << " needs two links" << std::endl;
+      return false;
+    }
+    set_up_ = true;
+    return true;
+  }
+  int NumberOfConstraints() const {
+    int n = 0;
+    for (bool d : constraint_directions_) n += d ? 1 : 0;
+    return n;
+  }
+  const std::string& name() const { return name_; }
+  const std::shared_ptr<Link>& link1_ptr() const { return link1_ptr_; }
+  const std::shared_ptr<Link>& link2_ptr() const { return link2_ptr_; }
+  const Transform3fA& body12joint1_pose() const { return body12joint1_pose_; }
+  const Transform3fA& body22joint2_pose() const { return body22joint2_pose_; }
+  const std::array<bool, 6>& constraint_directions() const { return constraint_directions_; }
+  bool set_up() const { return set_up_; }
+
+ protected:
+  std::string name_;
+  std::shared_ptr<Link> link1_ptr_, link2_ptr_;
+  Transform3fA body12joint1_pose_, body22joint2_pose_;
+  std::array<bool, 6> constraint_directions_;
+  bool set_up_ = false;
+};
+
+class SoftConstraint : public Constraint {
+ public:
+  SoftConstraint(const std::string& name, const std::shared_ptr<Link>& link1_ptr, const std::shared_ptr<Link>& link2_ptr,
+                 const Transform3fA& body12joint1_pose = Transform3fA::Identity(),
+                 const Transform3fA& body22joint2_pose = Transform3fA::Identity(),
+                 const std::array<bool, 6>& constraint_directions = {false, false, false, false, false, false},
+                 float max_distance_rotation = 0.0f, float max_distance_translation = 0.0f,
+                 float standard_deviation_rotation = 0.01f, float standard_deviation_translation = 0.001f)
+      : Constraint(name, link1_ptr, link2_ptr, body12joint1_pose, body22joint2_pose, constraint_directions),
+        max_distance_rotation_(max_distance_rotation), max_distance_translation_(max_distance_translation),
+        standard_deviation_rotation_(standard_deviation_rotation),
+        standard_deviation_translation_(standard_deviation_translation) {}
+  void set_max_distance_rotation(float v) { max_distance_rotation_ = v; }
+  void set_max_distance_translation(float v) { max_distance_translation_ = v; }
+  void set_standard_deviation_rotation(float v) { standard_deviation_rotation_ = v; }
+  void set_standard_deviation_translation(float v) { standard_deviation_translation_ = v; }
+  float max_distance_rotation() const { return max_distance_rotation_; }
+  float max_distance_translation() const { return max_distance_translation_; }
+  float standard_deviation_rotation() const { return standard_deviation_rotation_; }
+  float standard_deviation_translation() const { return standard_deviation_translation_; }
+
+ private:
+  float max_distance_rotation_, max_distance_translation_, standard_deviation_rotation_, standard_deviation_translation_;
 };
 
 // ---- optimizer.h ----------------------------------------------------------------------------------------------------
@@ -474,40 +602,86 @@ class Optimizer {
     params_.tikhonov_parameter_rotation = tikhonov_parameter_rotation;
     params_.tikhonov_parameter_translation = tikhonov_parameter_translation;
   }
+  bool AddConstraint(const std::shared_ptr<Constraint>& c) { constraint_ptrs_.push_back(c); set_up_ = false; return true; }
+  bool AddSoftConstraint(const std::shared_ptr<SoftConstraint>& c) { soft_constraint_ptrs_.push_back(c); set_up_ = false; return true; }
   void set_tikhonov_parameter_rotation(float v) { params_.tikhonov_parameter_rotation = v; set_up_ = false; }
   void set_tikhonov_parameter_translation(float v) { params_.tikhonov_parameter_translation = v; set_up_ = false; }
   const std::string& name() const { return name_; }
   const std::shared_ptr<Link>& root_link_ptr() const { return root_link_ptr_; }
+  const std::vector<std::shared_ptr<Constraint>>& constraint_ptrs() const { return constraint_ptrs_; }
+  const std::vector<std::shared_ptr<SoftConstraint>>& soft_constraint_ptrs() const { return soft_constraint_ptrs_; }
   bool set_up() const { return set_up_; }
+  int structure_index() const { return structure_index_; }
 
-  // Optimizer::SetUp (optimizer.cpp:22-40): here it also writes the body's device record (modalities + parameters)
+  // Optimizer::ReferencedLinks (optimizer.cpp:254-260): pre-order
+  std::vector<std::shared_ptr<Link>> ReferencedLinks() const {
+    std::vector<std::shared_ptr<Link>> out;
+    AddReferencedLinks(root_link_ptr_, &out);
+    return out;
+  }
+  int DegreesOfFreedom() const {
+    int n = 0;
+    for (auto& l : ReferencedLinks()) n += l->DegreesOfFreedom();
+    return n;
+  }
+  int NumberOfConstraints() const {
+    int n = 0;
+    for (auto& c : constraint_ptrs_) n += c->NumberOfConstraints();
+    return n;
+  }
+
+  // Optimizer::SetUp (optimizer.cpp:22-64): here it also writes the device records - one body record per link with
+  // a body (modalities + parameters) and, unless this is a plain rigid body, the structure (links + constraints) -
+  // and makes the poses consistent (UpdatePoses with theta = 0)
   bool SetUp() {
-    const m3tb_region_params* rp = nullptr;
-    const m3tb_depth_params* dp = nullptr;
-    int rmodel = 0, dmodel = 0, ccam = 0, dcam = 0;
-    if (root_link_ptr_->modality_ptrs().empty()) {
-      std::cerr << "No modalities were assigned to link " << root_link_ptr_->name() << std::endl;
+    set_up_ = false;
+    if (!root_link_ptr_) {
+      std::cerr << "No root link assigned to optimizer " << name_ << std::endl;
       return false;
     }
-    for (auto& m : root_link_ptr_->modality_ptrs()) {
-      if (!m->set_up()) {
-        std::cerr << "Modality " << m->name() << " was not set up" << std::endl;
+    const auto links = ReferencedLinks();
+    bool any_modality = false;
+    for (auto& l : links) {
+      if (!l->set_up()) {
+        std::cerr << "Link " << l->name() << " was not set up" << std::endl;
         return false;
       }
-      if (auto r = std::dynamic_pointer_cast<RegionModality>(m)) {
-        rp = &r->params();
-        rmodel = r->region_model_ptr()->index();
-        ccam = r->color_camera_ptr()->index();
-      } else if (auto d = std::dynamic_pointer_cast<DepthModality>(m)) {
-        dp = &d->params();
-        dmodel = d->depth_model_ptr()->index();
-        dcam = d->depth_camera_ptr()->index();
-      }
+      any_modality = any_modality || !l->modality_ptrs().empty();
     }
-    set_up_ = Check(batch_->ctx(),
-                    m3tb_set_body(batch_->ctx(), root_link_ptr_->body_ptr()->index(), rp, dp, &params_, rmodel, dmodel, ccam, dcam),
-                    "Optimizer::SetUp");
-    return set_up_;
+    if (!any_modality) {
+      std::cerr << "No modalities were assigned to the links of optimizer " << name_ << std::endl;
+      return false;
+    }
+    for (auto& c : constraint_ptrs_)
+      if (!c->set_up()) {
+        std::cerr << "Constraint " << c->name() << " was not set up" << std::endl;
+        return false;
+      }
+    for (auto& c : soft_constraint_ptrs_)
+      if (!c->set_up()) {
+        std::cerr << "SoftConstraint " << c->name() << " was not set up" << std::endl;
+        return false;
+      }
+    for (auto& l : links)
+      if (l->body_ptr() && !SetUpBody(*l)) return false;
+    const bool rigid = links.size() == 1 && constraint_ptrs_.empty() && soft_constraint_ptrs_.empty() &&
+                       root_link_ptr_->DegreesOfFreedom() == 6 && IsIdentity(root_link_ptr_->body2joint_pose());
+    if (!rigid || structure_index_ >= 0) {
+      if (!SetUpStructure(links)) return false;
+      if (!Check(batch_->ctx(), m3tb_calculate_consistent_poses(batch_->ctx()), "Optimizer::SetUp")) return false;
+      batch_->PosesChanged();
+    }
+    set_up_ = true;
+    return true;
+  }
+  // Optimizer::CalculateConsistentPoses (optimizer.cpp:133-142)
+  bool CalculateConsistentPoses() {
+    if (!set_up_) {
+      std::cerr << "Set up optimizer " << name_ << " first" << std::endl;
+      return false;
+    }
+    batch_->PosesChanged();
+    return Check(batch_->ctx(), m3tb_calculate_consistent_poses(batch_->ctx()), "Optimizer::CalculateConsistentPoses");
   }
   // Optimizer::CalculateOptimization (optimizer.cpp:144-167): batched over all optimizers of the Batch
   bool CalculateOptimization(int iteration, int corr_iteration, int opt_iteration) {
@@ -523,12 +697,114 @@ class Optimizer {
     batch_->MarkDone(Batch::kOptimize, iteration, corr_iteration, opt_iteration);
     return ok;
   }
+  // Refreshes Link::body2joint_pose / joint2parent_pose / link2world_pose of every referenced link from the device
+  bool FetchLinkPoses() {
+    if (structure_index_ < 0) return true;
+    const auto links = ReferencedLinks();
+    std::vector<float> b2j(12 * links.size()), j2p(12 * links.size()), l2w(12 * links.size());
+    if (!Check(batch_->ctx(), m3tb_get_link_poses(batch_->ctx(), structure_index_, b2j.data(), j2p.data(), l2w.data()),
+               "Optimizer::FetchLinkPoses"))
+      return false;
+    for (size_t i = 0; i < links.size(); ++i) {
+      std::copy(b2j.begin() + 12 * i, b2j.begin() + 12 * i + 12, links[i]->body2joint_pose_.m);
+      std::copy(j2p.begin() + 12 * i, j2p.begin() + 12 * i + 12, links[i]->joint2parent_pose_.m);
+      std::copy(l2w.begin() + 12 * i, l2w.begin() + 12 * i + 12, links[i]->link2world_pose_.m);
+    }
+    return true;
+  }
 
  private:
+  static bool IsIdentity(const Transform3fA& p) {
+    const Transform3fA i;
+    for (int k = 0; k < 12; ++k)
+      if (p.m[k] != i.m[k]) return false;
+    return true;
+  }
+  void AddReferencedLinks(const std::shared_ptr<Link>& l, std::vector<std::shared_ptr<Link>>* out) const {
+    out->push_back(l);
+    for (auto& c : l->child_link_ptrs()) AddReferencedLinks(c, out);
+  }
+  bool SetUpBody(const Link& link) {
+    const m3tb_region_params* rp = nullptr;
+    const m3tb_depth_params* dp = nullptr;
+    int rmodel = 0, dmodel = 0, ccam = 0, dcam = 0;
+    for (auto& m : link.modality_ptrs()) {
+      if (!m->set_up()) {
+        std::cerr << "Modality " << m->name() << " was not set up" << std::endl;
+        return false;
+      }
+      if (auto r = std::dynamic_pointer_cast<RegionModality>(m)) {
+        rp = &r->params();
+        rmodel = r->region_model_ptr()->index();
+        ccam = r->color_camera_ptr()->index();
+      } else if (auto d = std::dynamic_pointer_cast<DepthModality>(m)) {
+        dp = &d->params();
+        dmodel = d->depth_model_ptr()->index();
+        dcam = d->depth_camera_ptr()->index();
+      }
+    }
+    return Check(batch_->ctx(), m3tb_set_body(batch_->ctx(), link.body_ptr()->index(), rp, dp, &params_, rmodel, dmodel, ccam, dcam),
+                 "Optimizer::SetUp");
+  }
+  bool SetUpStructure(const std::vector<std::shared_ptr<Link>>& links) {
+    auto index_of = [&](const std::shared_ptr<Link>& l) {
+      for (size_t i = 0; i < links.size(); ++i)
+        if (links[i] == l) return int(i);
+      return -1;
+    };
+    std::vector<m3tb_link> ml(links.size());
+    for (size_t i = 0; i < links.size(); ++i) {
+      const Link& l = *links[i];
+      m3tb_link& o = ml[i];
+      o.body = l.body_ptr() ? l.body_ptr()->index() : -1;
+      o.parent = -1;
+      for (size_t p = 0; p < i && o.parent < 0; ++p)
+        for (auto& c : links[p]->child_link_ptrs())
+          if (c == links[i]) o.parent = int(p);
+      std::copy(l.body2joint_pose().m, l.body2joint_pose().m + 12, o.body2joint);
+      std::copy(l.joint2parent_pose().m, l.joint2parent_pose().m + 12, o.joint2parent);
+      std::copy(l.link2world_pose().m, l.link2world_pose().m + 12, o.link2world);
+      for (int d = 0; d < 6; ++d) o.free_directions[d] = l.free_directions()[d] ? 1 : 0;
+      o.fixed_body2joint_pose = l.fixed_body2joint_pose() ? 1 : 0;
+    }
+    std::vector<m3tb_constraint> mc;
+    auto add = [&](const Constraint& c, const SoftConstraint* soft) -> bool {
+      m3tb_constraint o{};
+      o.link1 = index_of(c.link1_ptr());
+      o.link2 = index_of(c.link2_ptr());
+      if (o.link1 < 0 || o.link2 < 0) {
+        std::cerr << "Constraint " << c.name() << " references a link outside optimizer " << name_ << std::endl;
+        return false;
+      }
+      std::copy(c.body12joint1_pose().m, c.body12joint1_pose().m + 12, o.body12joint1);
+      std::copy(c.body22joint2_pose().m, c.body22joint2_pose().m + 12, o.body22joint2);
+      for (int d = 0; d < 6; ++d) o.directions[d] = c.constraint_directions()[d] ? 1 : 0;
+      o.soft = soft ? 1 : 0;
+      o.standard_deviation_rotation = soft ? soft->standard_deviation_rotation() : 0.01f;
+      o.standard_deviation_translation = soft ? soft->standard_deviation_translation() : 0.001f;
+      o.max_distance_rotation = soft ? soft->max_distance_rotation() : 0.0f;
+      o.max_distance_translation = soft ? soft->max_distance_translation() : 0.0f;
+      mc.push_back(o);
+      return true;
+    };
+    for (auto& c : constraint_ptrs_)
+      if (!add(*c, nullptr)) return false;
+    for (auto& c : soft_constraint_ptrs_)
+      if (!add(*c, c.get())) return false;
+    if (structure_index_ < 0) structure_index_ = batch_->NextStructure();
+    return Check(batch_->ctx(),
+                 m3tb_set_structure(batch_->ctx(), structure_index_, ml.data(), int(ml.size()), mc.empty() ? nullptr : mc.data(),
+                                    int(mc.size()), &params_),
+                 "Optimizer::SetUp");
+  }
+
   std::string name_;
   std::shared_ptr<Batch> batch_;
   std::shared_ptr<Link> root_link_ptr_;
+  std::vector<std::shared_ptr<Constraint>> constraint_ptrs_;
+  std::vector<std::shared_ptr<SoftConstraint>> soft_constraint_ptrs_;
   m3tb_optimizer_params params_{};
+  int structure_index_ = -1;
   bool set_up_ = false;
 };
 
@@ -539,7 +815,8 @@ class Tracker {
       : name_(name), batch_(batch), n_corr_iterations_(n_corr_iterations), n_update_iterations_(n_update_iterations) {}
   bool AddOptimizer(const std::shared_ptr<Optimizer>& o) {
     optimizer_ptrs_.push_back(o);
-    for (auto& m : o->root_link_ptr()->modality_ptrs()) modality_ptrs_.push_back(m);
+    for (auto& l : o->ReferencedLinks())
+      for (auto& m : l->modality_ptrs()) modality_ptrs_.push_back(m);
     return true;
   }
   void set_n_corr_iterations(int v) { n_corr_iterations_ = v; }
@@ -550,8 +827,15 @@ class Tracker {
   bool SetUp() {  // Tracker::SetUp: set up all referenced objects (tracker.cpp:884-899 order: modalities, optimizers)
     for (auto& m : modality_ptrs_)
       if (!m->SetUp()) return false;
-    for (auto& o : optimizer_ptrs_)
+    for (auto& o : optimizer_ptrs_) {
+      for (auto& l : o->ReferencedLinks())
+        if (!l->SetUp()) return false;
+      for (auto& c : o->constraint_ptrs())
+        if (!c->SetUp()) return false;
+      for (auto& c : o->soft_constraint_ptrs())
+        if (!c->SetUp()) return false;
       if (!o->SetUp()) return false;
+    }
     set_up_ = true;
     return true;
   }

@@ -51,7 +51,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c4", choices=["c2", "c3", "c4", "c5"])
+    ap.add_argument("--variant", default="projected", choices=["projected", "constrained"],
+                    help="c5 only: joints as projected unknowns or as 6-DoF links + constraints (optimization_time.cpp)")
     ap.add_argument("--bodies", type=int, default=None, help="bodies per GPU (default: the preset's)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -63,6 +65,12 @@ def workload_description(wl, args, per_gpu=None):
     r = f"{wl.lines_per_body} lines" if wl.region else ""
     d = f"{wl.points_per_body} depth points" if wl.depth else ""
     both = " + ".join(x for x in (r, d) if x)
+    if args.workload == "c5":
+        st = wl.structures[0]
+        n_chains = (per_gpu or wl.n_bodies) // len(st.links)
+        return (f"configs[4] per-GPU shard (256 chains / 8 GPUs): {n_chains} chains/GPU x {len(st.links)} links x ({both}), "
+                f"{wl.notes['variant']} joints ({st.dof} unknowns + {st.n_constraint_rows} constraint rows per chain), "
+                f"one 640x480 RGB-D pair per link, {wl.n_corr_iterations} corr x {wl.n_update_iterations} update iterations")
     preset = {"c2": "configs[1]", "c3": "configs[2]", "c4": "configs[3] per-GPU shard (1024 bodies / 8 GPUs)"}[args.workload]
     return (f"{preset}: {per_gpu or wl.n_bodies} bodies/GPU x ({both}), one 640x480 "
             f"{'RGB-D pair' if wl.depth and wl.region else 'frame'} per body, "
@@ -72,6 +80,12 @@ def workload_description(wl, args, per_gpu=None):
 def build_workload(args, rank, n_shards=1):
     """Bodies [rank*nb, (rank+n_shards)*nb) of the weak-scaled job (nb bodies per GPU)."""
     pkg = importlib.import_module("3dobjecttracking_b200")
+    if args.workload == "c5":  # 8-link chains; --bodies counts links per GPU
+        n_chains = (args.bodies or 256) // 8
+        wl = pkg.synth.make_chain_workload(n_chains=n_chains * n_shards, n_links=8, n_lines=300, n_points=300,
+                                           variant=args.variant, n_divides=4, seed=args.seed,
+                                           first_chain=rank * n_chains)
+        return pkg, wl
     nb = args.bodies or pkg.synth.PRESETS[args.workload]["n_bodies"]
     wl = pkg.synth.make_workload(args.workload, n_bodies=nb * n_shards, n_divides=4, seed=args.seed,
                                  first_body=rank * nb)
@@ -162,7 +176,7 @@ def calibrate_threads(oracle_py, wl):
     cands = sorted(c for c in cands if c >= 1)
     best, best_t = cands[0], None
     for c in cands:
-        if c > max(1, wl.n_bodies):
+        if c > max(1, len(wl.structures) if getattr(wl, "structures", None) else wl.n_bodies):
             continue
         trk = oracle_py.OracleTracker(wl, n_threads=c, native=True)
         trk.tracking_step(0)  # warm-up (thread pool)
@@ -171,6 +185,7 @@ def calibrate_threads(oracle_py, wl):
         n, t_start = 0, time.perf_counter()
         while n < 2 or time.perf_counter() - t_start < 0.3:
             trk.set_poses(wl.start_body2world)
+            trk.reset_joint_poses()
             trk.tracking_step(0)
             n += 1
         dt = (time.perf_counter() - t_start) / n
@@ -194,10 +209,12 @@ def cpu_reference_run(args, wl, steps, warmup, threads=None):
     phases = np.zeros(3)
     for _ in range(warmup):
         trk.set_poses(wl.start_body2world)
+        trk.reset_joint_poses()
         trk.tracking_step(0)
     t_total, t_best = 0.0, None
     for _ in range(steps):
         trk.set_poses(wl.start_body2world)
+        trk.reset_joint_poses()
         t0 = time.perf_counter()
         ph = trk.tracking_step(0)
         t = time.perf_counter() - t0
@@ -275,6 +292,7 @@ def run_b200(args):
     # ---------------- value: device-resident frames, CUDA events per step, L2 flushed between steps --------
     for _ in range(max(args.warmup, 3)):
         ctx.set_poses(poses_np)
+        ctx.reset_joint_poses()
         step()
     torch.cuda.synchronize(dev)
     barrier()
@@ -283,6 +301,7 @@ def run_b200(args):
     for _ in range(args.steps):
         flush.zero_()
         ctx.set_poses(poses_np)
+        ctx.reset_joint_poses()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         step()
@@ -322,6 +341,7 @@ def run_b200(args):
             if h_depth is not None:
                 ctx.upload_batch_ptr(False, 0, nb, h_depth.data_ptr(), h_depth.stride(0), h_depth.stride(1))
             ctx.set_poses(poses_np)
+            ctx.reset_joint_poses()
             step()
             ctx._ck(ctx.L.m3tb_get_poses(ctx.h, 0, nb, capi._p(out_poses.numpy())))  # synchronises the stream
             if world > 1:  # publish: NCCL all-gather of the solved poses, once per frame
@@ -362,7 +382,8 @@ def run_b200(args):
     if rank == 0:
         total_b, region_b, depth_b, line_evals, point_evals = pkg.roofline.algorithmic_bytes_per_step(wl)
         peak, peak_src = measured_peak_gbs()
-        kernel_s = ms_per_step * 1e-3  # one k_track launch per step; events bracket exactly that launch
+        kernel_s = ms_per_step * 1e-3  # rigid bodies: one k_track launch per step, the events bracket exactly that launch
+        # (kinematic structures: k_track + k_structure per update iteration; the roofline is then quoted on the whole step)
         achieved = total_b / kernel_s / 1e9
         traffic = None
         try:

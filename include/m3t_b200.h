@@ -284,6 +284,9 @@ int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int
                        const m3tb_constraint* constraints, int n_constraints, const m3tb_optimizer_params* optimizer);
 int m3tb_clear_structures(m3tb_ctx* ctx);
 int m3tb_n_structures(const m3tb_ctx* ctx);
+/* Link::ResetJointPoses (link.cpp:243-246) for every link: body2joint / joint2parent back to the values given to
+ * m3tb_set_structure (the reference's default_*_pose_). One device-to-device copy, no synchronisation. */
+int m3tb_reset_joint_poses(m3tb_ctx* ctx);
 /* Optimizer::CalculateConsistentPoses (optimizer.cpp:133-142) for every structure. */
 int m3tb_calculate_consistent_poses(m3tb_ctx* ctx);
 /* Link::body2joint_pose / joint2parent_pose / link2world_pose of every link of one structure after the last update,

@@ -282,6 +282,12 @@ class OracleStructure:
                     K.standard_deviation_translation = c.standard_deviation_translation
         self.n_hard, self.n_soft = len(hard), len(soft)
 
+    def reset_joint_poses(self):
+        """Link::ResetJointPoses (link.cpp:243-246)"""
+        for i, l in enumerate(self.spec.links):
+            self.links[i].body2joint[:] = f32(l.body2joint).reshape(12).tolist()
+            self.links[i].joint2parent[:] = f32(l.joint2parent).reshape(12).tolist()
+
     def fill(self, S: Structure):
         S.links = C.cast(self.links, C.POINTER(Link))
         S.n_links = len(self.spec.links)
@@ -373,6 +379,10 @@ class OracleTracker:
         p = f32(poses).reshape(self.wl.n_bodies, 12)
         for b in range(self.wl.n_bodies):
             self.bodies[b].body2world[:] = p[b].tolist()
+
+    def reset_joint_poses(self):
+        for so in (self.structure_objs if self.structures is not None else []):
+            so.reset_joint_poses()
 
     def get_poses(self):
         return np.array([list(self.bodies[b].body2world) for b in range(self.wl.n_bodies)], np.float32).reshape(-1, 3, 4)
