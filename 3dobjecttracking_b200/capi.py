@@ -167,8 +167,12 @@ def region_params(settings=None) -> RegionParams:
         return p
     for k in ("n_lines_max", "min_continuous_distance", "function_amplitude", "function_slope", "learning_rate",
               "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
-              "unconsidered_line_length", "max_considered_line_length"):
+              "unconsidered_line_length", "max_considered_line_length", "reference_contour_length",
+              "measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
+              "n_unoccluded_iterations", "min_n_unoccluded_lines"):
         setattr(p, k, getattr(settings, k))
+    p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
+    p.measure_occlusions = int(settings.measure_occlusions)
     p.n_scales = len(settings.scales)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.scales):
@@ -185,6 +189,13 @@ def depth_params(settings=None) -> DepthParams:
         return p
     p.n_points_max = settings.n_points_max
     p.stride_length = settings.stride_length
+    p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
+    p.reference_surface_area = settings.reference_surface_area
+    p.use_depth_scaling = int(settings.use_depth_scaling)
+    p.measure_occlusions = int(settings.measure_occlusions)
+    for k in ("measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
+              "n_unoccluded_iterations", "min_n_unoccluded_points"):
+        setattr(p, k, getattr(settings, k))
     p.n_considered_distances = len(settings.considered_distances)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.considered_distances):
@@ -433,15 +444,17 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
     rp = region_params(wl.region) if wl.region else None
     dp = depth_params(wl.depth) if wl.depth else None
     op = OptimizerParams(wl.tikhonov_rotation, wl.tikhonov_translation)
+    # the depth camera serves the depth modality and RegionModality::MeasureOcclusions
+    need_depth_camera = bool(wl.depth) or bool(wl.region and wl.region.measure_occlusions and wl.depth_frames is not None)
     for b in range(count):
         if wl.region:
             ctx.set_color_camera(b, wl.color_intrinsics, wl.color_world2camera)
-        if wl.depth:
+        if need_depth_camera:
             ctx.set_depth_camera(b, wl.depth_intrinsics, wl.depth_world2camera, wl.depth_scale)
     if upload_frames:
         if wl.region:
             ctx.upload_color_batch(0, wl.color_frames[first:first + count])
-        if wl.depth:
+        if need_depth_camera:
             ctx.upload_depth_batch(0, wl.depth_frames[first:first + count])
     for b in range(count):
         ctx.set_body(b, rp, dp, op, 0, 0, b, b)

@@ -36,6 +36,7 @@ struct ModelAlloc {
   float4* orientations = nullptr;
   float* view_scalars = nullptr;
   float4* points = nullptr;
+  float* depth_offsets = nullptr;
 };
 
 }  // namespace
@@ -218,6 +219,12 @@ int ValidateBodies(m3tb_ctx* ctx) {
       if (!ctx->h_rmodels[B.region_model].set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "region model not set");
       const CameraDev& c = ctx->h_ccams[B.color_camera];
       if (!c.set || !c.image) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "color camera not set / no image uploaded");
+      if (B.rp.measure_occlusions) {  // RegionModality::SetUp / PrecalculateModelVariables (region_modality.cpp:965-977)
+        const CameraDev& d = ctx->h_dcams[B.depth_camera];
+        if (!d.set || !d.image) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "measure_occlusions: depth camera not set / no image uploaded");
+        if (B.rp.measured_depth_offset_radius > ctx->h_rmodels[B.region_model].max_radius_depth_offset)
+          return Fail(ctx, M3TB_ERR_INVALID, "Measured depth offset radius too large");
+      }
     }
     if (B.has_depth) {
       if (!ctx->h_dmodels[B.depth_model].set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "depth model not set");
@@ -292,15 +299,22 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   const size_t lut_bytes = lut_smem ? size_t(16 * 16 * 16) * sizeof(float2) : 0;
   const size_t dyn = ctx->use_tiles ? size_t(kDynSmemBytes) : lut_bytes;
   a.tile_bytes = ctx->use_tiles ? int(dyn - lut_bytes) : 0;
-#define M3TB_LAUNCH(T_, K_)                                                                       \
-  do {                                                                                            \
-    if (lut_smem) {                                                                               \
-      CU(cudaFuncSetAttribute(k_track<T_, K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn))); \
-      k_track<T_, K_, true><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                          \
-    } else {                                                                                      \
-      CU(cudaFuncSetAttribute(k_track<T_, K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn))); \
-      k_track<T_, K_, false><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                         \
-    }                                                                                             \
+  bool occ = false;  // measured occlusion handling anywhere: the kernel variant that carries the depth-window scans
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const BodyDev& B = ctx->h_bodies[b];
+    occ = occ || (B.has_region && B.rp.measure_occlusions) || (B.has_depth && B.dp.measure_occlusions);
+  }
+#define M3TB_LAUNCH1(T_, K_, L_, O_)                                                                                   \
+  do {                                                                                                                 \
+    CU(cudaFuncSetAttribute(k_track<T_, K_, L_, O_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));          \
+    k_track<T_, K_, L_, O_><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                                               \
+  } while (0)
+#define M3TB_LAUNCH(T_, K_)                               \
+  do {                                                    \
+    if (lut_smem && !occ) M3TB_LAUNCH1(T_, K_, true, false);  \
+    else if (lut_smem) M3TB_LAUNCH1(T_, K_, true, true);      \
+    else if (!occ) M3TB_LAUNCH1(T_, K_, false, false);        \
+    else M3TB_LAUNCH1(T_, K_, false, true);                   \
   } while (0)
   if (items <= 256) M3TB_LAUNCH(256, 1);
   else if (items <= 512) M3TB_LAUNCH(512, 1);
@@ -308,6 +322,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   else if (items <= 2048) M3TB_LAUNCH(512, 4);
   else return Fail(ctx, M3TB_ERR_UNSUPPORTED, "n_lines_max / n_points_max above 2048");
 #undef M3TB_LAUNCH
+#undef M3TB_LAUNCH1
   CU(cudaGetLastError());
   ctx->launches++;
   return M3TB_OK;
@@ -482,7 +497,7 @@ int StructureStep(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, in
   return M3TB_OK;
 }
 
-int LaunchHistogram(m3tb_ctx* ctx, int mode) {
+int LaunchHistogram(m3tb_ctx* ctx, int mode, int iteration) {
   int rc = ValidateBodies(ctx);
   if (rc) return rc;
   rc = SyncTables(ctx);
@@ -503,6 +518,8 @@ int LaunchHistogram(m3tb_ctx* ctx, int mode) {
   a.stride = ctx->hist_stride;
   a.mode = mode;
   a.roi = ctx->d_roi;
+  a.depth_cams = ctx->d_dcams;
+  a.iteration = iteration;
   k_histogram<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
@@ -510,12 +527,15 @@ int LaunchHistogram(m3tb_ctx* ctx, int mode) {
 }
 
 int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points, const float* orientations,
-             const float* scalars, const void* points) {
+             const float* scalars, const void* points, float stride_depth_offset, float max_radius_depth_offset) {
   if (model_id < 0 || model_id >= ctx->max_models || n_views <= 0 || n_points <= 0 || !orientations || !points)
     return Fail(ctx, M3TB_ERR_INVALID, "bad model arguments");
   std::vector<ModelAlloc>& allocs = region ? ctx->rmodel_alloc : ctx->dmodel_alloc;
   ModelAlloc& al = allocs[model_id];
-  if (al.orientations) { cudaFree(al.orientations); cudaFree(al.view_scalars); cudaFree(al.points); al = ModelAlloc(); }
+  if (al.orientations) {
+    cudaFree(al.orientations); cudaFree(al.view_scalars); cudaFree(al.points); cudaFree(al.depth_offsets);
+    al = ModelAlloc();
+  }
   // Repack the .bin AoS DataPoints (152 B / 144 B) into the 32 B records the kernels read:
   // region (cx,cy,cz,nx)(ny,nz,fg,bg), depth (cx,cy,cz,nx)(ny,nz,0,0). One-time setup, not on the hot path.
   const int fl = region ? M3TB_REGION_POINT_BYTES / 4 : M3TB_DEPTH_POINT_BYTES / 4;
@@ -528,6 +548,10 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
     d[6] = region ? s[6] : 0.0f;
     d[7] = region ? s[7] : 0.0f;
   }
+  // DataPoint::depth_offsets (30 floats per point) for the measured occlusion handling, kept as a separate table
+  std::vector<float> offsets(size_t(n_views) * n_points * kDepthOffsets);
+  for (size_t k = 0; k < size_t(n_views) * n_points; ++k)
+    std::memcpy(offsets.data() + k * kDepthOffsets, src + k * fl + (region ? 8 : 6), sizeof(float) * kDepthOffsets);
   float radius2 = 0.0f;
   for (size_t k = 0; k < size_t(n_views) * n_points; ++k) {
     const float* d = packed.data() + k * 8;
@@ -545,6 +569,8 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   CU(cudaMalloc(&al.orientations, sizeof(float4) * n_views));
   CU(cudaMalloc(&al.view_scalars, sizeof(float) * n_views));
   CU(cudaMalloc(&al.points, sizeof(float) * packed.size()));
+  CU(cudaMalloc(&al.depth_offsets, sizeof(float) * offsets.size()));
+  CU(cudaMemcpyAsync(al.depth_offsets, offsets.data(), sizeof(float) * offsets.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.orientations, ori4.data(), sizeof(float4) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.view_scalars, sc.data(), sizeof(float) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.points, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
@@ -557,6 +583,9 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   m.points = al.points;
   m.max_view_scalar = max_scalar;
   m.radius = std::sqrt(radius2);
+  m.depth_offsets = al.depth_offsets;
+  m.stride_depth_offset = stride_depth_offset;
+  m.max_radius_depth_offset = max_radius_depth_offset;
   m.set = 1;
   ctx->models_dirty = true;
   return M3TB_OK;
@@ -807,7 +836,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto* al : {&ctx->rmodel_alloc, &ctx->dmodel_alloc})
-    for (auto& a : *al) { cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); }
+    for (auto& a : *al) { cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); cudaFree(a.depth_offsets); }
   for (auto p : ctx->private_color) cudaFree(p);
   for (auto p : ctx->private_depth) cudaFree(p);
   cudaFree(ctx->color_pool.base); cudaFree(ctx->depth_pool.base);
@@ -841,15 +870,19 @@ int64_t m3tb_launch_count(const m3tb_ctx* ctx) { return ctx ? ctx->launches : 0;
 int m3tb_n_bodies(const m3tb_ctx* ctx) { return ctx ? ctx->n_bodies : 0; }
 
 int m3tb_set_region_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points, const float* orientations,
-                          const float* contour_lengths, const void* points, float, float) {
+                          const float* contour_lengths, const void* points, float stride_depth_offset,
+                          float max_radius_depth_offset) {
   CHECK_CTX();
-  return SetModel(ctx, true, model_id, n_views, n_points, orientations, contour_lengths, points);
+  return SetModel(ctx, true, model_id, n_views, n_points, orientations, contour_lengths, points, stride_depth_offset,
+                  max_radius_depth_offset);
 }
 
 int m3tb_set_depth_model(m3tb_ctx* ctx, int model_id, int n_views, int n_points, const float* orientations,
-                         const float* surface_areas, const void* points, float, float) {
+                         const float* surface_areas, const void* points, float stride_depth_offset,
+                         float max_radius_depth_offset) {
   CHECK_CTX();
-  return SetModel(ctx, false, model_id, n_views, n_points, orientations, surface_areas, points);
+  return SetModel(ctx, false, model_id, n_views, n_points, orientations, surface_areas, points, stride_depth_offset,
+                  max_radius_depth_offset);
 }
 
 int m3tb_set_color_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrinsics, const float world2camera[12]) {
@@ -910,13 +943,20 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
       return Fail(ctx, M3TB_ERR_INVALID, "region model / color camera id out of range");
     if (region->function_length != M3TB_FUNCTION_LENGTH || region->distribution_length != M3TB_DISTRIBUTION_LENGTH)
       return Fail(ctx, M3TB_ERR_UNSUPPORTED, "function_length / distribution_length other than 8 / 12");
-    if (region->measure_occlusions) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "measure_occlusions (SURVEY f4) not built yet");
+    if (region->measure_occlusions && (depth_camera < 0 || depth_camera >= ctx->max_cameras))
+      return Fail(ctx, M3TB_ERR_INVALID, "measure_occlusions needs a depth camera (RegionModality::MeasureOcclusions)");
     if (region->n_scales < 1 || region->n_scales > M3TB_MAX_SCHEDULE || region->n_standard_deviations < 1 ||
         region->n_standard_deviations > M3TB_MAX_SCHEDULE || region->n_lines_max < 1)
       return Fail(ctx, M3TB_ERR_INVALID, "bad region schedule / n_lines_max");
     int bs = Bitshift(region->n_histogram_bins);
     if (bs < 0) return Fail(ctx, M3TB_ERR_INVALID, "n_histogram_bins has to be 2, 4, 8, 16, 32 or 64");
     RegionParamsDev& r = B.rp;
+    r.measure_occlusions = region->measure_occlusions ? 1 : 0;
+    r.n_unoccluded_iterations = region->n_unoccluded_iterations;
+    r.min_n_unoccluded_lines = region->min_n_unoccluded_lines;
+    r.measured_depth_offset_radius = region->measured_depth_offset_radius;
+    r.measured_occlusion_radius = region->measured_occlusion_radius;
+    r.measured_occlusion_threshold = region->measured_occlusion_threshold;
     r.n_lines_max = region->n_lines_max;
     r.use_adaptive_coverage = region->use_adaptive_coverage;
     r.reference_contour_length = region->reference_contour_length;
@@ -969,12 +1009,17 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
   if (depth) {
     if (depth_model < 0 || depth_model >= ctx->max_models || depth_camera < 0 || depth_camera >= ctx->max_cameras)
       return Fail(ctx, M3TB_ERR_INVALID, "depth model / depth camera id out of range");
-    if (depth->measure_occlusions) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "measure_occlusions (SURVEY f4) not built yet");
     if (depth->n_considered_distances < 1 || depth->n_considered_distances > M3TB_MAX_SCHEDULE ||
         depth->n_standard_deviations < 1 || depth->n_standard_deviations > M3TB_MAX_SCHEDULE ||
         depth->n_points_max < 1 || !(depth->stride_length > 0.0f))
       return Fail(ctx, M3TB_ERR_INVALID, "bad depth schedule / n_points_max / stride_length");
     DepthParamsDev& d = B.dp;
+    d.measure_occlusions = depth->measure_occlusions ? 1 : 0;
+    d.n_unoccluded_iterations = depth->n_unoccluded_iterations;
+    d.min_n_unoccluded_points = depth->min_n_unoccluded_points;
+    d.measured_depth_offset_radius = depth->measured_depth_offset_radius;
+    d.measured_occlusion_radius = depth->measured_occlusion_radius;
+    d.measured_occlusion_threshold = depth->measured_occlusion_threshold;
     d.n_points_max = depth->n_points_max;
     d.use_adaptive_coverage = depth->use_adaptive_coverage;
     d.use_depth_scaling = depth->use_depth_scaling;
@@ -1074,13 +1119,12 @@ int m3tb_start_modalities(m3tb_ctx* ctx, int iteration) {
   CHECK_CTX();
   for (int b = 0; b < ctx->n_bodies; ++b) ctx->h_bodies[b].first_iteration = iteration;
   ctx->bodies_dirty = true;
-  return LaunchHistogram(ctx, 0);
+  return LaunchHistogram(ctx, 0, iteration);
 }
 
 int m3tb_calculate_results(m3tb_ctx* ctx, int iteration) {
   CHECK_CTX();
-  (void)iteration;
-  return LaunchHistogram(ctx, 1);
+  return LaunchHistogram(ctx, 1, iteration);
 }
 
 int m3tb_region_correspondences(m3tb_ctx* ctx, int iteration, int corr_iteration) {

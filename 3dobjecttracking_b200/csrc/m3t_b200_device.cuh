@@ -72,6 +72,8 @@ struct ModelDev {
   float max_view_scalar;
   float radius;               // max |center_f_body| over all points: bounding sphere used for the ROI tiles
   int set;
+  const float* depth_offsets; // [n_views][n_points][30]: DataPoint::depth_offsets (measured occlusion handling)
+  float stride_depth_offset, max_radius_depth_offset;  // Model::stride_depth_offset / max_radius_depth_offset
 };
 
 struct RegionParamsDev {
@@ -86,6 +88,9 @@ struct RegionParamsDev {
   float learning_rate_f, learning_rate_b, unconsidered_line_length, max_considered_line_length;
   float lookup_f[kFunctionLength], lookup_b[kFunctionLength];  // PrecalculateFunctionLookup
   float min_expected_variance;                                  // PrecalculateDistributionVariables
+  // measured occlusion handling (region_modality.h:432-443)
+  int measure_occlusions, n_unoccluded_iterations, min_n_unoccluded_lines;
+  float measured_depth_offset_radius, measured_occlusion_radius, measured_occlusion_threshold;
 };
 
 struct DepthParamsDev {
@@ -95,7 +100,13 @@ struct DepthParamsDev {
   float considered_distances[kMaxSchedule];
   int n_standard_deviations;
   float standard_deviations[kMaxSchedule];
+  // measured occlusion handling (depth_modality.h:313-321)
+  int measure_occlusions, n_unoccluded_iterations, min_n_unoccluded_points;
+  float measured_depth_offset_radius, measured_occlusion_radius, measured_occlusion_threshold;
 };
+
+constexpr int kDepthOffsets = 30;        // DataPoint::depth_offsets (region_model.h:97, depth_model.h:74)
+constexpr int kMaxNOcclusionStrides = 5; // region_modality.h:145, depth_modality.h:113
 
 struct BodyDev {
   int has_region, has_depth;

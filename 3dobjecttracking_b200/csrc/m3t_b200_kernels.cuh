@@ -249,6 +249,58 @@ struct LineState {  // RegionModality::DataLine (region_modality.h:150-165), the
   bool valid;
 };
 
+// The strided window scan shared by RegionModality::IsLineUnoccludedMeasured (region_modality.cpp:1355-1388) and
+// DepthModality::IsPointUnoccludedMeasured (depth_modality.cpp:739-775). ushort(x) of the reference is restated as
+// truncation to int and reduction modulo 2^16 (identical to the oracle).
+__device__ __noinline__ bool WindowUnoccluded(const Tile& t, const uint16_t* tile, const FrameView& f, int w_m1, int h_m1,
+                                              float center_u, float center_v, float diameter, float min_depth_value) {
+  const int stride = int(diameter / float(kMaxNOcclusionStrides) + 1.0f);
+  const int n_strides = int(diameter / float(stride) + 0.5f);
+  const int rounded_diameter = n_strides * stride;
+  const float rounded_radius = 0.5f * float(rounded_diameter);
+  int u_min = int(center_u - rounded_radius + 0.5f);
+  int v_min = int(center_v - rounded_radius + 0.5f);
+  int u_max = u_min + rounded_diameter;
+  int v_max = v_min + rounded_diameter;
+  u_min = max(u_min, 0);
+  v_min = max(v_min, 0);
+  u_max = min(u_max, w_m1);
+  v_max = min(v_max, h_m1);
+  const unsigned min_depth = unsigned(int(min_depth_value)) & 0xffffu;
+  for (int v = v_min; v <= v_max; v += stride)
+    for (int u = u_min; u <= u_max; u += stride) {
+      const unsigned depth = DepthAt(t, tile, f, u, v);
+      if (depth > 0u && depth < min_depth) return false;
+    }
+  return true;
+}
+
+// What RegionModality needs of its depth camera to measure occlusions (region_modality.cpp:944-962,1003-1005)
+struct RegionOcclusion {
+  const float* b2d;          // body2depth_camera_pose_
+  const float* offsets;      // depth_offsets of the closest view: [n_points][30]
+  int offset_id;             // measured_depth_offset_id_
+  float fu, fv, ppu, ppv, depth_scale;
+  int w_m1, h_m1;
+  float radius, threshold;
+  const FrameView* frame;
+  const Tile* tile;
+  const uint16_t* tile_px;
+};
+
+// RegionModality::IsLineUnoccludedMeasured (region_modality.cpp:1343-1389)
+__device__ __forceinline__ bool LineUnoccludedMeasured(const RegionOcclusion& o, float cbx, float cby, float cbz, int point) {
+  float x, y, z;
+  PoseApply(o.b2d, cbx, cby, cbz, x, y, z);
+  const float center_u = x * o.fu / z + o.ppu;
+  const float center_v = y * o.fv / z + o.ppv;
+  const float meter_to_pixel = o.fu / z;
+  const float diameter = 2.0f * o.radius * meter_to_pixel;
+  const float depth_offset = __ldg(o.offsets + size_t(point) * kDepthOffsets + o.offset_id);
+  return WindowUnoccluded(*o.tile, o.tile_px, *o.frame, o.w_m1, o.h_m1, center_u, center_v, diameter,
+                          (z - depth_offset - o.threshold) / o.depth_scale);
+}
+
 template <bool LUT_SMEM>
 __device__ __forceinline__ float2 LutFetch(const float2* __restrict__ lut_g, const float2* lut_s, int idx) {
   if (LUT_SMEM) return lut_s[idx];
@@ -317,11 +369,12 @@ __device__ __noinline__ void GatherSlow(int scale, int bs, int nb, bool horizont
   }
 }
 
-template <bool LUT_SMEM>
+template <bool LUT_SMEM, bool OCC = false>
 __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionParamsDev& rp, const float4 p0,
                                            const float4 p1, const FrameView& frame,
                                            const Tile& tile, const uint16_t* tile_px,
-                                           const float2* __restrict__ lut_g, const float2* lut_s, LineState& L) {
+                                           const float2* __restrict__ lut_g, const float2* lut_s, LineState& L,
+                                           const RegionOcclusion* occ = nullptr, int point = 0) {
   L.valid = false;
   // CalculateBasicLineData (:1231-1250)
   float x, y, z;
@@ -342,6 +395,9 @@ __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionPar
   if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
   if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
+  if (OCC) {  // measured occlusions (:1274-1281)
+    if (occ && !LineUnoccludedMeasured(*occ, p0.x, p0.y, p0.z, point)) return;
+  }
 
   // CalculateSegmentProbabilities (:1433-1573); horizontal / vertical cases folded into major / minor axes
   const bool horizontal = fabsf(nv) < fabsf(nu);
@@ -534,9 +590,10 @@ __device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int
   r[0] = best; r[1] = bx; r[2] = by; r[3] = bz;
 }
 
+template <bool OCC = false>
 __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
                                            const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
-                                           PointState& P) {
+                                           PointState& P, const float* offsets = nullptr, float stride_depth_offset = 1.0f) {
   P.valid = false;
   float x, y, z;
   PoseApply(it.b2c, p0.x, p0.y, p0.z, x, y, z);
@@ -548,6 +605,22 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
   if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
   if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
+  if (OCC) {  // IsPointUnoccludedMeasured (:736-776), depth offset selected as in CalculateBasicPointData (:669-681)
+    if (offsets) {
+      float radius = dp.measured_depth_offset_radius;
+      if (dp.use_depth_scaling) radius *= z;
+      int id = int(radius / stride_depth_offset + 0.5f);
+      if (id >= kDepthOffsets) id = kDepthOffsets - 1;
+      const float measured_depth_offset = __ldg(offsets + id);
+      float diameter = 2.0f * dp.measured_occlusion_radius * it.fu;
+      if (!dp.use_depth_scaling) diameter /= z;
+      float threshold = dp.measured_occlusion_threshold;
+      if (dp.use_depth_scaling) threshold *= z;
+      if (!WindowUnoccluded(tile, tile_px, frame, it.w_m1, it.h_m1, center_u, center_v, diameter,
+                            (z - measured_depth_offset - threshold) / it.depth_scale))
+        return;
+    }
+  }
   // FindCorrespondence (:826-884)
   float considered_distance = it.considered_distance;
   if (dp.use_depth_scaling) considered_distance *= z;
@@ -872,7 +945,7 @@ __device__ __forceinline__ void FitTile(Tile& t, int budget, int align_x) {
 // The fused kernel
 // ---------------------------------------------------------------------------------------------
 
-template <int T, int K, bool LUT_SMEM>
+template <int T, int K, bool LUT_SMEM, bool OCC>
 __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ TrackArgs args) {
   extern __shared__ __align__(128) unsigned char dyn[];
   __shared__ Shared sh;
@@ -897,7 +970,9 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
   M3TB_STAMP();
   // ---- prologue: pose, LUT bulk copy, ROI tiles ----------------------------------------------------
   const CameraDev* ccam = has_region ? &args.color_cams[body.color_camera] : nullptr;
-  const CameraDev* dcam = has_depth ? &args.depth_cams[body.depth_camera] : nullptr;
+  // the depth camera serves the depth modality and, with measured occlusion handling, the region modality
+  const bool region_occ = OCC && has_region && body.rp.measure_occlusions;
+  const CameraDev* dcam = (has_depth || region_occ) ? &args.depth_cams[body.depth_camera] : nullptr;
   const ModelDev* rmodel = has_region ? &args.region_models[body.region_model] : nullptr;
   const ModelDev* dmodel = has_depth ? &args.depth_models[body.depth_model] : nullptr;
   const bool do_rcorr = has_region && (args.phases & PH_REGION_CORR);
@@ -1069,14 +1144,41 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
         n_lines = min(n_lines, min(lcap, K * T));
         if (!lut_ready) { MbarWait(&sh.lut_bar, 0); lut_ready = true; }
         const float4* pts = rmodel->points + size_t(view_r) * rmodel->n_points * 2;
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int i = tid + k * T;
-          L[k].valid = false;
-          if (i < n_lines) {
-            float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-            RegionLine<LUT_SMEM>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, lut_g, lut_s, L[k]);
+        // measured occlusion handling: two passes (region_modality.cpp:435-463)
+        RegionOcclusion rocc;
+        bool handle = false;
+        if (OCC) {
+          handle = region_occ && rmodel->depth_offsets != nullptr &&
+                   (args.iteration - body.first_iteration) >= body.rp.n_unoccluded_iterations;
+          if (handle) {
+            if (!depth_ready) { MbarWait(&sh.depth_bar, 0); depth_ready = true; }
+            rocc.b2d = sh.db2c;
+            rocc.offsets = rmodel->depth_offsets + size_t(view_r) * rmodel->n_points * kDepthOffsets;
+            rocc.offset_id = int(body.rp.measured_depth_offset_radius / rmodel->stride_depth_offset + 0.5f);
+            rocc.fu = dcam->fu; rocc.fv = dcam->fv; rocc.ppu = dcam->ppu; rocc.ppv = dcam->ppv;
+            rocc.depth_scale = dcam->depth_scale;
+            rocc.w_m1 = dcam->width - 1; rocc.h_m1 = dcam->height - 1;
+            rocc.radius = body.rp.measured_occlusion_radius; rocc.threshold = body.rp.measured_occlusion_threshold;
+            rocc.frame = &dframe; rocc.tile = &dtile; rocc.tile_px = dtile_px;
           }
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+          for (int k = 0; k < K; ++k) {
+            const int i = tid + k * T;
+            L[k].valid = false;
+            if (i < n_lines) {
+              float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
+              RegionLine<LUT_SMEM, OCC>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, lut_g, lut_s, L[k],
+                                        handle ? &rocc : nullptr, i);
+            }
+          }
+          if (!OCC || !handle) break;
+          int survivors = 0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) survivors += __syncthreads_count(L[k].valid);
+          if (survivors >= body.rp.min_n_unoccluded_lines) break;
+          handle = false;
         }
       }
       M3TB_STAMP();  // region lines (thread 0's own line)
@@ -1089,14 +1191,30 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
         n_points = min(n_points, min(pcap, K * T));
         if (!depth_ready) { MbarWait(&sh.depth_bar, 0); depth_ready = true; }
         const float4* pts = dmodel->points + size_t(view_d) * dmodel->n_points * 2;
+        bool handle = false;
+        const float* offs = nullptr;
+        if (OCC) {  // depth_modality.cpp:295-313
+          handle = body.dp.measure_occlusions && dmodel->depth_offsets != nullptr &&
+                   (args.iteration - body.first_iteration) >= body.dp.n_unoccluded_iterations;
+          if (handle) offs = dmodel->depth_offsets + size_t(view_d) * dmodel->n_points * kDepthOffsets;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-          const int i = tid + k * T;
-          P[k].valid = false;
-          if (i < n_points) {
-            float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
-            DepthPoint(dit, body.dp, p0, p1, dframe, dtile, dtile_px, P[k]);
+          for (int k = 0; k < K; ++k) {
+            const int i = tid + k * T;
+            P[k].valid = false;
+            if (i < n_points) {
+              float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
+              DepthPoint<OCC>(dit, body.dp, p0, p1, dframe, dtile, dtile_px, P[k],
+                              handle ? offs + size_t(i) * kDepthOffsets : nullptr, dmodel->stride_depth_offset);
+            }
           }
+          if (!OCC || !handle) break;
+          int survivors = 0;
+#pragma unroll
+          for (int k = 0; k < K; ++k) survivors += __syncthreads_count(P[k].valid);
+          if (survivors >= body.dp.min_n_unoccluded_points) break;
+          handle = false;
         }
       }
     }
@@ -1263,6 +1381,8 @@ struct HistArgs {
   size_t stride;
   int mode;
   const RoiRecord* roi;
+  const CameraDev* depth_cams;  // measured occlusion handling
+  int iteration;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1336,7 +1456,8 @@ __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
     for (int i = 0; i < 12; ++i) pose[i] = args.poses[12 * body_id + i];
     for (int which = 0; which < 2; ++which) {
       todo[which] = 0;
-      const bool present = which == 0 ? body.has_region : body.has_depth;
+      const bool region_occ = body.has_region && body.rp.measure_occlusions;
+      const bool present = which == 0 ? body.has_region : (body.has_depth || region_occ);
       if (!present) continue;
       const CameraDev& cam = which == 0 ? args.color_cams[body.color_camera] : args.depth_cams[body.depth_camera];
       RoiRecord& rec = args.roi[2 * body_id + which];
@@ -1350,12 +1471,21 @@ __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
         const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + kIngestMotionMarginPx;
         RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 16, t);
       } else {
-        const ModelDev& m = args.depth_models[body.depth_model];
+        // depth search windows and, with measured occlusion handling, the occlusion windows around the region points
+        const ModelDev& m = body.has_depth ? args.depth_models[body.depth_model] : args.region_models[body.region_model];
         float d_max = 0.0f;
-        for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
+        if (body.has_depth) {
+          for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
+          if (body.dp.measure_occlusions) d_max = fmaxf(d_max, body.dp.measured_occlusion_radius);
+        }
+        float radius = m.radius;
+        if (region_occ) {
+          d_max = fmaxf(d_max, body.rp.measured_occlusion_radius);
+          radius = fmaxf(radius, args.region_models[body.region_model].radius);
+        }
         const float z = b2c[11];
-        const float reach = (z > 2.0f * m.radius) ? d_max * cam.fu / (z - m.radius) + 2.0f + kIngestMotionMarginPx : 0.0f;
-        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 8, t);
+        const float reach = (z > 2.0f * radius) ? d_max * cam.fu / (z - radius) + 2.0f + kIngestMotionMarginPx : 0.0f;
+        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, radius, reach, 8, t);
       }
       rect[which] = t;
       todo[which] = 1;
@@ -1401,6 +1531,27 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   const float4* pts = model.points + size_t(view) * model.n_points * 2;
   const FrameView frame = MakeFrameView(cam, args.roi[2 * body_id + 0]);
   const int bs = rp.bitshift, nb = rp.n_bins;
+  // handle_occlusions: StartModality (:382) n_unoccluded_iterations == 0, CalculateResults (:578-579)
+  const bool handle_occlusions = args.mode == 0 ? rp.n_unoccluded_iterations == 0
+                                                : (args.iteration - body.first_iteration) >= rp.n_unoccluded_iterations;
+  const bool occ_on = handle_occlusions && rp.measure_occlusions && model.depth_offsets != nullptr;
+  RegionOcclusion occ;
+  FrameView dframe;
+  Tile no_tile;
+  float b2d[12];
+  no_tile.x0 = no_tile.y0 = no_tile.w = no_tile.h = no_tile.pitch = 0; no_tile.offset = 0u;
+  if (occ_on) {
+    const CameraDev& dcam = args.depth_cams[body.depth_camera];
+    PoseMul(dcam.w2c, sh.pose, b2d);
+    dframe = MakeFrameView(dcam, args.roi[2 * body_id + 1]);
+    occ.b2d = b2d;
+    occ.offsets = model.depth_offsets + size_t(view) * model.n_points * kDepthOffsets;
+    occ.offset_id = int(rp.measured_depth_offset_radius / model.stride_depth_offset + 0.5f);
+    occ.fu = dcam.fu; occ.fv = dcam.fv; occ.ppu = dcam.ppu; occ.ppv = dcam.ppv; occ.depth_scale = dcam.depth_scale;
+    occ.w_m1 = dcam.width - 1; occ.h_m1 = dcam.height - 1;
+    occ.radius = rp.measured_occlusion_radius; occ.threshold = rp.measured_occlusion_threshold;
+    occ.frame = &dframe; occ.tile = &no_tile; occ.tile_px = nullptr;
+  }
   for (int i = tid; i < n_lines; i += kBlockThreads) {
     float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
     float x, y, z;
@@ -1410,6 +1561,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     float center_v = y * it.fv / z + it.ppv;
     int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
     if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) continue;
+    if (occ_on && !LineUnoccludedMeasured(occ, p0.x, p0.y, p0.z, i)) continue;  // :1086-1089
     float length_f = rp.max_considered_line_length, length_b = rp.max_considered_line_length;
     float l_f = p1.z * it.fu / z;
     float l_b = p1.w * it.fu / z;

@@ -168,6 +168,15 @@ class RegionSettings:
     learning_rate_b: float = 0.2
     unconsidered_line_length: float = 0.5
     max_considered_line_length: float = 20.0
+    use_adaptive_coverage: bool = False
+    reference_contour_length: float = 0.0
+    # measured occlusion handling (region_modality.h:432-443)
+    measure_occlusions: bool = False
+    measured_depth_offset_radius: float = 0.01
+    measured_occlusion_radius: float = 0.01
+    measured_occlusion_threshold: float = 0.03
+    n_unoccluded_iterations: int = 10
+    min_n_unoccluded_lines: int = 0
 
 
 @dataclass
@@ -176,6 +185,16 @@ class DepthSettings:
     stride_length: float = 0.005
     considered_distances: tuple = (0.05, 0.02, 0.01)
     standard_deviations: tuple = (0.05, 0.03, 0.02)
+    use_adaptive_coverage: bool = False
+    reference_surface_area: float = 0.0
+    use_depth_scaling: bool = False
+    # measured occlusion handling (depth_modality.h:313-321)
+    measure_occlusions: bool = False
+    measured_depth_offset_radius: float = 0.01
+    measured_occlusion_radius: float = 0.01
+    measured_occlusion_threshold: float = 0.03
+    n_unoccluded_iterations: int = 10
+    min_n_unoccluded_points: int = 0
 
 
 @dataclass
@@ -273,6 +292,59 @@ def rotation_pose(axis, deg):
     p = identity_pose()
     p[:, :3] = _rot(axis, deg)
     return p
+
+
+def fill_depth_offsets(model: Model, seed=0):
+    """Synthetic DataPoint::depth_offsets (the analytic generator leaves them at 0): non-negative and non-decreasing
+    with the radius index, like Model::CalculateDepthOffsets (model.cpp:338-384) produces them. In place."""
+    first = 8 if model.kind == "region" else 6
+    rng = np.random.default_rng([seed, 0x4F46, model.n_views, model.n_points])
+    slope = rng.uniform(0.0, 0.6, size=model.points.shape[:2]).astype(np.float32)
+    k = np.arange(30, dtype=np.float32)
+    model.points[:, :, first:first + 30] = slope[:, :, None] * (k * np.float32(model.stride_depth_offset))[None, None, :]
+
+
+def add_occluder(wl: Workload, body: int, side="left", cover=0.45, gap_m=0.12, color_mean=(60, 170, 70), sigma=8.0, seed=0):
+    """Paints a fronto-parallel occluder (a plane patch in the colour camera's frame, gap_m in front of the body) over
+    `cover` of the body's image extent into the body's colour and depth frames, consistently in both cameras."""
+    b2w = wl.gt_body2world[body]
+    T = lambda p: np.vstack([np.asarray(p, np.float64), [0, 0, 0, 1]])
+    b2c = (T(wl.color_world2camera) @ T(b2w))[:3]
+    zc = b2c[2, 3]
+    z_occ = zc - gap_m
+    r = 0.045  # prism circumradius
+    cx, cy = b2c[0, 3], b2c[1, 3]
+    if side == "left":
+        x0, x1, y0, y1 = cx - 3 * r, cx - r + 2 * r * cover, cy - 3 * r, cy + 3 * r
+    else:
+        x0, x1, y0, y1 = cx - 3 * r, cx + 3 * r, cy - 3 * r, cy - r + 2 * r * cover
+    # the patch is given at the body's depth; seen from the camera it is the cone through it cut at z_occ
+    x0, x1, y0, y1 = (v * z_occ / zc for v in (x0, x1, y0, y1))
+    rng = np.random.default_rng([seed, 0x4F43, body])
+    ci, di = wl.color_intrinsics, wl.depth_intrinsics
+    if wl.color_frames is not None:
+        v, u = np.mgrid[0:ci.height, 0:ci.width]
+        X = (u - ci.ppu) / ci.fu * z_occ
+        Y = (v - ci.ppv) / ci.fv * z_occ
+        m = (X >= x0) & (X <= x1) & (Y >= y0) & (Y <= y1)
+        img = wl.color_frames[body][:, :3 * ci.width].reshape(ci.height, ci.width, 3)
+        noise = rng.normal(0.0, sigma, size=(int(m.sum()), 3))
+        img[m] = np.clip(np.rint(np.asarray(color_mean, np.float64)[None, :] + noise), 0, 255).astype(np.uint8)
+    if wl.depth_frames is not None:
+        # plane z = z_occ of the colour camera expressed in the depth camera: n . X = d
+        c2d = T(wl.depth_world2camera) @ np.linalg.inv(T(wl.color_world2camera))
+        n = c2d[:3, :3] @ np.array([0.0, 0.0, 1.0])
+        p0 = c2d[:3, :3] @ np.array([0.0, 0.0, z_occ]) + c2d[:3, 3]
+        d = float(n @ p0)
+        v, u = np.mgrid[0:di.height, 0:di.width]
+        ray = np.stack([(u - di.ppu) / di.fu, (v - di.ppv) / di.fv, np.ones_like(u, np.float64)], -1)
+        t = d / (ray @ n)
+        P = ray * t[..., None]
+        Pc = (P - c2d[:3, 3]) @ c2d[:3, :3]      # back into the colour camera frame (R^T (P - t))
+        m = (t > 0) & (Pc[..., 0] >= x0) & (Pc[..., 0] <= x1) & (Pc[..., 1] >= y0) & (Pc[..., 1] <= y1)
+        z = P[..., 2] + rng.normal(0.0, 0.001, size=P.shape[:2])
+        wl.depth_frames[body][m] = np.clip(np.rint(z[m] / wl.depth_scale), 1, 65535).astype(np.uint16)
+    wl.notes.setdefault("occluders", []).append(dict(body=body, side=side, cover=cover, z=z_occ))
 
 
 PRESETS = {

@@ -747,9 +747,76 @@ int orc_closest_view(const orc_model* model, const float body2camera[12], int ro
   return ClosestView(model, body2camera, rotation_mode);
 }
 
+}  // extern "C"
+namespace {
+constexpr int kMaxNOcclusionStrides = 5;  // region_modality.h:145, depth_modality.h:113
+
+// The strided window scan shared by RegionModality::IsLineUnoccludedMeasured (region_modality.cpp:1355-1388) and
+// DepthModality::IsPointUnoccludedMeasured (depth_modality.cpp:739-775): false if any valid depth sample inside the
+// window lies in front of min_depth. The reference converts the float threshold with ushort(x); that is restated as
+// truncation to int followed by reduction modulo 2^16 (what x86 does), so that a negative threshold behaves the same
+// on both sides of the parity tests.
+bool WindowUnoccluded(const orc_depth_frame* f, float center_u, float center_v, float diameter, float min_depth_value) {
+  int stride = int(diameter / kMaxNOcclusionStrides + 1.0f);
+  int n_strides = int(diameter / stride + 0.5f);
+  int rounded_diameter = n_strides * stride;
+  float rounded_radius = 0.5f * float(rounded_diameter);
+  int u_min = int(center_u - rounded_radius + 0.5f);
+  int v_min = int(center_v - rounded_radius + 0.5f);
+  int u_max = u_min + rounded_diameter;
+  int v_max = v_min + rounded_diameter;
+  u_min = std::max(u_min, 0);
+  v_min = std::max(v_min, 0);
+  u_max = std::min(u_max, f->intrinsics.width - 1);
+  v_max = std::min(v_max, f->intrinsics.height - 1);
+  const uint16_t min_depth = uint16_t(unsigned(int(min_depth_value)) & 0xffffu);
+  for (int v = v_min; v <= v_max; v += stride) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(f->depth) + size_t(v) * f->pitch);
+    for (int u = u_min; u <= u_max; u += stride) {
+      uint16_t depth = row[u];
+      if (depth > 0 && depth < min_depth) return false;
+    }
+  }
+  return true;
+}
+
+// RegionModality::IsLineUnoccludedMeasured (region_modality.cpp:1343-1389)
+bool LineUnoccludedMeasured(const orc_region_params* p, const orc_depth_frame* f, const float* body2depth_camera,
+                            const float* center_f_body, float depth_offset) {
+  float cd[3];
+  PoseApply(body2depth_camera, center_f_body, cd);
+  float center_u = cd[0] * f->intrinsics.fu / cd[2] + f->intrinsics.ppu;
+  float center_v = cd[1] * f->intrinsics.fv / cd[2] + f->intrinsics.ppv;
+  float meter_to_pixel = f->intrinsics.fu / cd[2];
+  float diameter = 2.0f * p->measured_occlusion_radius * meter_to_pixel;
+  return WindowUnoccluded(f, center_u, center_v, diameter,
+                          (cd[2] - depth_offset - p->measured_occlusion_threshold) / f->depth_scale);
+}
+
+// measured_depth_offset_id_ (region_modality.cpp:965-977); -1 if the radius exceeds the model's table
+int RegionOffsetId(const orc_region_params* p, const orc_model* model) {
+  if (p->measured_depth_offset_radius > model->max_radius_depth_offset) return -1;
+  return int(p->measured_depth_offset_radius / model->stride_depth_offset + 0.5f);
+}
+}  // namespace
+extern "C" {
+
 // ---- RegionModality::AddLinePixelColorsToTempHistograms (region_modality.cpp:1025-1155) -------
 void orc_region_add_line_pixels(const orc_region_params* p, const orc_model* model, const orc_color_frame* c,
                                 const float body2world[12], int rotation_mode, float* memory_f, float* memory_b) {
+  orc_region_add_line_pixels_occ(p, model, c, nullptr, 0, body2world, rotation_mode, memory_f, memory_b);
+}
+
+void orc_region_add_line_pixels_occ(const orc_region_params* p, const orc_model* model, const orc_color_frame* c,
+                                    const orc_depth_frame* occlusion_depth, int handle_occlusions,
+                                    const float body2world[12], int rotation_mode, float* memory_f, float* memory_b) {
+  const bool occ = handle_occlusions && p->measure_occlusions && occlusion_depth;
+  float body2depth_camera[12];
+  int offset_id = 0;
+  if (occ) {
+    PoseMul(occlusion_depth->world2camera, body2world, body2depth_camera);  // region_modality.cpp:1003-1005
+    offset_id = std::max(0, RegionOffsetId(p, model));
+  }
   RegionVars v;
   RegionPrecalc(p, c, body2world, 0, rotation_mode, &v);
   int view = ClosestView(model, v.body2camera, rotation_mode);
@@ -770,6 +837,8 @@ void orc_region_add_line_pixels(const orc_region_params* p, const orc_model* mod
     int i_center_u = int(center_u + 0.5f);
     int i_center_v = int(center_v + 0.5f);
     if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+    if (occ && !LineUnoccludedMeasured(p, occlusion_depth, body2depth_camera, center_f_body, dp[8 + offset_id]))
+      continue;  // :1086-1089
     float length_f = p->max_considered_line_length;
     float length_b = p->max_considered_line_length;
     float l_f = foreground_distance * v.fu / cc[2];
@@ -820,7 +889,6 @@ int orc_region_correspondences(const orc_region_params* p, const orc_model* mode
                                const orc_depth_frame* occlusion_depth, const float* hist_f, const float* hist_b,
                                const float body2world[12], int iteration, int first_iteration, int corr_iteration,
                                int rotation_mode, orc_region_line* lines, int* view_index) {
-  (void)occlusion_depth; (void)iteration; (void)first_iteration;  // occlusion handling: not configured
   RegionVars v;
   RegionPrecalc(p, c, body2world, corr_iteration, rotation_mode, &v);
   int view = ClosestView(model, v.body2camera, rotation_mode);
@@ -830,36 +898,53 @@ int orc_region_correspondences(const orc_region_params* p, const orc_model* mode
                               model->n_points);
   const float* pts = model->points + size_t(view) * model->n_points * ORC_REGION_POINT_FLOATS;
   float sf[32], sb[32];
-  // Without occlusion handling pass j == 0 always suffices (:435-463).
-  for (int i = 0; i < n_lines; ++i) {
-    const float* dp = pts + size_t(i) * ORC_REGION_POINT_FLOATS;
-    orc_region_line& L = lines[i];
-    std::memset(&L, 0, sizeof(L));
-    L.model_index = i;
-    // CalculateBasicLineData (:1231-1250)
-    float cc[3];
-    PoseApply(v.body2camera, dp, cc);
-    float n2[2] = {v.rot[0] * dp[3] + v.rot[1] * dp[4] + v.rot[2] * dp[5],
-                   v.rot[3] * dp[3] + v.rot[4] * dp[4] + v.rot[5] * dp[5]};
-    Normalize2(n2);
-    L.center_f_body[0] = dp[0]; L.center_f_body[1] = dp[1]; L.center_f_body[2] = dp[2];
-    L.center_u = cc[0] * v.fu / cc[2] + v.ppu;
-    L.center_v = cc[1] * v.fv / cc[2] + v.ppv;
-    L.normal_u = n2[0];
-    L.normal_v = n2[1];
-    float continuous_distance = std::min(dp[7], dp[6]) * v.fu / (cc[2] * v.fscale);
-    // IsLineValid (:1252-1291)
-    if (continuous_distance < p->min_continuous_distance) continue;
-    if (cc[2] <= 0.0f) continue;
-    int i_center_u = int(L.center_u + 0.5f);
-    int i_center_v = int(L.center_v + 0.5f);
-    if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
-    if (!SegmentProbabilities(v, c, hist_f, hist_b, L.center_u, L.center_v, L.normal_u, L.normal_v, sf, sb,
-                              &L.normal_component_to_scale, &L.delta_r))
-      continue;
-    Distribution(v, p->function_length, p->distribution_length, sf, sb, L.distribution);
-    Moments(v, p->distribution_length, L.distribution, &L.mean, &L.measured_variance);
-    L.valid = 1;
+  const bool can_measure = p->measure_occlusions && occlusion_depth;
+  float body2depth_camera[12];
+  int offset_id = 0;
+  if (can_measure) {
+    PoseMul(occlusion_depth->world2camera, body2world, body2depth_camera);
+    offset_id = std::max(0, RegionOffsetId(p, model));
+  }
+  // Two passes (:435-463): the first handles occlusions once the modality has run n_unoccluded_iterations; if too
+  // few lines survive, everything is recomputed without occlusion handling. Without an occlusion source the two
+  // passes are identical, so one suffices.
+  for (int j = 0; j < 2; ++j) {
+    const bool handle_occlusions = j == 0 && (iteration - first_iteration) >= p->n_unoccluded_iterations;
+    const bool occ = handle_occlusions && can_measure;
+    int survivors = 0;
+    for (int i = 0; i < n_lines; ++i) {
+      const float* dp = pts + size_t(i) * ORC_REGION_POINT_FLOATS;
+      orc_region_line& L = lines[i];
+      std::memset(&L, 0, sizeof(L));
+      L.model_index = i;
+      // CalculateBasicLineData (:1231-1250)
+      float cc[3];
+      PoseApply(v.body2camera, dp, cc);
+      float n2[2] = {v.rot[0] * dp[3] + v.rot[1] * dp[4] + v.rot[2] * dp[5],
+                     v.rot[3] * dp[3] + v.rot[4] * dp[4] + v.rot[5] * dp[5]};
+      Normalize2(n2);
+      L.center_f_body[0] = dp[0]; L.center_f_body[1] = dp[1]; L.center_f_body[2] = dp[2];
+      L.center_u = cc[0] * v.fu / cc[2] + v.ppu;
+      L.center_v = cc[1] * v.fv / cc[2] + v.ppv;
+      L.normal_u = n2[0];
+      L.normal_v = n2[1];
+      float continuous_distance = std::min(dp[7], dp[6]) * v.fu / (cc[2] * v.fscale);
+      // IsLineValid (:1252-1291)
+      if (continuous_distance < p->min_continuous_distance) continue;
+      if (cc[2] <= 0.0f) continue;
+      int i_center_u = int(L.center_u + 0.5f);
+      int i_center_v = int(L.center_v + 0.5f);
+      if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+      if (occ && !LineUnoccludedMeasured(p, occlusion_depth, body2depth_camera, dp, dp[8 + offset_id])) continue;
+      if (!SegmentProbabilities(v, c, hist_f, hist_b, L.center_u, L.center_v, L.normal_u, L.normal_v, sf, sb,
+                                &L.normal_component_to_scale, &L.delta_r))
+        continue;
+      Distribution(v, p->function_length, p->distribution_length, sf, sb, L.distribution);
+      Moments(v, p->distribution_length, L.distribution, &L.mean, &L.measured_variance);
+      L.valid = 1;
+      survivors++;
+    }
+    if (!occ || survivors >= p->min_n_unoccluded_lines) break;
   }
   return n_lines;
 }
@@ -917,7 +1002,6 @@ void orc_region_gradient_hessian(const orc_region_params* p, const orc_color_fra
 int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model, const orc_depth_frame* f,
                               const float body2world[12], int iteration, int first_iteration, int corr_iteration,
                               int rotation_mode, orc_depth_point* points, int* view_index) {
-  (void)iteration; (void)first_iteration;
   DepthVars v;
   DepthPrecalc(p, f, body2world, corr_iteration, &v);
   int view = ClosestView(model, v.body2camera, rotation_mode);
@@ -926,25 +1010,44 @@ int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model,
                                model->view_scalars ? model->view_scalars[view] : 0.0f, model->max_view_scalar,
                                model->n_points);
   const float* pts = model->points + size_t(view) * model->n_points * ORC_DEPTH_POINT_FLOATS;
-  for (int i = 0; i < n_points; ++i) {
-    const float* dp = pts + size_t(i) * ORC_DEPTH_POINT_FLOATS;
-    orc_depth_point& P = points[i];
-    std::memset(&P, 0, sizeof(P));
-    P.model_index = i;
-    // CalculateBasicPointData (:656-695)
-    float cc[3];
-    PoseApply(v.body2camera, dp, cc);
-    for (int k = 0; k < 3; ++k) { P.center_f_body[k] = dp[k]; P.normal_f_body[k] = dp[3 + k]; }
-    float center_u = cc[0] * v.fu / cc[2] + v.ppu;
-    float center_v = cc[1] * v.fv / cc[2] + v.ppv;
-    float depth = cc[2];
-    // IsPointValid (:697-726)
-    if (depth <= 0.0f) continue;
-    int i_center_u = int(center_u + 0.5f);
-    int i_center_v = int(center_v + 0.5f);
-    if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
-    if (!FindCorrespondence(p, v, f, cc, center_u, center_v, depth, P.correspondence_center_f_camera)) continue;
-    P.valid = 1;
+  for (int j = 0; j < 2; ++j) {  // :295-313
+    const bool occ = j == 0 && (iteration - first_iteration) >= p->n_unoccluded_iterations && p->measure_occlusions;
+    int survivors = 0;
+    for (int i = 0; i < n_points; ++i) {
+      const float* dp = pts + size_t(i) * ORC_DEPTH_POINT_FLOATS;
+      orc_depth_point& P = points[i];
+      std::memset(&P, 0, sizeof(P));
+      P.model_index = i;
+      // CalculateBasicPointData (:656-695)
+      float cc[3];
+      PoseApply(v.body2camera, dp, cc);
+      for (int k = 0; k < 3; ++k) { P.center_f_body[k] = dp[k]; P.normal_f_body[k] = dp[3 + k]; }
+      float center_u = cc[0] * v.fu / cc[2] + v.ppu;
+      float center_v = cc[1] * v.fv / cc[2] + v.ppv;
+      float depth = cc[2];
+      // IsPointValid (:697-726)
+      if (depth <= 0.0f) continue;
+      int i_center_u = int(center_u + 0.5f);
+      int i_center_v = int(center_v + 0.5f);
+      if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+      if (occ) {  // IsPointUnoccludedMeasured (:736-776) with the depth offset selected in CalculateBasicPointData
+        float radius = p->measured_depth_offset_radius;
+        if (p->use_depth_scaling) radius *= depth;
+        int id = int(radius / model->stride_depth_offset + 0.5f);
+        if (id >= ORC_N_DEPTH_OFFSETS) id = ORC_N_DEPTH_OFFSETS - 1;
+        float measured_depth_offset = dp[6 + id];
+        float diameter = 2.0f * p->measured_occlusion_radius * v.fu;
+        if (!p->use_depth_scaling) diameter /= depth;
+        float threshold = p->measured_occlusion_threshold;
+        if (p->use_depth_scaling) threshold *= depth;
+        if (!WindowUnoccluded(f, center_u, center_v, diameter, (depth - measured_depth_offset - threshold) / v.depth_scale))
+          continue;
+      }
+      if (!FindCorrespondence(p, v, f, cc, center_u, center_v, depth, P.correspondence_center_f_camera)) continue;
+      P.valid = 1;
+      survivors++;
+    }
+    if (!occ || survivors >= p->min_n_unoccluded_points) break;
   }
   return n_points;
 }
@@ -1027,7 +1130,8 @@ static void StartOne(orc_body* b, int iteration, int rotation_mode) {
   int nb = b->region->n_histogram_bins;
   size_t n = size_t(nb) * nb * nb;
   std::vector<float> mf(n, 0.0f), mb(n, 0.0f);
-  orc_region_add_line_pixels(b->region, b->region_model, b->color, b->body2world, rotation_mode, mf.data(), mb.data());
+  orc_region_add_line_pixels_occ(b->region, b->region_model, b->color, b->region_occlusion_frame,
+                                 b->region->n_unoccluded_iterations == 0, b->body2world, rotation_mode, mf.data(), mb.data());
   orc_hist_calculate(nb, 1.0f, mf.data(), b->histogram_f);  // InitializeHistograms (color_histograms.cpp:72-81)
   orc_hist_calculate(nb, 1.0f, mb.data(), b->histogram_b);
 }
@@ -1037,21 +1141,22 @@ void orc_start_modalities(orc_body* bodies, int n_bodies, int iteration, int rot
   for (int i = 0; i < n_bodies; ++i) StartOne(&bodies[i], iteration, rotation_mode);
 }
 
-static void ResultsOne(orc_body* b, int rotation_mode) {
+static void ResultsOne(orc_body* b, int iteration, int rotation_mode) {
   // RegionModality::CalculateResults (region_modality.cpp:572-583)
   if (!b->region) return;
   int nb = b->region->n_histogram_bins;
   size_t n = size_t(nb) * nb * nb;
   std::vector<float> mf(n, 0.0f), mb(n, 0.0f);
-  orc_region_add_line_pixels(b->region, b->region_model, b->color, b->body2world, rotation_mode, mf.data(), mb.data());
+  orc_region_add_line_pixels_occ(b->region, b->region_model, b->color, b->region_occlusion_frame,
+                                 (iteration - b->first_iteration) >= b->region->n_unoccluded_iterations, b->body2world,
+                                 rotation_mode, mf.data(), mb.data());
   orc_hist_calculate(nb, b->region->learning_rate_f, mf.data(), b->histogram_f);  // UpdateHistograms (:83-92)
   orc_hist_calculate(nb, b->region->learning_rate_b, mb.data(), b->histogram_b);
 }
 
 void orc_calculate_results(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads) {
-  (void)iteration;
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
-  for (int i = 0; i < n_bodies; ++i) ResultsOne(&bodies[i], rotation_mode);
+  for (int i = 0; i < n_bodies; ++i) ResultsOne(&bodies[i], iteration, rotation_mode);
 }
 
 // Tracker::ExecuteTrackingStep (tracker.cpp:344-361) for one body (= one optimizer with a root link).
@@ -1060,9 +1165,9 @@ static void StepOne(orc_body* b, int iteration, int corr_begin, int corr_end, in
   for (int corr = corr_begin; corr < corr_end; ++corr) {
     double t0 = Now();
     if (b->region)
-      b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, nullptr, b->histogram_f,
-                                              b->histogram_b, b->body2world, iteration, b->first_iteration, corr,
-                                              rotation_mode, b->lines, &b->region_view);
+      b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, b->region_occlusion_frame,
+                                              b->histogram_f, b->histogram_b, b->body2world, iteration,
+                                              b->first_iteration, corr, rotation_mode, b->lines, &b->region_view);
     if (b->depth)
       b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
                                               b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);
@@ -1530,9 +1635,9 @@ void orc_tracking_step_structures(orc_body* bodies, orc_structure* structures, i
         if (s->links[l].body < 0) continue;
         orc_body* b = &bodies[s->links[l].body];
         if (b->region)
-          b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, nullptr, b->histogram_f,
-                                                  b->histogram_b, b->body2world, iteration, b->first_iteration, corr,
-                                                  rotation_mode, b->lines, &b->region_view);
+          b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, b->region_occlusion_frame,
+                                                  b->histogram_f, b->histogram_b, b->body2world, iteration,
+                                                  b->first_iteration, corr, rotation_mode, b->lines, &b->region_view);
         if (b->depth)
           b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
                                                   b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);

@@ -93,7 +93,8 @@ class Body(C.Structure):
                 ("depth_frame", C.POINTER(DepthFrame)), ("histogram_f", fp), ("histogram_b", fp),
                 ("tikhonov_rotation", C.c_float), ("tikhonov_translation", C.c_float), ("first_iteration", C.c_int32),
                 ("lines", C.POINTER(RegionLine)), ("points", C.POINTER(DepthPoint)), ("n_lines", C.c_int32),
-                ("n_points", C.c_int32), ("region_view", C.c_int32), ("depth_view", C.c_int32)]
+                ("n_points", C.c_int32), ("region_view", C.c_int32), ("depth_view", C.c_int32),
+                ("region_occlusion_frame", C.POINTER(DepthFrame))]
 
 
 class Link(C.Structure):
@@ -211,8 +212,12 @@ def region_params(settings) -> RegionParams:
         return p
     for k in ("n_lines_max", "min_continuous_distance", "function_amplitude", "function_slope", "learning_rate",
               "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
-              "unconsidered_line_length", "max_considered_line_length"):
+              "unconsidered_line_length", "max_considered_line_length", "reference_contour_length",
+              "measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
+              "n_unoccluded_iterations", "min_n_unoccluded_lines"):
         setattr(p, k, getattr(settings, k))
+    p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
+    p.measure_occlusions = int(settings.measure_occlusions)
     p.n_scales = len(settings.scales)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.scales):
@@ -229,6 +234,13 @@ def depth_params(settings) -> DepthParams:
         return p
     p.n_points_max = settings.n_points_max
     p.stride_length = settings.stride_length
+    p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
+    p.reference_surface_area = settings.reference_surface_area
+    p.use_depth_scaling = int(settings.use_depth_scaling)
+    p.measure_occlusions = int(settings.measure_occlusions)
+    for k in ("measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
+              "n_unoccluded_iterations", "min_n_unoccluded_points"):
+        setattr(p, k, getattr(settings, k))
     p.n_considered_distances = len(settings.considered_distances)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.considered_distances):
@@ -329,6 +341,7 @@ class OracleTracker:
         self.bodies = (Body * nb)()
         self.color_frames = (ColorFrame * nb)()
         self.depth_frames = (DepthFrame * nb)()
+        self.occlusion_frames = (DepthFrame * nb)()  # RegionModality::depth_camera_ptr (measure_occlusions)
         nbins = wl.region.n_histogram_bins if wl.region else 1
         self.hist_f = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
         self.hist_b = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
@@ -348,6 +361,14 @@ class OracleTracker:
                 B.histogram_f = ptr(self.hist_f[b])
                 B.histogram_b = ptr(self.hist_b[b])
                 B.lines = self.lines[b].ctypes.data_as(C.POINTER(RegionLine))
+                if wl.region.measure_occlusions and wl.depth_frames is not None:
+                    of = self.occlusion_frames[b]
+                    of.intrinsics = _intr(wl.depth_intrinsics)
+                    of.world2camera[:] = f32(wl.depth_world2camera).reshape(12).tolist()
+                    of.depth = wl.depth_frames[b].ctypes.data
+                    of.pitch = wl.depth_frames[b].strides[0]
+                    of.depth_scale = wl.depth_scale
+                    B.region_occlusion_frame = C.pointer(of)
             if wl.depth:
                 df = self.depth_frames[b]
                 df.intrinsics = _intr(wl.depth_intrinsics)
@@ -415,7 +436,7 @@ class OracleTracker:
     def region_correspondences(self, b, iteration, corr):
         B = self.bodies[b]
         view = C.c_int(0)
-        n = self.L.orc_region_correspondences(B.region, B.region_model, B.color, None, B.histogram_f, B.histogram_b,
+        n = self.L.orc_region_correspondences(B.region, B.region_model, B.color, B.region_occlusion_frame, B.histogram_f, B.histogram_b,
                                               B.body2world, iteration, B.first_iteration, corr, self.rotation_mode,
                                               B.lines, C.byref(view))
         B.n_lines, B.region_view = n, view.value
