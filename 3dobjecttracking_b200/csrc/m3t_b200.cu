@@ -992,6 +992,7 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
     B.has_region = 1;
     B.region_model = region_model;
     B.color_camera = color_camera;
+    if (region->measure_occlusions) B.depth_camera = depth_camera;  // RegionModality::depth_camera_ptr()
     const size_t n3 = size_t(r.n_bins) * r.n_bins * r.n_bins;
     int rc = EnsureHist(ctx, n3);
     if (rc) return rc;
