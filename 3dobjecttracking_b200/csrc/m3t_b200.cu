@@ -10,8 +10,8 @@
 #include <string>
 #include <vector>
 
-#include "m3t_b200_kernels.cuh"
 #include "m3t_b200_structures.cuh"
+#include "m3t_b200_kernels.cuh"
 
 using namespace m3tb;
 
@@ -83,6 +83,8 @@ struct m3tb_ctx {
   bool structures_dirty = false;
   int n_struct_launch = 0;                 // user structures + one implicit structure per unreferenced body
   std::vector<int> struct_first_link;      // per launched structure
+  std::vector<int> h_link_bodies;          // body index of every launched link
+  bool use_clusters = true;                // M3TB_NO_CLUSTER=1: always take the multi-launch structure path
   std::vector<StructureDev> h_structures;
   StructureDev* d_structures = nullptr;
   LinkDev* d_links = nullptr;
@@ -255,8 +257,11 @@ int LaunchIngestIfPending(m3tb_ctx* ctx) {
   return M3TB_OK;
 }
 
+int SyncStructures(m3tb_ctx* ctx);
+
+// cluster > 0: one thread-block cluster of `cluster` CTAs per kinematic structure (PH_CLUSTER_SOLVE)
 int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update, int opt_base,
-                unsigned phases) {
+                unsigned phases, int cluster = 0) {
   int rc = ValidateBodies(ctx);
   if (rc) return rc;
   rc = EnsureState(ctx);
@@ -290,6 +295,12 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   a.phases = phases;
   a.phase_clock = ctx->d_phase_clock;
   a.roi = ctx->d_roi;
+  a.structures = ctx->d_structures;
+  a.links = ctx->d_links;
+  a.constraints = ctx->d_constraints;
+  a.theta_out = ctx->d_theta;
+  a.struct_status = ctx->d_struct_status;
+  a.struct_offset = 0u;
   // thread <-> line mapping: T threads per body, K lines and K points per thread (state in registers)
   const int items = std::max(ctx->line_cap, ctx->point_cap);
   bool lut_smem = true;  // normalised LUT staged in shared memory when every region body has <= 16 bins (32 KB)
@@ -297,8 +308,12 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
     if (ctx->h_bodies[b].has_region && ctx->h_bodies[b].rp.n_bins > 16) lut_smem = false;
   // dynamic shared memory: [normalised LUT 32 KB (16 bins)] [colour bin-index tile] [depth tile]
   const size_t lut_bytes = lut_smem ? size_t(16 * 16 * 16) * sizeof(float2) : 0;
-  const size_t dyn = ctx->use_tiles ? size_t(kDynSmemBytes) : lut_bytes;
-  a.tile_bytes = ctx->use_tiles ? int(dyn - lut_bytes) : 0;
+  // with cluster-fused structures the solver workspace sits at the end of the dynamic shared memory
+  const size_t struct_bytes = cluster > 0 ? Align(ctx->struct_smem, 128) : 0;
+  const size_t dyn = ctx->use_tiles ? size_t(kDynSmemBytes) : lut_bytes + struct_bytes;
+  if (cluster > 0 && dyn < lut_bytes + struct_bytes + 1024) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "structure workspace does not fit");
+  a.tile_bytes = ctx->use_tiles ? int(dyn - lut_bytes - struct_bytes) : 0;
+  a.struct_offset = unsigned(dyn - struct_bytes);
   bool occ = false;  // measured occlusion handling anywhere: the kernel variant that carries the depth-window scans
   for (int b = 0; b < ctx->n_bodies; ++b) {
     const BodyDev& B = ctx->h_bodies[b];
@@ -306,15 +321,34 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   }
 #define M3TB_LAUNCH1(T_, K_, L_, O_)                                                                                   \
   do {                                                                                                                 \
-    CU(cudaFuncSetAttribute(k_track<T_, K_, L_, O_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));          \
-    k_track<T_, K_, L_, O_><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                                               \
+    CU(cudaFuncSetAttribute(k_track<T_, K_, L_, O_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn)));   \
+    k_track<T_, K_, L_, O_, false><<<ctx->n_bodies, T_, dyn, ctx->stream>>>(a);                                        \
   } while (0)
-#define M3TB_LAUNCH(T_, K_)                               \
-  do {                                                    \
-    if (lut_smem && !occ) M3TB_LAUNCH1(T_, K_, true, false);  \
-    else if (lut_smem) M3TB_LAUNCH1(T_, K_, true, true);      \
-    else if (!occ) M3TB_LAUNCH1(T_, K_, false, false);        \
-    else M3TB_LAUNCH1(T_, K_, false, true);                   \
+#define M3TB_LAUNCH_CLUSTER(T_, K_, L_)                                                                                \
+  do {                                                                                                                 \
+    CU(cudaFuncSetAttribute(k_track<T_, K_, L_, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn))); \
+    cudaLaunchConfig_t cfg = {};                                                                                       \
+    cfg.gridDim = dim3(unsigned(ctx->n_bodies));                                                                       \
+    cfg.blockDim = dim3(T_);                                                                                           \
+    cfg.dynamicSmemBytes = dyn;                                                                                        \
+    cfg.stream = ctx->stream;                                                                                          \
+    cudaLaunchAttribute attr;                                                                                          \
+    attr.id = cudaLaunchAttributeClusterDimension;                                                                     \
+    attr.val.clusterDim.x = unsigned(cluster);                                                                         \
+    attr.val.clusterDim.y = 1;                                                                                         \
+    attr.val.clusterDim.z = 1;                                                                                         \
+    cfg.attrs = &attr;                                                                                                 \
+    cfg.numAttrs = 1;                                                                                                  \
+    CU(cudaLaunchKernelEx(&cfg, k_track<T_, K_, L_, false, true>, a));                                                 \
+  } while (0)
+#define M3TB_LAUNCH(T_, K_)                                       \
+  do {                                                            \
+    if (cluster > 0 && lut_smem) M3TB_LAUNCH_CLUSTER(T_, K_, true);   \
+    else if (cluster > 0) M3TB_LAUNCH_CLUSTER(T_, K_, false);         \
+    else if (lut_smem && !occ) M3TB_LAUNCH1(T_, K_, true, false); \
+    else if (lut_smem) M3TB_LAUNCH1(T_, K_, true, true);          \
+    else if (!occ) M3TB_LAUNCH1(T_, K_, false, false);            \
+    else M3TB_LAUNCH1(T_, K_, false, true);                       \
   } while (0)
   if (items <= 256) M3TB_LAUNCH(256, 1);
   else if (items <= 512) M3TB_LAUNCH(512, 1);
@@ -323,6 +357,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   else return Fail(ctx, M3TB_ERR_UNSUPPORTED, "n_lines_max / n_points_max above 2048");
 #undef M3TB_LAUNCH
 #undef M3TB_LAUNCH1
+#undef M3TB_LAUNCH_CLUSTER
   CU(cudaGetLastError());
   ctx->launches++;
   return M3TB_OK;
@@ -440,6 +475,8 @@ int SyncStructures(m3tb_ctx* ctx) {
     CU(cudaMemcpyAsync(ctx->d_constraints, cons.data(), sizeof(ConstraintDev) * cons.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
   ctx->h_structures = sts;
+  ctx->h_link_bodies.resize(links.size());
+  for (size_t k = 0; k < links.size(); ++k) ctx->h_link_bodies[k] = links[k].body;
   ctx->n_struct_launch = ns;
   ctx->struct_smem = smem;
   ctx->structures_dirty = false;
@@ -470,10 +507,41 @@ int LaunchStructure(m3tb_ctx* ctx, int mode, bool from_modalities) {
   return M3TB_OK;
 }
 
+// Can every structure run as one thread-block cluster inside k_track? All structures have the same number of links
+// (2..8, the portable cluster size), every link carries a body, and structure s, link l is body s * n_links + l, so
+// that CTA rank = link index. Anything else takes the general multi-launch path below.
+int ClusterLinks(m3tb_ctx* ctx) {
+  if (!ctx->use_clusters || ctx->n_struct_launch == 0) return 0;
+  const int nl = ctx->h_structures[0].n_links;
+  if (nl < 2 || nl > 8 || ctx->n_struct_launch * nl != ctx->n_bodies) return 0;
+  for (int si = 0; si < ctx->n_struct_launch; ++si) {
+    const StructureDev& d = ctx->h_structures[si];
+    if (d.n_links != nl) return 0;
+    for (int l = 0; l < nl; ++l)
+      if (ctx->h_link_bodies[d.first_link + l] != si * nl + l) return 0;
+  }
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const BodyDev& B = ctx->h_bodies[b];
+    if ((B.has_region && B.rp.measure_occlusions) || (B.has_depth && B.dp.measure_occlusions)) return 0;
+  }
+  return nl;
+}
+
 // Tracker::ExecuteTrackingStep's loop nest (tracker.cpp:344-361) when the optimisers are kinematic structures: the
 // per-body work stays in k_track (correspondences, gradient / Hessian -> gh_link), every
 // Optimizer::CalculateOptimization is one k_structure launch over all structures.
 int StructureStep(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update) {
+  int rc0 = SyncStructures(ctx);
+  if (rc0) return rc0;
+  if (const int nl = ClusterLinks(ctx)) {
+    // fused: the whole corr x update loop nest in ONE launch, one cluster per structure, CalculateOptimization over
+    // distributed shared memory
+    if (n_update > 0)
+      return LaunchTrack(ctx, iteration, corr_begin, corr_end, n_update, 0,
+                         PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_CLUSTER_SOLVE | PH_STORE_REGION |
+                             PH_STORE_DEPTH,
+                         nl);
+  }
   for (int corr = corr_begin; corr < corr_end; ++corr) {
     if (n_update == 0) {
       int rc = LaunchTrack(ctx, iteration, corr, corr + 1, 0, 0, PH_REGION_CORR | PH_DEPTH_CORR | PH_STORE_REGION | PH_STORE_DEPTH);
@@ -792,6 +860,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->private_depth.assign(max_cameras, nullptr);
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_NO_ROI_INGEST")) ctx->roi_ingest = !(e[0] == '1');
+  if (const char* e = std::getenv("M3TB_NO_CLUSTER")) ctx->use_clusters = !(e[0] == '1');
   const char* timing_env = std::getenv("M3TB_TIMING");
   const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {

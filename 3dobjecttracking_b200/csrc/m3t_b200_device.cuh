@@ -35,7 +35,9 @@ enum Phase : unsigned {
   PH_REGION_CORR = 1u, PH_DEPTH_CORR = 2u, PH_REGION_GH = 4u, PH_DEPTH_GH = 8u, PH_SOLVE = 16u,
   PH_LOAD_REGION = 32u, PH_LOAD_DEPTH = 64u, PH_STORE_REGION = 128u, PH_STORE_DEPTH = 256u,
   PH_STORE_GH = 512u, PH_LOAD_GH = 1024u,
-  PH_STORE_LINK_GH = 2048u  // sum over the body's modalities -> gh_link (input of k_structure)
+  PH_STORE_LINK_GH = 2048u,  // sum over the body's modalities -> gh_link (input of k_structure)
+  PH_CLUSTER_SOLVE = 4096u   // one thread-block cluster per kinematic structure: Optimizer::CalculateOptimization
+                             // over distributed shared memory inside k_track (CLUSTER variants only)
 };
 
 struct CameraDev {
@@ -139,6 +141,13 @@ struct TrackArgs {
   int tile_bytes;               // dynamic shared memory available for the colour / depth ROI tiles (0: no tiling)
   RoiRecord* roi;               // [n_bodies][2]: colour, depth
   long long* phase_clock;       // optional [n_bodies][kPhaseSlots] clock64() stamps of thread 0 (profiling aid), or null
+  // cluster-fused kinematic structures (PH_CLUSTER_SOLVE): CTA rank r of cluster c handles link r of structure c
+  const struct StructureDev* structures;
+  struct LinkDev* links;
+  const struct ConstraintDev* constraints;
+  float* theta_out;             // [n_structures][kMaxSystem]
+  int* struct_status;           // [n_structures]
+  unsigned struct_offset;       // byte offset of the solver workspace in dynamic shared memory
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -18,6 +18,9 @@
 
 namespace m3tb {
 
+// index of (i, j), i >= j, in the packed lower triangle
+__host__ __device__ __forceinline__ constexpr int Tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
 constexpr int kMaxLinks = 16;        // links per structure
 constexpr int kMaxStructDof = 96;    // 16 x 6
 constexpr int kMaxSystem = 128;      // DoF + constraint rows
@@ -291,8 +294,9 @@ __device__ inline StructSmem CarveStructSmem(float* base, int nl, int dof, int n
   return s;
 }
 
-// Link::UpdatePoses for every link (optimizer.cpp:334-346, link.cpp:205-241); theta in s.dst
-__device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int nl, float* poses, int tid) {
+// Link::UpdatePoses for every link (optimizer.cpp:334-346, link.cpp:205-241); theta in s.dst. The new link poses are
+// left in s.l2w (the caller publishes the bodies' poses), joint poses go to the links' global records.
+__device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int nl, int tid) {
   // ---- Link::UpdatePoses: pose variations in parallel, then the chain products in pre-order ----
   if (tid < nl) {
     const LinkDev& link = links[tid];
@@ -333,52 +337,22 @@ __device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int
         PoseMul(tmp2, link.body2joint, out);
       }
       for (int k = 0; k < 12; ++k) l2w[k] = out[k];
-      if (link.body >= 0) {
-        for (int k = 0; k < 12; ++k) poses[12 * link.body + k] = out[k];
-      } else {
+      if (link.body < 0)
         for (int k = 0; k < 12; ++k) link.link2world[k] = out[k];
-      }
     }
   }
 }
 
-__global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs args) {
-  extern __shared__ __align__(16) float smem_f[];
-  const StructureDev st = args.structures[blockIdx.x];
-  LinkDev* links = args.links + st.first_link;
-  const ConstraintDev* cons = args.constraints + st.first_constraint;
+// Optimizer::CalculateOptimization for one structure, executed by all T threads of one CTA. In: s.l2w (link poses),
+// s.g / s.H (the links' summed modality gradients / Hessians), the links' joint poses in global memory. Out: s.l2w,
+// joint poses, theta_out[n] (optional). Returns false when the NaN guard (optimizer.cpp:165) skipped the update.
+// Not inlined: it is shared by k_structure and by the cluster-fused variant of k_track, whose register allocation
+// must not be disturbed by this (rarely executed, latency-bound) code.
+__device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev* links, const ConstraintDev* cons,
+                                                 const StructSmem& s, float* theta_out, int tid, int T) {
   const int nl = st.n_links, dof = st.dof, nc = st.n_constraints, n = st.dof + st.n_rows;
-  const int tid = threadIdx.x, T = blockDim.x;
-  StructSmem s = CarveStructSmem(smem_f, nl, dof, n, nc);
   const int lda = s.lda;
-
-  // ---- load link poses and link gradients / Hessians (Link::CalculateGradientAndHessian result) ----
-  for (int e = tid; e < nl * 12; e += T) {
-    const int l = e / 12, k = e - 12 * l;
-    const int body = links[l].body;
-    s.l2w[e] = body >= 0 ? args.poses[12 * body + k] : links[l].link2world[k];
-  }
-  for (int e = tid; e < nl * 42; e += T) {
-    const int l = e / 42, k = e - 42 * l;
-    const int body = links[l].body;
-    float v = 0.0f;
-    if (body >= 0) {
-      int src = k;
-      if (k >= 6) {
-        const int i = (k - 6) / 6, j = (k - 6) - 6 * i;
-        src = 6 + (i >= j ? Tri(i, j) : Tri(j, i));
-      }
-      v = args.gh_link ? args.gh_link[27 * body + src]
-                       : 0.0f + args.gh_region[27 * body + src] + args.gh_depth[27 * body + src];
-    }
-    if (k < 6) s.g[6 * l + k] = v; else s.H[36 * l + k - 6] = v;
-  }
-  if (args.mode == 1) {
-    for (int e = tid; e < n; e += T) s.dst[e] = 0.0f;
-    __syncthreads();
-    UpdatePosesBlock(s, links, nl, args.poses, tid);
-    return;
-  }
+  __syncthreads();
   // ---- Link::CalculateJacobian, part 1: the two adjoints of every link (independent of the parent) ----
   if (tid < nl) {
     const LinkDev& link = links[tid];
@@ -588,11 +562,61 @@ __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs a
   int has_nan = 0;
   for (int i = tid; i < n; i += T) has_nan |= (s.dst[i] != s.dst[i]) ? 1 : 0;
   has_nan = __syncthreads_or(has_nan);
-  if (args.theta_out)
-    for (int i = tid; i < n; i += T) args.theta_out[size_t(blockIdx.x) * kMaxSystem + i] = s.dst[i];
-  if (tid == 0) args.status[blockIdx.x] = has_nan ? 0 : 1;
-  if (has_nan) return;
-  UpdatePosesBlock(s, links, nl, args.poses, tid);
+  if (theta_out)
+    for (int i = tid; i < n; i += T) theta_out[i] = s.dst[i];
+  if (has_nan) return false;
+  UpdatePosesBlock(s, links, nl, tid);
+  __syncthreads();
+  return true;
+}
+
+__global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs args) {
+  extern __shared__ __align__(16) float smem_f[];
+  const StructureDev st = args.structures[blockIdx.x];
+  LinkDev* links = args.links + st.first_link;
+  const ConstraintDev* cons = args.constraints + st.first_constraint;
+  const int nl = st.n_links, dof = st.dof, nc = st.n_constraints, n = st.dof + st.n_rows;
+  const int tid = threadIdx.x, T = blockDim.x;
+  StructSmem s = CarveStructSmem(smem_f, nl, dof, n, nc);
+  const int lda = s.lda;
+
+  // ---- load link poses and link gradients / Hessians (Link::CalculateGradientAndHessian result) ----
+  for (int e = tid; e < nl * 12; e += T) {
+    const int l = e / 12, k = e - 12 * l;
+    const int body = links[l].body;
+    s.l2w[e] = body >= 0 ? args.poses[12 * body + k] : links[l].link2world[k];
+  }
+  for (int e = tid; e < nl * 42; e += T) {
+    const int l = e / 42, k = e - 42 * l;
+    const int body = links[l].body;
+    float v = 0.0f;
+    if (body >= 0) {
+      int src = k;
+      if (k >= 6) {
+        const int i = (k - 6) / 6, j = (k - 6) - 6 * i;
+        src = 6 + (i >= j ? Tri(i, j) : Tri(j, i));
+      }
+      v = args.gh_link ? args.gh_link[27 * body + src]
+                       : 0.0f + args.gh_region[27 * body + src] + args.gh_depth[27 * body + src];
+    }
+    if (k < 6) s.g[6 * l + k] = v; else s.H[36 * l + k - 6] = v;
+  }
+  if (args.mode == 1) {
+    for (int e = tid; e < n; e += T) s.dst[e] = 0.0f;
+    __syncthreads();
+    UpdatePosesBlock(s, links, nl, tid);
+    __syncthreads();
+  } else {
+    const bool updated = StructureSolveBlock(st, links, cons, s, args.theta_out ? args.theta_out + size_t(blockIdx.x) * kMaxSystem : nullptr, tid, T);
+    if (tid == 0) args.status[blockIdx.x] = updated ? 1 : 0;
+    if (!updated) return;
+  }
+  // Body::set_body2world_pose of every link that carries a body
+  for (int e = tid; e < nl * 12; e += T) {
+    const int l = e / 12, k = e - 12 * l;
+    const int body = links[l].body;
+    if (body >= 0) args.poses[12 * body + k] = s.l2w[e];
+  }
 }
 
 }  // namespace m3tb

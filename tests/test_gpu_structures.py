@@ -237,3 +237,33 @@ def test_rigid_bodies_through_structure_path(capi, synth):
     assert dt.max() < 2e-6 and dr.max() < 2e-6, (dt, dr)
     ctx_a.close()
     ctx_b.close()
+
+
+@pytest.mark.parametrize("variant", ["projected", "constrained"])
+def test_cluster_fused_path_equals_multi_launch_path(capi, synth, variant, monkeypatch):
+    """Chains whose links map 1:1 onto the CTAs of a thread-block cluster run the whole corr x update loop nest in ONE
+    k_track launch (Optimizer::CalculateOptimization by the cluster leader over distributed shared memory). Same
+    arithmetic as the general path (k_track + k_structure per update iteration): identical poses, bit for bit."""
+    wl = synth.make_chain_workload(n_chains=5, n_links=8, n_lines=300, n_points=300, n_divides=4, variant=variant, seed=8)
+    ctx_a = capi.context_from_workload(wl)
+    monkeypatch.setenv("M3TB_NO_CLUSTER", "1")
+    ctx_b = capi.context_from_workload(wl)
+    monkeypatch.delenv("M3TB_NO_CLUSTER")
+    for c in (ctx_a, ctx_b):
+        c.start_modalities(0)
+    la, lb = ctx_a.launch_count, ctx_b.launch_count
+    ctx_a.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
+    ctx_b.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
+    assert ctx_a.launch_count - la == 1
+    assert ctx_b.launch_count - lb == wl.n_corr_iterations * 2 * wl.n_update_iterations
+    pa, pb = ctx_a.get_poses(), ctx_b.get_poses()
+    assert np.array_equal(pa.view(np.uint32), pb.view(np.uint32)), np.abs(pa - pb).max()
+    for i in range(5):
+        ja, jb = ctx_a.get_link_poses(i, 8), ctx_b.get_link_poses(i, 8)
+        for x, y in zip(ja, jb):
+            assert np.array_equal(x.view(np.uint32), y.view(np.uint32))
+        ta, ua = ctx_a.get_structure_theta(i)
+        tb, ub = ctx_b.get_structure_theta(i)
+        assert ua and ub and np.array_equal(ta.view(np.uint32), tb.view(np.uint32))
+    ctx_a.close()
+    ctx_b.close()
