@@ -49,7 +49,8 @@ def build_cuda(force=False, verbose=False):
     srcs = [s for s in cuda_sources() if s.endswith(".cu")]
     deps = cuda_sources() + [os.path.join(_ROOT, "include", "m3t_b200.h")]
     if force or _stale(out, deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + ["-I", os.path.join(_ROOT, "include"), "-o", out] + srcs
+        cmd = ([_nvcc()] + NVCC_FLAGS + os.environ.get("M3TB_EXTRA_NVCC_FLAGS", "").split() +
+               ["-I", os.path.join(_ROOT, "include"), "-o", out] + srcs)
         r = subprocess.run(cmd, capture_output=True, text=True)
         log = r.stdout + r.stderr
         with open(os.path.join(d, "build.log"), "w") as f:

@@ -84,7 +84,7 @@ struct m3tb_ctx {
   int n_struct_launch = 0;                 // user structures + one implicit structure per unreferenced body
   std::vector<int> struct_first_link;      // per launched structure
   std::vector<int> h_link_bodies;          // body index of every launched link
-  bool use_clusters = true;                // M3TB_NO_CLUSTER=1: always take the multi-launch structure path
+  bool use_clusters = false;               // M3TB_CLUSTER=1: cluster-fused structure path (measured slower)
   std::vector<StructureDev> h_structures;
   StructureDev* d_structures = nullptr;
   LinkDev* d_links = nullptr;
@@ -310,9 +310,9 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   const size_t lut_bytes = lut_smem ? size_t(16 * 16 * 16) * sizeof(float2) : 0;
   // with cluster-fused structures the solver workspace sits at the end of the dynamic shared memory
   const size_t struct_bytes = cluster > 0 ? Align(ctx->struct_smem, 128) : 0;
-  const size_t dyn = ctx->use_tiles ? size_t(kDynSmemBytes) : lut_bytes + struct_bytes;
-  if (cluster > 0 && dyn < lut_bytes + struct_bytes + 1024) return Fail(ctx, M3TB_ERR_UNSUPPORTED, "structure workspace does not fit");
-  a.tile_bytes = ctx->use_tiles ? int(dyn - lut_bytes - struct_bytes) : 0;
+  const bool tiles = ctx->use_tiles && cluster == 0;
+  const size_t dyn = tiles ? size_t(kDynSmemBytes) : lut_bytes + struct_bytes;
+  a.tile_bytes = tiles ? int(dyn - lut_bytes - struct_bytes) : 0;
   a.struct_offset = unsigned(dyn - struct_bytes);
   bool occ = false;  // measured occlusion handling anywhere: the kernel variant that carries the depth-window scans
   for (int b = 0; b < ctx->n_bodies; ++b) {
@@ -339,18 +339,28 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
     attr.val.clusterDim.z = 1;                                                                                         \
     cfg.attrs = &attr;                                                                                                 \
     cfg.numAttrs = 1;                                                                                                  \
+    if (ctx->d_phase_clock) {                                                                                          \
+      int n_clusters = -1;                                                                                             \
+      cudaOccupancyMaxActiveClusters(&n_clusters, k_track<T_, K_, L_, false, true>, &cfg);                             \
+      std::fprintf(stderr, "m3tb: cluster launch %d x %d CTAs, dyn smem %zu, max active clusters %d\n",                \
+                   ctx->n_bodies / cluster, cluster, size_t(dyn), n_clusters);                                         \
+    }                                                                                                                  \
     CU(cudaLaunchKernelEx(&cfg, k_track<T_, K_, L_, false, true>, a));                                                 \
   } while (0)
 #define M3TB_LAUNCH(T_, K_)                                       \
   do {                                                            \
-    if (cluster > 0 && lut_smem) M3TB_LAUNCH_CLUSTER(T_, K_, true);   \
-    else if (cluster > 0) M3TB_LAUNCH_CLUSTER(T_, K_, false);         \
-    else if (lut_smem && !occ) M3TB_LAUNCH1(T_, K_, true, false); \
+    if (lut_smem && !occ) M3TB_LAUNCH1(T_, K_, true, false);      \
     else if (lut_smem) M3TB_LAUNCH1(T_, K_, true, true);          \
     else if (!occ) M3TB_LAUNCH1(T_, K_, false, false);            \
     else M3TB_LAUNCH1(T_, K_, false, true);                       \
   } while (0)
-  if (items <= 256) M3TB_LAUNCH(256, 1);
+  if (cluster > 0) {
+    // cluster-fused structures: 256-thread CTAs without ROI tiles, so that two CTAs share an SM and every cluster of
+    // a 32-chain shard is resident at once (with 220 KB tiles only 15 clusters of 8 fit on the 148 SMs)
+    if (items <= 256) { if (lut_smem) M3TB_LAUNCH_CLUSTER(256, 1, true); else M3TB_LAUNCH_CLUSTER(256, 1, false); }
+    else if (items <= 512) { if (lut_smem) M3TB_LAUNCH_CLUSTER(256, 2, true); else M3TB_LAUNCH_CLUSTER(256, 2, false); }
+    else return Fail(ctx, M3TB_ERR_UNSUPPORTED, "cluster-fused structures: n_lines_max / n_points_max above 512");
+  } else if (items <= 256) M3TB_LAUNCH(256, 1);
   else if (items <= 512) M3TB_LAUNCH(512, 1);
   else if (items <= 1024) M3TB_LAUNCH(512, 2);
   else if (items <= 2048) M3TB_LAUNCH(512, 4);
@@ -523,6 +533,7 @@ int ClusterLinks(m3tb_ctx* ctx) {
   for (int b = 0; b < ctx->n_bodies; ++b) {
     const BodyDev& B = ctx->h_bodies[b];
     if ((B.has_region && B.rp.measure_occlusions) || (B.has_depth && B.dp.measure_occlusions)) return 0;
+    if ((B.has_region && B.rp.n_lines_max > 512) || (B.has_depth && B.dp.n_points_max > 512)) return 0;
   }
   return nl;
 }
@@ -860,7 +871,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->private_depth.assign(max_cameras, nullptr);
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_NO_ROI_INGEST")) ctx->roi_ingest = !(e[0] == '1');
-  if (const char* e = std::getenv("M3TB_NO_CLUSTER")) ctx->use_clusters = !(e[0] == '1');
+  if (const char* e = std::getenv("M3TB_CLUSTER")) ctx->use_clusters = e[0] == '1';
   const char* timing_env = std::getenv("M3TB_TIMING");
   const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {
@@ -1273,6 +1284,7 @@ int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int
     }
     dof += l.dof;
     l.fixed_body2joint = in.fixed_body2joint_pose ? 1 : 0;
+    l.level = in.parent < 0 ? 0 : h.links[in.parent].level + 1;
     std::memcpy(l.body2joint, in.body2joint, sizeof(l.body2joint));
     std::memcpy(l.joint2parent, in.joint2parent, sizeof(l.joint2parent));
     std::memcpy(l.link2world, in.link2world, sizeof(l.link2world));
@@ -1399,7 +1411,8 @@ int m3tb_get_structure_theta(m3tb_ctx* ctx, int structure, float* theta, int cap
   if (n_out) *n_out = n;
   if (theta) {
     if (capacity < n) return Fail(ctx, M3TB_ERR_INVALID, "theta buffer too small");
-    CU(cudaMemcpyAsync(theta, ctx->d_theta + size_t(structure) * kMaxSystem, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    const int n_copy = capacity >= kMaxSystem ? kMaxSystem : n;  // the tail holds debug stamps in M3TB_STRUCT_STAMPS builds
+    CU(cudaMemcpyAsync(theta, ctx->d_theta + size_t(structure) * kMaxSystem, sizeof(float) * n_copy, cudaMemcpyDeviceToHost, ctx->stream));
   }
   int st = 0;
   CU(cudaMemcpyAsync(&st, ctx->d_struct_status + structure, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -1305,18 +1305,19 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
         cg::cluster_group cluster = cg::this_cluster();
         cluster.sync();
         const int nl = int(cluster.num_blocks());
-        if (cluster.block_rank() == 0) {
+        constexpr int kSolveThreads = T < kStructThreads ? T : kStructThreads;  // the first four warps solve
+        if (cluster.block_rank() == 0 && tid < kSolveThreads) {
           const int sidx = body_id / nl;
           const StructureDev st = args.structures[sidx];
           LinkDev* links = args.links + st.first_link;
           const ConstraintDev* cons = args.constraints + st.first_constraint;
           StructSmem s = CarveStructSmem(reinterpret_cast<float*>(dyn + args.struct_offset), nl, st.dof, st.dof + st.n_rows,
                                          st.n_constraints);
-          for (int e = tid; e < nl * 12; e += T) {
+          for (int e = tid; e < nl * 12; e += kSolveThreads) {
             const int l = e / 12, k = e - 12 * l;
             s.l2w[e] = cluster.map_shared_rank(sh.pose, l)[k];
           }
-          for (int e = tid; e < nl * 42; e += T) {
+          for (int e = tid; e < nl * 42; e += kSolveThreads) {
             const int l = e / 42, k = e - 42 * l;
             int src = k;
             if (k >= 6) {
@@ -1326,10 +1327,10 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
             const float val = cluster.map_shared_rank(sh.link_gh, l)[src];
             if (k < 6) s.g[6 * l + k] = val; else s.H[36 * l + k - 6] = val;
           }
-          const bool updated = StructureSolveBlock(st, links, cons, s, args.theta_out + size_t(sidx) * kMaxSystem, tid, T);
+          const bool updated = StructureSolveBlock(st, links, cons, s, args.theta_out + size_t(sidx) * kMaxSystem, tid, kSolveThreads);
           if (tid == 0) args.struct_status[sidx] = updated ? 1 : 0;
           if (updated)
-            for (int e = tid; e < nl * 12; e += T) {
+            for (int e = tid; e < nl * 12; e += kSolveThreads) {
               const int l = e / 12, k = e - 12 * l;
               cluster.map_shared_rank(sh.pose, l)[k] = s.l2w[e];
             }

@@ -32,7 +32,7 @@ struct LinkDev {
   int first_index, dof;      // first_jacobian_index_, DegreesOfFreedom()
   int free_directions[6];
   int fixed_body2joint;
-  int pad;
+  int level;                 // depth in the tree (root 0)
   float body2joint[12], joint2parent[12];
   float link2world[12];      // links without a body
 };
@@ -294,9 +294,27 @@ __device__ inline StructSmem CarveStructSmem(float* base, int nl, int dof, int n
   return s;
 }
 
+// The solver runs on the first T threads of a CTA (T a multiple of 32): the whole CTA in k_structure, the first four
+// warps of the leader CTA in the cluster-fused k_track. Named barrier 1 keeps it independent of the other warps.
+__device__ __forceinline__ void StructSync(int T) { asm volatile("bar.sync 1, %0;" ::"r"(T) : "memory"); }
+__device__ __forceinline__ int StructSyncOr(int T, int pred) {
+  int out;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.s32 p, %1, 0;\n"
+      "bar.red.or.pred q, 1, %2, p;\n"
+      "selp.s32 %0, 1, 0, q;\n"
+      "}\n"
+      : "=r"(out)
+      : "r"(pred), "r"(T)
+      : "memory");
+  return out;
+}
+
 // Link::UpdatePoses for every link (optimizer.cpp:334-346, link.cpp:205-241); theta in s.dst. The new link poses are
 // left in s.l2w (the caller publishes the bodies' poses), joint poses go to the links' global records.
-__device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int nl, int tid) {
+__device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int nl, int tid, int T) {
   // ---- Link::UpdatePoses: pose variations in parallel, then the chain products in pre-order ----
   if (tid < nl) {
     const LinkDev& link = links[tid];
@@ -310,7 +328,7 @@ __device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int
     var[4] = e[3]; var[5] = e[4]; var[6] = e[5]; var[7] = th[4];
     var[8] = e[6]; var[9] = e[7]; var[10] = e[8]; var[11] = th[5];
   }
-  __syncthreads();
+  StructSync(T);
   if (tid == 0) {
     for (int l = 0; l < nl; ++l) {
       LinkDev& link = links[l];
@@ -343,7 +361,7 @@ __device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int
   }
 }
 
-// Optimizer::CalculateOptimization for one structure, executed by all T threads of one CTA. In: s.l2w (link poses),
+// Optimizer::CalculateOptimization for one structure, executed by the first T threads of one CTA (tid < T). In: s.l2w (link poses),
 // s.g / s.H (the links' summed modality gradients / Hessians), the links' joint poses in global memory. Out: s.l2w,
 // joint poses, theta_out[n] (optional). Returns false when the NaN guard (optimizer.cpp:165) skipped the update.
 // Not inlined: it is shared by k_structure and by the cluster-fused variant of k_track, whose register allocation
@@ -352,7 +370,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
                                                  const StructSmem& s, float* theta_out, int tid, int T) {
   const int nl = st.n_links, dof = st.dof, nc = st.n_constraints, n = st.dof + st.n_rows;
   const int lda = s.lda;
-  __syncthreads();
+  StructSync(T);
   // ---- Link::CalculateJacobian, part 1: the two adjoints of every link (independent of the parent) ----
   if (tid < nl) {
     const LinkDev& link = links[tid];
@@ -367,7 +385,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
   }
   for (int e = tid; e < n * lda; e += T) s.a[e] = 0.0f;
   for (int e = tid; e < n; e += T) s.b[e] = 0.0f;
-  __syncthreads();
+  StructSync(T);
   // part 2: parent Jacobian pushed through the adjoint, then the link's own joint columns (pre-order = list order)
   for (int l = 0; l < nl; ++l) {
     const LinkDev& link = links[l];
@@ -389,7 +407,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
       }
       J[e] = v;
     }
-    __syncthreads();
+    StructSync(T);
   }
   // ---- constraints: one thread each (soft: the two links' terms, hard: residual + unprojected Jacobians) ----
   if (tid < nc) {
@@ -408,7 +426,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
       UnprojectedJacobianDev(jg, c.body12joint1, c.directions, true, true, out + 42);
     }
   }
-  __syncthreads();
+  StructSync(T);
   // SoftConstraint terms are added to the links in constraint order (optimizer.cpp:283-288)
   for (int e = tid; e < nl * 42; e += T) {
     const int l = e / 42, k = e - 42 * l;
@@ -421,7 +439,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
     }
     *dst = v;
   }
-  __syncthreads();
+  StructSync(T);
   // ---- AddProjectedGradientsAndHessians: b += J^T g, a(lower) -= J^T H J, links in pre-order ----
   for (int e = tid; e < dof * (dof + 1) / 2; e += T) {
     int i = int((sqrtf(8.0f * float(e) + 1.0f) - 1.0f) * 0.5f);
@@ -464,7 +482,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
     }
     if (tid < nr) s.b[row0 + tid] = out[tid];
   }
-  __syncthreads();
+  StructSync(T);
   // tikhonov_vector_ on the diagonal of the unknowns
   for (int l = tid; l < nl; l += T) {
     int di = links[l].first_index;
@@ -474,11 +492,11 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
         di++;
       }
   }
-  __syncthreads();
+  StructSync(T);
 
   // ---- Eigen::LDLT<Lower>: the transposition sequence follows from the original diagonal (left-looking) ----
   for (int e = tid; e < n; e += T) s.absdiag[e] = fabsf(s.a[e * lda + e]);
-  __syncthreads();
+  StructSync(T);
   if (tid < 32) {
     for (int k = 0; k < n; ++k) {
       float best = -1.0f;
@@ -501,7 +519,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
       __syncwarp();
     }
   }
-  __syncthreads();
+  StructSync(T);
   bool zero_matrix = false;
   if (n > 1) {
     for (int k = 0; k < n; ++k) {
@@ -511,62 +529,62 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
         for (int i = big + 1 + tid; i < n; i += T) { const float t = s.a[i * lda + k]; s.a[i * lda + k] = s.a[i * lda + big]; s.a[i * lda + big] = t; }
         for (int i = k + 1 + tid; i < big; i += T) { const float t = s.a[i * lda + k]; s.a[i * lda + k] = s.a[big * lda + i]; s.a[big * lda + i] = t; }
         if (tid == 0) { const float t = s.a[k * lda + k]; s.a[k * lda + k] = s.a[big * lda + big]; s.a[big * lda + big] = t; }
-        __syncthreads();
+        StructSync(T);
       }
       if (k > 0) {
         for (int j = tid; j < k; j += T) s.temp[j] = s.a[j * lda + j] * s.a[k * lda + j];
-        __syncthreads();
+        StructSync(T);
         for (int i = k + tid; i < n; i += T) {
           float acc = 0.0f;
           for (int j = 0; j < k; ++j) acc += s.a[i * lda + j] * s.temp[j];
           s.a[i * lda + k] -= acc;
         }
-        __syncthreads();
+        StructSync(T);
       }
       const float akk = s.a[k * lda + k];
       const bool pivot_is_valid = fabsf(akk) > 0.0f;
       if (k == 0 && !pivot_is_valid) { zero_matrix = true; break; }
       if (pivot_is_valid)
         for (int i = k + 1 + tid; i < n; i += T) s.a[i * lda + k] /= akk;
-      __syncthreads();
+      StructSync(T);
     }
   }
   if (zero_matrix || n == 1)
     for (int e = tid; e < n; e += T) s.trans[e] = (zero_matrix || n == 1) ? e : s.trans[e];
-  __syncthreads();
+  StructSync(T);
   // ---- solve: P b, L^-1, D^-1, L^-T, P^T (Eigen LDLT::_solve_impl) ----
   if (tid == 0) {
     for (int k = 0; k < n; ++k) s.dst[k] = s.b[k];
     for (int k = 0; k < n; ++k) { const float t = s.dst[k]; s.dst[k] = s.dst[s.trans[k]]; s.dst[s.trans[k]] = t; }
   }
-  __syncthreads();
+  StructSync(T);
   for (int j = 0; j < n; ++j) {
     const float dj = s.dst[j];
     for (int i = j + 1 + tid; i < n; i += T) s.dst[i] -= s.a[i * lda + j] * dj;
-    __syncthreads();
+    StructSync(T);
   }
   for (int i = tid; i < n; i += T) {
     const float d = s.a[i * lda + i];
     s.dst[i] = fabsf(d) > (1.0f / 3.40282347e+38f) ? s.dst[i] / d : 0.0f;
   }
-  __syncthreads();
+  StructSync(T);
   for (int j = n - 1; j >= 0; --j) {
     const float dj = s.dst[j];
     for (int i = tid; i < j; i += T) s.dst[i] -= s.a[j * lda + i] * dj;
-    __syncthreads();
+    StructSync(T);
   }
   if (tid == 0)
     for (int k = n - 1; k >= 0; --k) { const float t = s.dst[k]; s.dst[k] = s.dst[s.trans[k]]; s.dst[s.trans[k]] = t; }
-  __syncthreads();
+  StructSync(T);
   // theta = dst; NaN guard (optimizer.cpp:165)
   int has_nan = 0;
   for (int i = tid; i < n; i += T) has_nan |= (s.dst[i] != s.dst[i]) ? 1 : 0;
-  has_nan = __syncthreads_or(has_nan);
+  has_nan = StructSyncOr(T, has_nan);
   if (theta_out)
     for (int i = tid; i < n; i += T) theta_out[i] = s.dst[i];
   if (has_nan) return false;
-  UpdatePosesBlock(s, links, nl, tid);
-  __syncthreads();
+  UpdatePosesBlock(s, links, nl, tid, T);
+  StructSync(T);
   return true;
 }
 
@@ -604,7 +622,7 @@ __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs a
   if (args.mode == 1) {
     for (int e = tid; e < n; e += T) s.dst[e] = 0.0f;
     __syncthreads();
-    UpdatePosesBlock(s, links, nl, tid);
+    UpdatePosesBlock(s, links, nl, tid, T);
     __syncthreads();
   } else {
     const bool updated = StructureSolveBlock(st, links, cons, s, args.theta_out ? args.theta_out + size_t(blockIdx.x) * kMaxSystem : nullptr, tid, T);
