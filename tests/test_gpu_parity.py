@@ -246,3 +246,49 @@ def test_pinned_roi_ingest_matches_full_upload(capi, synth, rot_deg, trans_m):
         ctx.close()
     assert np.array_equal(results[0][0].view(np.uint32), results[1][0].view(np.uint32))
     assert np.array_equal(results[0][1], results[1][1]) and np.array_equal(results[0][2], results[1][2])
+
+
+@pytest.mark.parametrize("mode", ["reference_length", "max_length", "depth_scaling"])
+def test_adaptive_coverage_and_depth_scaling_bit_exact(capi, oracle, synth, mode):
+    """use_adaptive_coverage (region_modality.cpp:415-425, depth_modality.cpp:280-287: the number of lines / points
+    follows the contour length / surface area of the closest view, against a reference value or the model's maximum)
+    and use_depth_scaling (depth_modality.cpp:829-830: search radius proportional to the point's depth): per-line /
+    per-point state bit-exact against the oracle, and fewer items than n_max are processed."""
+    import copy
+    wl = copy.deepcopy(synth.make_workload("c2", n_bodies=4, n_divides=3, seed=12))
+    if mode == "reference_length":
+        wl.region.use_adaptive_coverage = True
+        wl.region.reference_contour_length = float(np.median(wl.region_model.view_scalars)) * 1.3
+        wl.depth.use_adaptive_coverage = True
+        wl.depth.reference_surface_area = float(np.median(wl.depth_model.view_scalars)) * 1.3
+    elif mode == "max_length":
+        wl.region.use_adaptive_coverage = True
+        wl.depth.use_adaptive_coverage = True
+    else:
+        wl.depth.use_depth_scaling = True
+        wl.depth.considered_distances = (0.08, 0.04, 0.02)
+    ctx, orc = _setup(capi, oracle, wl, oracle.ROTATION_LINEAR, oracle.EXP_RODRIGUES)
+    orc.start_modalities(0)
+    ctx.start_modalities(0)
+    fewer = 0
+    for corr in (0, 1, 3):
+        ctx.set_poses(orc.get_poses())
+        ctx.region_correspondences(0, corr)
+        ctx.depth_correspondences(0, corr)
+        for b in range(wl.n_bodies):
+            n, _ = orc.region_correspondences(b, 0, corr)
+            lines = ctx.get_region_lines(b, wl.lines_per_body)
+            assert len(lines) == n
+            assert_lines_bit_equal(lines, orc.lines[b][:n])
+            m, _ = orc.depth_correspondences(b, 0, corr)
+            pts = ctx.get_depth_points(b, wl.points_per_body)
+            assert len(pts) == m
+            assert_points_bit_equal(pts, orc.points[b][:m])
+            fewer += int(n < wl.lines_per_body) + int(m < wl.points_per_body)
+        ctx.corr_iteration(0, corr, wl.n_update_iterations)
+        orc.tracking_step(0, n_corr=corr + 1, corr_begin=corr)
+        dt, dr = pose_error(ctx.get_poses(), orc.get_poses())
+        assert dt.max() < TOL_POSE_M and dr.max() < TOL_POSE_RAD, (mode, corr, dt, dr)
+    if mode != "depth_scaling":
+        assert fewer > 0
+    ctx.close()
