@@ -21,7 +21,7 @@ from __future__ import annotations
 import os
 
 # Before anything can load an OpenMP runtime (numpy / torch do): pin the CPU arm's threads to cores. Unbound, a
-# 128-thread team on this host alternates between 2.4 ms and 95 ms per step (measured, scripts_cpu_diag.py); bound it
+# 128-thread team on this host alternates between 2.4 ms and 95 ms per step (measured, scripts/cpu_diag.py); bound it
 # is stable and fastest, which is the honest baseline. stdout carries exactly one JSON line: keep NCCL's banner out.
 os.environ.setdefault("OMP_PROC_BIND", "close")
 os.environ.setdefault("OMP_PLACES", "cores")

@@ -1,5 +1,7 @@
 """Phase clocks of the cluster-fused chain path (M3TB_TIMING=1): per corr iteration views / region / depth, per update
 accumulate / barrier / cluster solve."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import importlib, os, sys
 import numpy as np
 os.environ["M3TB_TIMING"] = "1"

@@ -1,5 +1,7 @@
 """Times one config-5 tracking step (32 chains x 8 links x (300 + 300)) on the cluster-fused path and on the general
-multi-launch path (M3TB_NO_CLUSTER=1), CUDA events, device-resident frames."""
+multi-launch path (default) - M3TB_CLUSTER=1 selects the former, CUDA events, device-resident frames."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import importlib, os, sys
 import numpy as np
 import torch

@@ -1,8 +1,9 @@
 """Prints the per-phase clock budget of one fused launch (M3TB_TIMING=1)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import importlib, os, sys
 import numpy as np
 os.environ["M3TB_TIMING"] = "1"
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 pkg = importlib.import_module("3dobjecttracking_b200")
 capi = importlib.import_module("3dobjecttracking_b200.capi")
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"

@@ -1,4 +1,6 @@
 """Debug: cycle stamps inside StructureSolveBlock (library built with M3TB_EXTRA_NVCC_FLAGS=-DM3TB_STRUCT_STAMPS)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import importlib, os, sys
 import numpy as np
 synth = importlib.import_module("3dobjecttracking_b200.synth")
