@@ -87,7 +87,7 @@ SYMBOLS = [
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
     "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes", "m3tb_set_structure", "m3tb_clear_structures",
     "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
-    "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses",
+    "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses", "m3tb_prefetch_frames",
 ]
 
 _lib = None
@@ -145,6 +145,7 @@ def lib():
     L.m3tb_n_structures.argtypes = [vp]
     L.m3tb_calculate_consistent_poses.argtypes = [vp]
     L.m3tb_reset_joint_poses.argtypes = [vp]
+    L.m3tb_prefetch_frames.argtypes = [vp]
     L.m3tb_get_link_poses.argtypes = [vp, ci, fp, fp, fp]
     L.m3tb_get_structure_theta.argtypes = [vp, ci, fp, ci, C.POINTER(ci), C.POINTER(ci)]
     L.m3tb_set_gradient_hessian.argtypes = [vp, ci, fp, fp]
@@ -280,6 +281,9 @@ class Context:
     def upload_batch_ptr(self, color, first, count, ptr, frame_stride, pitch):
         f = self.L.m3tb_upload_color_batch if color else self.L.m3tb_upload_depth_batch
         self._ck(f(self.h, first, count, C.c_void_p(ptr), frame_stride, pitch))
+
+    def prefetch_frames(self):
+        self._ck(self.L.m3tb_prefetch_frames(self.h))
 
     def set_body(self, body, region, depth, optimizer, region_model=0, depth_model=0, color_camera=0, depth_camera=0):
         self._ck(self.L.m3tb_set_body(self.h, body, C.byref(region) if region is not None else None,

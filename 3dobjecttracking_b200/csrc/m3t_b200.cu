@@ -74,6 +74,16 @@ struct m3tb_ctx {
   RoiRecord* d_roi = nullptr;             // [max_bodies][2]
   unsigned long long* d_ingest_bytes = nullptr;
   bool ingest_pending = false;            // a pinned frame was handed over since the last k_ingest launch
+  // frame prefetch (m3tb_prefetch_frames): second set of image pools / camera tables / ROI records, side stream
+  ImagePool color_pool_alt, depth_pool_alt;
+  CameraDev *d_ccams_alt = nullptr, *d_dcams_alt = nullptr;
+  RoiRecord* d_roi_alt = nullptr;
+  float* d_poses_snap = nullptr;          // poses at the start of the last tracking launch (what the prefetch projects with)
+  cudaStream_t ingest_stream = nullptr;
+  cudaEvent_t ev_ingest_done = nullptr, ev_poses_snap = nullptr;
+  bool prefetch_enabled = false;          // set by the first m3tb_prefetch_frames
+  bool prefetched = false;                // the next consumer launch has to wait for ev_ingest_done
+  bool poses_snap_valid = false;
   bool roi_ingest = true;                 // M3TB_NO_ROI_INGEST=1 forces full-frame copies
   long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
@@ -239,6 +249,10 @@ int ValidateBodies(m3tb_ctx* ctx) {
 
 // Frame ingest for pinned host frames: fetch every body's ROI (k_ingest) before the first consumer of the new frame.
 int LaunchIngestIfPending(m3tb_ctx* ctx) {
+  if (ctx->prefetched) {  // the frames were prefetched on the side stream: order the consumers behind that ingest
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_ingest_done, 0));
+    ctx->prefetched = false;
+  }
   if (!ctx->ingest_pending) return M3TB_OK;
   IngestArgs a;
   a.bodies = ctx->d_bodies;
@@ -270,6 +284,13 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   if (rc) return rc;
   rc = LaunchIngestIfPending(ctx);
   if (rc) return rc;
+  if (ctx->prefetch_enabled && (phases & (PH_REGION_CORR | PH_DEPTH_CORR))) {
+    // what the next prefetch projects the ROIs with: the poses this launch starts from (the side stream must not
+    // read d_poses while this launch writes them)
+    CU(cudaMemcpyAsync(ctx->d_poses_snap, ctx->d_poses, sizeof(float) * 12 * ctx->n_bodies, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(cudaEventRecord(ctx->ev_poses_snap, ctx->stream));
+    ctx->poses_snap_valid = true;
+  }
   TrackArgs a;
   a.bodies = ctx->d_bodies;
   a.poses = ctx->d_poses;
@@ -925,6 +946,11 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
   cudaFree(ctx->d_phase_clock); cudaFree(ctx->d_roi); cudaFree(ctx->d_ingest_bytes);
+  cudaFree(ctx->color_pool_alt.base); cudaFree(ctx->depth_pool_alt.base); cudaFree(ctx->d_ccams_alt);
+  cudaFree(ctx->d_dcams_alt); cudaFree(ctx->d_roi_alt); cudaFree(ctx->d_poses_snap);
+  if (ctx->ingest_stream) { cudaStreamSynchronize(ctx->ingest_stream); cudaStreamDestroy(ctx->ingest_stream); }
+  if (ctx->ev_ingest_done) cudaEventDestroy(ctx->ev_ingest_done);
+  if (ctx->ev_poses_snap) cudaEventDestroy(ctx->ev_poses_snap);
   cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_links_default); cudaFree(ctx->d_constraints);
   cudaFree(ctx->d_gh_link);
   cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
@@ -941,6 +967,7 @@ int m3tb_set_stream(m3tb_ctx* ctx, void* cuda_stream) {
 
 int m3tb_synchronize(m3tb_ctx* ctx) {
   CHECK_CTX();
+  if (ctx->ingest_stream) CU(cudaStreamSynchronize(ctx->ingest_stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return M3TB_OK;
 }
@@ -1477,6 +1504,80 @@ int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int
     }
   }
   if (n_out) *n_out = counts[1];
+  return M3TB_OK;
+}
+
+int m3tb_prefetch_frames(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  if (!ctx->ingest_pending || ctx->n_bodies == 0) return M3TB_OK;
+  // Only when every camera in use has a fresh pinned frame in a pool slot: the whole frame set moves to the other
+  // buffer. Anything else keeps the synchronous ingest at the next consumer launch.
+  for (int k = 0; k < 2; ++k) {
+    const bool color = k == 0;
+    const ImagePool& pool = color ? ctx->color_pool : ctx->depth_pool;
+    for (int i = 0; i < ctx->max_cameras; ++i) {
+      const CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[i];
+      if (!c.set || !c.image) continue;
+      if (!c.host_src || !pool.base || c.image != pool.base + pool.frame_bytes * i) return M3TB_OK;
+    }
+  }
+  if (!ctx->ingest_stream) {
+    CU(cudaStreamCreateWithFlags(&ctx->ingest_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_ingest_done, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_poses_snap, cudaEventDisableTiming));
+    CU(cudaMalloc(&ctx->d_ccams_alt, sizeof(CameraDev) * ctx->max_cameras));
+    CU(cudaMalloc(&ctx->d_dcams_alt, sizeof(CameraDev) * ctx->max_cameras));
+    CU(cudaMalloc(&ctx->d_roi_alt, sizeof(RoiRecord) * 2 * ctx->max_bodies));
+    CU(cudaMemset(ctx->d_roi_alt, 0xff, sizeof(RoiRecord) * 2 * ctx->max_bodies));
+    CU(cudaMalloc(&ctx->d_poses_snap, sizeof(float) * 12 * ctx->max_bodies));
+  }
+  for (int k = 0; k < 2; ++k) {
+    ImagePool& pool = k == 0 ? ctx->color_pool : ctx->depth_pool;
+    ImagePool& alt = k == 0 ? ctx->color_pool_alt : ctx->depth_pool_alt;
+    if (pool.base && !alt.base) {
+      alt = pool;
+      alt.base = nullptr;
+      CU(cudaMalloc(&alt.base, alt.frame_bytes * alt.capacity));
+    }
+    std::swap(pool, alt);
+    std::vector<CameraDev>& cams = k == 0 ? ctx->h_ccams : ctx->h_dcams;
+    for (int i = 0; i < ctx->max_cameras; ++i)
+      if (cams[i].set && cams[i].image) cams[i].image = pool.base + pool.frame_bytes * i;
+  }
+  ctx->cams_dirty = false;   // the camera tables go to the alternate device copies below, on the side stream
+  int rc = SyncTables(ctx);  // bodies / models only (main stream, small)
+  if (rc) return rc;
+  std::swap(ctx->d_ccams, ctx->d_ccams_alt);
+  std::swap(ctx->d_dcams, ctx->d_dcams_alt);
+  std::swap(ctx->d_roi, ctx->d_roi_alt);
+  cudaStream_t is = ctx->ingest_stream;
+  CU(cudaMemcpyAsync(ctx->d_ccams, ctx->h_ccams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, is));
+  CU(cudaMemcpyAsync(ctx->d_dcams, ctx->h_dcams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, is));
+  ctx->cams_dirty = false;
+  const float* poses = ctx->d_poses;
+  if (ctx->poses_snap_valid) {
+    CU(cudaStreamWaitEvent(is, ctx->ev_poses_snap, 0));
+    poses = ctx->d_poses_snap;
+  } else {
+    CU(cudaStreamSynchronize(ctx->stream));  // first frame: nothing in flight that could be writing the poses
+  }
+  IngestArgs a;
+  a.bodies = ctx->d_bodies;
+  a.poses = poses;
+  a.color_cams = ctx->d_ccams;
+  a.depth_cams = ctx->d_dcams;
+  a.region_models = ctx->d_rmodels;
+  a.depth_models = ctx->d_dmodels;
+  a.roi = ctx->d_roi;
+  a.bytes = ctx->d_ingest_bytes;
+  CU(cudaMemsetAsync(ctx->d_ingest_bytes, 0, sizeof(unsigned long long), is));
+  k_ingest<<<ctx->n_bodies, kBlockThreads, 0, is>>>(a);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(ctx->ev_ingest_done, is));
+  ctx->launches++;
+  ctx->ingest_pending = false;
+  ctx->prefetched = true;
+  ctx->prefetch_enabled = true;
   return M3TB_OK;
 }
 

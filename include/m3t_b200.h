@@ -307,6 +307,14 @@ int m3tb_get_depth_points(m3tb_ctx* ctx, int body, m3tb_depth_point* points, int
 /* Index of the closest view chosen by the last *correspondences call (GetClosestView). */
 int m3tb_get_closest_views(m3tb_ctx* ctx, int body, int* region_view, int* depth_view);
 
+/* Optional frame prefetch ("overlap upload of frame t+1 with iterations of frame t"). Call it after the
+ * pinned frames of the NEXT step have been handed over with m3tb_upload_* and while the current step may still be
+ * running: the ROI ingest of those frames runs on a side stream into a second set of device buffers (the ROIs are
+ * projected with the poses the last tracking launch started from), and the next tracking / histogram launch waits for
+ * it. Results do not change (pixels outside a ROI are read from the pinned frame). It only takes effect when every
+ * camera in use got a new pinned frame; otherwise, and for pageable frames, nothing happens and the frames are
+ * ingested at the next launch as usual. The frames must stay unchanged until that next launch has completed. */
+int m3tb_prefetch_frames(m3tb_ctx* ctx);
 /* Bytes the last frame ingest (pinned-frame ROI fetch) moved host -> device; 0 if frames were copied in full. */
 int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes);
 

@@ -292,3 +292,40 @@ def test_adaptive_coverage_and_depth_scaling_bit_exact(capi, oracle, synth, mode
     if mode != "depth_scaling":
         assert fewer > 0
     ctx.close()
+
+
+def test_frame_prefetch_matches_synchronous_ingest(capi, synth):
+    """m3tb_prefetch_frames: frames handed over one step ahead and ingested on a side stream into the alternate buffers
+    while the previous step is tracking; three consecutive frames (different images per step) give bit-identical
+    poses to the synchronous path."""
+    import torch
+    wls = [synth.make_workload("c2", n_bodies=6, n_divides=3, seed=20 + k) for k in range(3)]
+    wl = wls[0]
+    hc = [torch.from_numpy(w.color_frames).pin_memory() for w in wls]
+    hd = [torch.from_numpy(w.depth_frames.view(np.uint8).reshape(w.n_bodies, w.depth_frames.shape[1], -1)).pin_memory() for w in wls]
+
+    def hand_over(ctx, k, prefetch):
+        ctx.upload_batch_ptr(True, 0, wl.n_bodies, hc[k].data_ptr(), hc[k].stride(0), hc[k].stride(1))
+        ctx.upload_batch_ptr(False, 0, wl.n_bodies, hd[k].data_ptr(), hd[k].stride(0), hd[k].stride(1))
+        if prefetch:
+            ctx.prefetch_frames()
+
+    out = []
+    for prefetch in (False, True):
+        ctx = capi.context_from_workload(wl, upload_frames=False)
+        hand_over(ctx, 0, prefetch)
+        ctx.start_modalities(0)
+        poses = []
+        for k in range(3):
+            ctx.set_poses(wls[k].start_body2world)
+            ctx.tracking_step(k, wl.n_corr_iterations, wl.n_update_iterations)
+            ctx.calculate_results(k)
+            if k < 2:
+                hand_over(ctx, k + 1, prefetch)      # while step k may still be running
+            poses.append(ctx.get_poses())
+        assert ctx.last_ingest_bytes() > 0
+        out.append(np.stack(poses))
+        ctx.close()
+    assert np.array_equal(out[0].view(np.uint32), out[1].view(np.uint32))
+    # and the frames really differed from step to step
+    assert np.abs(out[0][0] - out[0][1]).max() > 1e-3
