@@ -21,7 +21,7 @@ from __future__ import annotations
 import os
 
 # Before anything can load an OpenMP runtime (numpy / torch do): pin the CPU arm's threads to cores. Unbound, a
-# 128-thread team on this host alternates between 2.4 ms and 95 ms per step (measured, scripts/cpu_diag.py); bound it
+# 128-thread team on this host alternates between 2.4 ms and 95 ms per step (measured, tests/diag/cpu_arm_threads.py); bound it
 # is stable and fastest, which is the honest baseline. stdout carries exactly one JSON line: keep NCCL's banner out.
 os.environ.setdefault("OMP_PROC_BIND", "close")
 os.environ.setdefault("OMP_PLACES", "cores")
@@ -333,6 +333,9 @@ def run_b200(args):
         d2h = nb * 48
         out_poses = torch.empty((nb, 12), dtype=torch.float32).pin_memory()
         gathered = None
+        if world > 1:  # persistent buffers of the per-frame pose all-gather
+            poses_dev = torch.empty((nb, 12), dtype=torch.float32, device=dev)
+            gathered = torch.empty((world * nb, 12), dtype=torch.float32, device=dev)
 
         def hand_over_frames():
             # Camera::UpdateImage for every camera (pinned frames: pointers only) + the optional prefetch: the ROI
@@ -346,14 +349,14 @@ def run_b200(args):
         def e2e_step():
             # software pipeline, one frame deep: step t tracks the frames handed over during step t-1; the frames of
             # step t+1 are handed over (and start crossing PCIe) right after step t has been launched
-            nonlocal gathered
             ctx.set_poses(poses_np)
             ctx.reset_joint_poses()
             step()
             hand_over_frames()
             ctx._ck(ctx.L.m3tb_get_poses(ctx.h, 0, nb, capi._p(out_poses.numpy())))  # synchronises the stream
-            if world > 1:  # publish: NCCL all-gather of the solved poses, once per frame
-                gathered = pkg.sharding.all_gather_poses(out_poses.to(dev, non_blocking=True).reshape(nb, 3, 4))
+            if world > 1:  # publish: NCCL all-gather of the solved poses, once per frame, not waited for by the next step
+                poses_dev.copy_(out_poses, non_blocking=True)
+                dist.all_gather_into_tensor(gathered, poses_dev)
 
         hand_over_frames()  # frame 0
         for _ in range(max(args.warmup, 3)):

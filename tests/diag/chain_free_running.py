@@ -1,10 +1,11 @@
 """Diagnostic: free-running divergence GPU vs oracle on config-5 chains, per correspondence iteration."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 import importlib, sys, os
 import numpy as np
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_py as oracle
 from helpers import pose_error
 synth = importlib.import_module("3dobjecttracking_b200.synth")

@@ -195,7 +195,7 @@ def test_chain_pose_parity_per_iteration(capi, oracle, synth, variant, soft):
 def test_chain_tracking_free_running(capi, oracle, synth):
     """Whole cycle free-running on both sides. With RTB's weak regularisation (lambda 100 / 1000) and 19 x 9 px lines
     the chain iteration is strongly expanding in its first steps (the oracle's own rotation error triples before it
-    collapses, scripts/chain_diag.py), so a 1e-7 difference in summation order grows to ~1e-5 m / 2e-3 rad within
+    collapses, tests/diag/chain_free_running.py), so a 1e-7 difference in summation order grows to ~1e-5 m / 2e-3 rad within
     the first frame and further in the next one: the gate for parity is the per-iteration test above; here the
     first frame must stay within a loose band and both sides must converge towards the ground truth."""
     wl = synth.make_chain_workload(n_chains=4, n_links=8, n_lines=300, n_points=300, n_divides=4, seed=6)
