@@ -14,6 +14,7 @@ NVCC_FLAGS = [
     # validity) bit-identical to the reference restatement (DESIGN.md "Numerics").
     "-fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
     "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v",
+    "-t", "0",  # the translation units (k_track variant groups) compile in parallel
 ]
 
 

@@ -13,6 +13,15 @@
 #include "m3t_b200_structures.cuh"
 #include "m3t_b200_kernels.cuh"
 
+#include "m3t_b200_track_variants.h"
+
+namespace m3tb {
+// the fused kernel's variants are compiled in m3t_b200_track_<g>.cu
+#define M3TB_DECLARE(T_, K_, L_, O_, C_) extern template __global__ void k_track<T_, K_, L_, O_, C_>(const __grid_constant__ TrackArgs);
+M3TB_TRACK_ALL(M3TB_DECLARE)
+#undef M3TB_DECLARE
+}  // namespace m3tb
+
 using namespace m3tb;
 
 namespace {

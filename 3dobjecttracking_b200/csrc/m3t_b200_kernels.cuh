@@ -254,7 +254,7 @@ struct LineState {  // RegionModality::DataLine (region_modality.h:150-165), the
 // The strided window scan shared by RegionModality::IsLineUnoccludedMeasured (region_modality.cpp:1355-1388) and
 // DepthModality::IsPointUnoccludedMeasured (depth_modality.cpp:739-775). ushort(x) of the reference is restated as
 // truncation to int and reduction modulo 2^16 (identical to the oracle).
-__device__ __noinline__ bool WindowUnoccluded(const Tile& t, const uint16_t* tile, const FrameView& f, int w_m1, int h_m1,
+static __device__ __noinline__ bool WindowUnoccluded(const Tile& t, const uint16_t* tile, const FrameView& f, int w_m1, int h_m1,
                                               float center_u, float center_v, float diameter, float min_depth_value) {
   const int stride = int(diameter / float(kMaxNOcclusionStrides) + 1.0f);
   const int n_strides = int(diameter / float(stride) + 0.5f);
@@ -572,7 +572,7 @@ struct PointState {  // DepthModality::DataPoint (depth_modality.h:139-150)
   bool valid;
 };
 
-__device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int u_max, int v_min, int v_max, int stride,
+static __device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_min, int u_max, int v_min, int v_max, int stride,
                                              float min_depth_value, float max_depth_value, float x, float y, float z,
                                              const FrameView& frame, const Tile& tile, const uint16_t* tile_px, float* r) {
   float best = r[0], bx = r[1], by = r[2], bz = r[3];
@@ -1400,6 +1400,7 @@ __device__ __forceinline__ float2 NormaliseBin(float pf, float pb) {
   return make_float2(0.5f, 0.5f);
 }
 
+#ifndef M3TB_TRACK_TU  // the auxiliary kernels are compiled once, in m3t_b200.cu
 __global__ void k_lut(const float* hist_f, const float* hist_b, float2* lut, int n, size_t stride, int first_body) {
   const int body = first_body + blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1697,5 +1698,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     lut[k] = NormaliseBin(hf, hb);
   }
 }
+
+#endif  // M3TB_TRACK_TU
 
 }  // namespace m3tb

@@ -366,7 +366,7 @@ __device__ inline void UpdatePosesBlock(const StructSmem& s, LinkDev* links, int
 // joint poses, theta_out[n] (optional). Returns false when the NaN guard (optimizer.cpp:165) skipped the update.
 // Not inlined: it is shared by k_structure and by the cluster-fused variant of k_track, whose register allocation
 // must not be disturbed by this (rarely executed, latency-bound) code.
-__device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev* links, const ConstraintDev* cons,
+static __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev* links, const ConstraintDev* cons,
                                                  const StructSmem& s, float* theta_out, int tid, int T) {
   const int nl = st.n_links, dof = st.dof, nc = st.n_constraints, n = st.dof + st.n_rows;
   const int lda = s.lda;
@@ -588,6 +588,7 @@ __device__ __noinline__ bool StructureSolveBlock(const StructureDev& st, LinkDev
   return true;
 }
 
+#ifndef M3TB_TRACK_TU
 __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs args) {
   extern __shared__ __align__(16) float smem_f[];
   const StructureDev st = args.structures[blockIdx.x];
@@ -636,5 +637,7 @@ __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs a
     if (body >= 0) args.poses[12 * body + k] = s.l2w[e];
   }
 }
+
+#endif  // M3TB_TRACK_TU
 
 }  // namespace m3tb
