@@ -104,6 +104,8 @@ class ClockSampler:
         self.lines = []
 
     def start(self):
+        if self.idx is None:
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
@@ -286,7 +288,9 @@ def run_b200(args):
     def step():
         ctx.tracking_step(0, n_corr, n_upd)
 
-    sampler = ClockSampler(local_rank)
+    # one sampler for the job (rank 0's GPU): a polling nvidia-smi per rank makes the ranks queue on the driver's
+    # locks - at 8 ranks that stalled the host-side calls of the end-to-end loop to 33 ms per step
+    sampler = ClockSampler(local_rank if rank == 0 else None)
     sampler.start()
 
     # ---------------- value: device-resident frames, CUDA events per step, L2 flushed between steps --------
