@@ -19,12 +19,17 @@ e2e   : the same through the C ABI with HOST buffers: per step the pinned-host -
 from __future__ import annotations
 
 import os
+import sys
 
 # Before anything can load an OpenMP runtime (numpy / torch do): pin the CPU arm's threads to cores. Unbound, a
 # 128-thread team on this host alternates between 2.4 ms and 95 ms per step (measured, tests/diag/cpu_arm_threads.py); bound it
-# is stable and fastest, which is the honest baseline. stdout carries exactly one JSON line: keep NCCL's banner out.
-os.environ.setdefault("OMP_PROC_BIND", "close")
-os.environ.setdefault("OMP_PLACES", "cores")
+# is stable and fastest, which is the honest baseline. ONLY in processes that run the CPU arm (single-process runs and
+# --impl reference): OMP_PROC_BIND also pins the initial thread to the first place, so under torchrun every rank's host
+# thread would land on the same core - at 4 and 8 ranks that made every other end-to-end step wait ~19 ms for a
+# time slice (scripts/e2e_scaling_diag.py). stdout carries exactly one JSON line: keep NCCL's banner out.
+if int(os.environ.get("WORLD_SIZE", "1")) == 1 or "reference" in sys.argv:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+    os.environ.setdefault("OMP_PLACES", "cores")
 if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
     os.environ["NCCL_DEBUG"] = "WARN"
 
@@ -32,7 +37,6 @@ import argparse  # noqa: E402
 import importlib  # noqa: E402
 import json  # noqa: E402
 import subprocess  # noqa: E402
-import sys  # noqa: E402
 import threading  # noqa: E402
 import time  # noqa: E402
 
@@ -290,7 +294,7 @@ def run_b200(args):
 
     # one sampler for the job (rank 0's GPU): a polling nvidia-smi per rank makes the ranks queue on the driver's
     # locks - at 8 ranks that stalled the host-side calls of the end-to-end loop to 33 ms per step
-    sampler = ClockSampler(local_rank if rank == 0 else None)
+    sampler = ClockSampler(local_rank if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None)
     sampler.start()
 
     # ---------------- value: device-resident frames, CUDA events per step, L2 flushed between steps --------
@@ -368,9 +372,14 @@ def run_b200(args):
         torch.cuda.synchronize(dev)
         barrier()
         t0 = time.perf_counter()
+        step_ms = []
         for _ in range(args.steps):
+            ts = time.perf_counter()
             e2e_step()
+            step_ms.append(1e3 * (time.perf_counter() - ts))
         ctx.synchronize()  # includes the side stream: K steps tracked, K frame sets ingested inside the timed region
+        if os.environ.get("BENCH_DEBUG_E2E"):
+            print(f"[e2e debug] rank {rank}: per-step ms " + " ".join(f"{v:.2f}" for v in step_ms), file=sys.stderr, flush=True)
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
         barrier()
