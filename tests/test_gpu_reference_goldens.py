@@ -77,3 +77,62 @@ def test_cuda_path_reproduces_reference_optimizer_golden(capi, synth):
     assert np.abs(pose[:3] - golden[:3]).max() < 1e-5
     assert np.abs(pose[:3, :3] - golden[:3, :3]).max() < 1e-6
     ctx.close()
+
+
+@pytest.mark.parametrize("scenario", ["tracker", "refiner"])
+def test_cuda_path_replays_tracker_and_refiner_known_answers(capi, synth, oracle, scenario):
+    """TrackerTest / RefinerTest.OptimizePoseMatrix through the C ABI (m3tb_start_modalities, m3tb_tracking_step /
+    m3tb_corr_iteration) on the regenerated views of triangle_tracker_views.npz: the CUDA path follows the oracle's
+    replay (tight) and therefore lands as close to the reference's stored pose as the oracle does (soft, see
+    test_reference_goldens.py)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import reference_rig as rr
+    from replay import ReferenceReplay
+    z = np.load(os.path.join(GOLDEN, "triangle_tracker_views.npz"))
+    views = {k: {int(i): (z[f"{k}_points"][n], float(z[f"{k}_scalars"][n])) for n, i in enumerate(z[f"{k}_ids"])}
+             for k in ("region", "depth")}
+    rep = ReferenceReplay(oracle, views)
+    assert rep.run(scenario) == []
+    rig, ka = rep.rig, rep.ka
+    nv = z["orientations"].shape[0]
+
+    def model(kind, fl):
+        pts = np.zeros((nv, 200, fl), np.float32)
+        scal = np.zeros(nv, np.float32)
+        for vid, (p, s) in views[kind].items():
+            pts[vid], scal[vid] = p, s
+        return SimpleNamespace(n_views=nv, n_points=200, orientations=np.ascontiguousarray((-rr.geodesic_points()).astype(np.float32)),
+                               view_scalars=scal, points=pts, stride_depth_offset=0.002, max_radius_depth_offset=0.05)
+
+    ctx = capi.Context(0, 1, 1, 1)
+    ctx.set_region_model(0, model("region", 38))
+    ctx.set_depth_model(0, model("depth", 36))
+    cc, dc = ka["color_camera"], ka["depth_camera"]
+    ctx.set_color_camera(0, synth.Intrinsics(cc["fu"], cc["fv"], cc["ppu"], cc["ppv"], cc["width"], cc["height"]), rig["color_w2c"][:3])
+    ctx.set_depth_camera(0, synth.Intrinsics(dc["fu"], dc["fv"], dc["ppu"], dc["ppv"], dc["width"], dc["height"]), rig["depth_w2c"][:3],
+                         dc["depth_scale"])
+    ctx.upload_color(0, rig["color"].reshape(540, -1))
+    ctx.upload_depth(0, rig["depth"])
+    rp, dp = capi.region_params(), capi.depth_params()
+    rp.measure_occlusions = 1   # MeasureOcclusions(): inactive at iteration 0 (n_unoccluded_iterations = 10)
+    dp.measure_occlusions = 1
+    ctx.set_body(0, rp, dp, capi.OptimizerParams(1000.0, 30000.0), 0, 0, 0, 0)
+    ctx.set_poses(rig["body2world"][:3].astype(np.float32))
+    if scenario == "tracker":
+        ctx.start_modalities(0)
+        ctx.tracking_step(0, 7, 2)
+        ctx.calculate_results(0)
+    else:
+        for corr in range(7):
+            ctx.start_modalities(0)
+            ctx.corr_iteration(0, corr, 3)
+    pose = np.eye(4)
+    pose[:3] = ctx.get_poses()[0]
+    ours_cpu = rep.pose().astype(np.float64)
+    dt = np.linalg.norm(pose[:3, 3] - ours_cpu[:3, 3])
+    dr = np.abs(pose[:3, :3] - ours_cpu[:3, :3]).max()
+    assert dt < 1e-4 and dr < 1e-3, (scenario, dt, dr)     # free-running over 14-21 updates on a real image pair
+    golden = T._mat(ka, f"{scenario}_triangle_pose")
+    assert np.linalg.norm(pose[:3, 3] - golden[:3, 3]) < (8e-4 if scenario == "tracker" else 1.3e-3)
+    ctx.close()

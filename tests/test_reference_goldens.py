@@ -199,3 +199,38 @@ def test_optimizer_pose_after_one_gauss_newton_step(ref, oracle):
     err = np.abs(ours[:3] - golden[:3]).max()
     assert moved > 3e-3 and err < 1e-5, (moved, err)      # a 4 mm step reproduced to 8 um ...
     assert np.abs(ours[:3, :3] - golden[:3, :3]).max() < 1e-6  # ... rotation to the 6 stored digits
+
+
+@pytest.mark.parametrize("scenario", ["tracker", "refiner"])
+def test_tracker_and_refiner_pose_known_answers(oracle, scenario):
+    """TrackerTest.OptimizePoseMatrix (StartModalities + ExecuteTrackingStep: 7 x 2 iterations, tracker_test.cpp:164-179)
+    and RefinerTest.OptimizePoseMatrix (7 x (StartModalities, correspondences, 3 updates), refiner.cpp:99-118) replayed on
+    the oracle with the template views regenerated on demand (tests/golden/make_tracker_views.py ->
+    triangle_tracker_views.npz: the 4 + 4 views the loop visits). SOFT check: the loop corrects the pose by ~1 cm / 3 deg
+    and lands within 0.55 mm / 0.21 deg (tracker) resp. 0.93 mm / 0.3 deg (refiner) of the stored pose, i.e. 5-10 % of
+    the correction. Bit-level agreement
+    is not attainable here: the visited views other than the first are resampled from a software raster (+-1 px), the
+    path selects views by arg-max near Voronoi boundaries, and the stored poses predate the current update convention
+    (see the optimizer test above)."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    from replay import ReferenceReplay
+    z = np.load(os.path.join(GOLDEN, "triangle_tracker_views.npz"))
+    views = {k: {int(i): (z[f"{k}_points"][n], float(z[f"{k}_scalars"][n])) for n, i in enumerate(z[f"{k}_ids"])}
+             for k in ("region", "depth")}
+    rep = ReferenceReplay(oracle, views)
+    start = rep.pose().astype(np.float64)
+    assert rep.run(scenario) == []          # every view the loop asked for is in the fixture
+    ours = rep.pose().astype(np.float64)
+    golden = _mat(rep.ka, f"{scenario}_triangle_pose")
+
+    def dist(a, b):
+        R = a[:3, :3] @ b[:3, :3].T
+        return np.linalg.norm(a[:3, 3] - b[:3, 3]), np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))
+
+    moved_t, moved_r = dist(golden, start)
+    err_t, err_r = dist(ours, golden)
+    assert moved_t > 8e-3 and moved_r > 0.03, (moved_t, moved_r)
+    tol_t, tol_r = (7e-4, 4.5e-3) if scenario == "tracker" else (1.2e-3, 6e-3)
+    assert err_t < tol_t and err_r < tol_r, (scenario, err_t, err_r, moved_t, moved_r)
+    assert err_t < 0.12 * moved_t and err_r < 0.15 * moved_r
