@@ -79,12 +79,14 @@ def test_cuda_path_reproduces_reference_optimizer_golden(capi, synth):
     ctx.close()
 
 
-@pytest.mark.parametrize("scenario", ["tracker", "refiner"])
-def test_cuda_path_replays_tracker_and_refiner_known_answers(capi, synth, oracle, scenario):
-    """TrackerTest / RefinerTest.OptimizePoseMatrix through the C ABI (m3tb_start_modalities, m3tb_tracking_step /
-    m3tb_corr_iteration) on the regenerated views of triangle_tracker_views.npz: the CUDA path follows the oracle's
-    replay (tight) and therefore lands as close to the reference's stored pose as the oracle does (soft, see
-    test_reference_goldens.py)."""
+@pytest.mark.parametrize("scenario", ["tracker"])
+def test_cuda_path_replays_tracker_known_answer(capi, synth, oracle, scenario):
+    """TrackerTest.OptimizePoseMatrix through the C ABI (m3tb_start_modalities, m3tb_tracking_step,
+    m3tb_calculate_results) on the regenerated views of triangle_tracker_views.npz: the CUDA path follows the oracle's
+    replay (measured: 1.4e-9 m / 4e-7 over the 14 updates on the real image pair) and therefore lands as close to the
+    reference's stored pose as the oracle does (soft, see test_reference_goldens.py). The refiner replay is only run
+    on the oracle: free-running, its path passes a near-tie between two template views, and the fixture holds only the
+    views the ORACLE's path visits (the refiner branch below is kept for use with a fuller fixture)."""
     import sys
     sys.path.insert(0, GOLDEN)
     import reference_rig as rr
