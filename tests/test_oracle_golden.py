@@ -124,3 +124,16 @@ def test_function_lookup_and_min_expected_variance(oracle):
     L.orc_function_lookup(C.byref(rp), oracle.ptr(lf), oracle.ptr(lb), C.byref(mev))
     assert np.allclose(lf, [0.86] * 4 + [0.14] * 4, atol=1e-6)
     assert abs(mev.value - 1.0 / (2.0 * np.arctanh(0.72) ** 2)) < 1e-5
+
+
+def test_oracle_is_frozen(oracle):
+    """The oracle checks every GPU parity test; its own outputs on small seeded workloads (rigid, chains with projected /
+    constrained / soft joints, measured occlusion) are frozen in tests/golden/oracle_regression.npz
+    (tests/golden/make_oracle_regression.py) so that an edit cannot shift them unnoticed."""
+    import sys
+    sys.path.insert(0, GOLDEN)
+    import make_oracle_regression as m
+    ref = np.load(os.path.join(GOLDEN, "oracle_regression.npz"))
+    for name, wl in m.cases():
+        poses = m.run(oracle, wl)
+        assert np.allclose(poses, ref[name], atol=2e-6), (name, np.abs(poses - ref[name]).max())
