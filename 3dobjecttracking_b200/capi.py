@@ -87,19 +87,29 @@ SYMBOLS = [
     "m3tb_calculate_optimization", "m3tb_get_region_lines", "m3tb_get_depth_points", "m3tb_get_closest_views",
     "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes", "m3tb_set_structure", "m3tb_clear_structures",
     "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
-    "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses", "m3tb_prefetch_frames",
+    "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses", "m3tb_prefetch_frames", "m3tb_detach_frames",
+    "m3tb_debug_closest_view",
 ]
 
 _lib = None
 
 
 def lib():
-    """Loads libm3t_b200.so (building it in-tree with nvcc if the sources are newer). Raises if that fails."""
+    """Loads libm3t_b200.so; builds it in-tree with nvcc when it is missing. When the sources are newer than the
+    library it is rebuilt only with M3TB_AUTO_REBUILD=1 (never under torchrun: ranks would race) - otherwise a
+    warning is printed, because a stale binary silently running is worse than a loud one. Raises if loading fails."""
     global _lib
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
         _build.build_cuda()
+    elif _build._stale(LIB_PATH, _build.cuda_sources()):
+        if os.environ.get("M3TB_AUTO_REBUILD") == "1" and int(os.environ.get("WORLD_SIZE", "1")) == 1:
+            _build.build_cuda()
+        else:
+            import sys
+            print("3dobjecttracking_b200.capi: WARNING libm3t_b200.so is older than its sources "
+                  "(python __graft_entry__.py rebuilds it)", file=sys.stderr)
     L = C.CDLL(LIB_PATH)
     vp, ci = C.c_void_p, C.c_int
     L.m3tb_region_params_default.argtypes = [C.POINTER(RegionParams)]
@@ -146,6 +156,9 @@ def lib():
     L.m3tb_calculate_consistent_poses.argtypes = [vp]
     L.m3tb_reset_joint_poses.argtypes = [vp]
     L.m3tb_prefetch_frames.argtypes = [vp]
+    L.m3tb_detach_frames.argtypes = [vp]
+    ip = C.POINTER(C.c_int)
+    L.m3tb_debug_closest_view.argtypes = [fp, ci, fp, ci, ip, ip, ip, ip]
     L.m3tb_get_link_poses.argtypes = [vp, ci, fp, fp, fp]
     L.m3tb_get_structure_theta.argtypes = [vp, ci, fp, ci, C.POINTER(ci), C.POINTER(ci)]
     L.m3tb_set_gradient_hessian.argtypes = [vp, ci, fp, fp]
@@ -284,6 +297,9 @@ class Context:
 
     def prefetch_frames(self):
         self._ck(self.L.m3tb_prefetch_frames(self.h))
+
+    def detach_frames(self):
+        self._ck(self.L.m3tb_detach_frames(self.h))
 
     def set_body(self, body, region, depth, optimizer, region_model=0, depth_model=0, color_camera=0, depth_camera=0):
         self._ck(self.L.m3tb_set_body(self.h, body, C.byref(region) if region is not None else None,
@@ -434,6 +450,21 @@ class Context:
         a, b = C.c_int(0), C.c_int(0)
         self._ck(self.L.m3tb_get_closest_views(self.h, body, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+
+def debug_closest_view(orientations, queries, prev=None):
+    """(scan, pruned, n_evaluated) of m3tb_debug_closest_view: host-only check of the pruned GetClosestView."""
+    ori = _f32(orientations).reshape(-1, 3)
+    q = _f32(queries).reshape(-1, 3)
+    n = q.shape[0]
+    pv = np.ascontiguousarray(prev if prev is not None else np.zeros(n), np.int32)
+    out = [np.zeros(n, np.int32) for _ in range(3)]
+    ip = C.POINTER(C.c_int)
+    rc = lib().m3tb_debug_closest_view(_p(ori), ori.shape[0], _p(q), n, pv.ctypes.data_as(ip),
+                                       *[o.ctypes.data_as(ip) for o in out])
+    if rc != 0:
+        raise M3TBError(f"m3tb_debug_closest_view: status {rc}")
+    return tuple(out)
 
 
 def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=True, first=0, count=None) -> Context:

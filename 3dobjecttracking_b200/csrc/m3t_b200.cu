@@ -12,6 +12,7 @@
 
 #include "m3t_b200_structures.cuh"
 #include "m3t_b200_kernels.cuh"
+#include "m3t_b200_views.cuh"
 
 #include "m3t_b200_track_variants.h"
 
@@ -46,6 +47,8 @@ struct ModelAlloc {
   float* view_scalars = nullptr;
   float4* points = nullptr;
   float* depth_offsets = nullptr;
+  float4* cluster_info = nullptr;
+  float4* sorted_views = nullptr;
 };
 
 }  // namespace
@@ -196,12 +199,15 @@ int EnsureState(m3tb_ctx* ctx) {
     if (ctx->d_rstate) cudaFree(ctx->d_rstate);
     CU(cudaMalloc(&ctx->d_rstate, size_t(ctx->max_bodies) * RF_COUNT * lc * sizeof(float)));
     CU(cudaMemsetAsync(ctx->d_rstate, 0, size_t(ctx->max_bodies) * RF_COUNT * lc * sizeof(float), ctx->stream));
+    // the stored correspondences are gone: a load-state call before the next CalculateCorrespondences sees 0 lines
+    if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, sizeof(int) * 4 * ctx->max_bodies, ctx->stream));
     ctx->line_cap = lc;
   }
   if (pc > ctx->point_cap || !ctx->d_dstate) {
     if (ctx->d_dstate) cudaFree(ctx->d_dstate);
     CU(cudaMalloc(&ctx->d_dstate, size_t(ctx->max_bodies) * DF_COUNT * pc * sizeof(float)));
     CU(cudaMemsetAsync(ctx->d_dstate, 0, size_t(ctx->max_bodies) * DF_COUNT * pc * sizeof(float), ctx->stream));
+    if (ctx->d_counts) CU(cudaMemsetAsync(ctx->d_counts, 0, sizeof(int) * 4 * ctx->max_bodies, ctx->stream));
     ctx->point_cap = pc;
   }
   return M3TB_OK;
@@ -643,6 +649,7 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   ModelAlloc& al = allocs[model_id];
   if (al.orientations) {
     cudaFree(al.orientations); cudaFree(al.view_scalars); cudaFree(al.points); cudaFree(al.depth_offsets);
+    cudaFree(al.cluster_info); cudaFree(al.sorted_views);
     al = ModelAlloc();
   }
   // Repack the .bin AoS DataPoints (152 B / 144 B) into the 32 B records the kernels read:
@@ -683,6 +690,13 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   CU(cudaMemcpyAsync(al.orientations, ori4.data(), sizeof(float4) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.view_scalars, sc.data(), sizeof(float) * n_views, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(al.points, packed.data(), sizeof(float) * packed.size(), cudaMemcpyHostToDevice, ctx->stream));
+  // cluster tables of the pruned closest-view search (one-time, host)
+  ViewClustersHost vc;
+  BuildViewClusters(orientations, n_views, vc);
+  CU(cudaMalloc(&al.cluster_info, sizeof(float) * std::max<size_t>(vc.info.size(), 8)));
+  CU(cudaMalloc(&al.sorted_views, sizeof(float) * vc.sorted.size()));
+  CU(cudaMemcpyAsync(al.cluster_info, vc.info.data(), sizeof(float) * vc.info.size(), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(al.sorted_views, vc.sorted.data(), sizeof(float) * vc.sorted.size(), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));  // staging vectors go out of scope
   ModelDev& m = (region ? ctx->h_rmodels : ctx->h_dmodels)[model_id];
   m.n_views = n_views;
@@ -695,6 +709,9 @@ int SetModel(m3tb_ctx* ctx, bool region, int model_id, int n_views, int n_points
   m.depth_offsets = al.depth_offsets;
   m.stride_depth_offset = stride_depth_offset;
   m.max_radius_depth_offset = max_radius_depth_offset;
+  m.cluster_info = al.cluster_info;
+  m.sorted_views = al.sorted_views;
+  m.n_clusters = vc.n_clusters;
   m.set = 1;
   ctx->models_dirty = true;
   return M3TB_OK;
@@ -946,7 +963,10 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   for (auto* al : {&ctx->rmodel_alloc, &ctx->dmodel_alloc})
-    for (auto& a : *al) { cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); cudaFree(a.depth_offsets); }
+    for (auto& a : *al) {
+      cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); cudaFree(a.depth_offsets);
+      cudaFree(a.cluster_info); cudaFree(a.sorted_views);
+    }
   for (auto p : ctx->private_color) cudaFree(p);
   for (auto p : ctx->private_depth) cudaFree(p);
   cudaFree(ctx->color_pool.base); cudaFree(ctx->depth_pool.base);
@@ -1590,6 +1610,32 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
   return M3TB_OK;
 }
 
+int m3tb_detach_frames(m3tb_ctx* ctx) {
+  CHECK_CTX();
+  if (ctx->ingest_stream) CU(cudaStreamSynchronize(ctx->ingest_stream));  // a prefetch may still be reading the frames
+  bool any = false;
+  for (int k = 0; k < 2; ++k) {
+    std::vector<CameraDev>& cams = k == 0 ? ctx->h_ccams : ctx->h_dcams;
+    for (CameraDev& c : cams) {
+      if (!c.set || !c.image || !c.host_src) continue;
+      const size_t row = size_t(c.width) * (k == 0 ? 3 : 2);
+      CU(cudaMemcpy2DAsync(const_cast<uint8_t*>(c.image), c.pitch, c.host_src, c.host_pitch, row, c.height,
+                           cudaMemcpyHostToDevice, ctx->stream));
+      c.host_src = nullptr;  // FrameView: the whole device copy is valid from now on
+      c.host_pitch = 0;
+      any = true;
+    }
+  }
+  if (any) {
+    ctx->cams_dirty = true;
+    ctx->ingest_pending = false;  // nothing left to fetch by rectangle
+    int rc = SyncTables(ctx);
+    if (rc) return rc;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
 int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes) {
   CHECK_CTX();
   if (!bytes) return Fail(ctx, M3TB_ERR_INVALID, "null output");
@@ -1606,6 +1652,28 @@ int m3tb_debug_phase_clocks(m3tb_ctx* ctx, int body, long long* out, int capacit
   CU(cudaMemcpyAsync(out, ctx->d_phase_clock + size_t(body) * kPhaseSlots, sizeof(long long) * n, cudaMemcpyDeviceToHost,
                      ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return M3TB_OK;
+}
+
+int m3tb_debug_closest_view(const float* orientations, int n_views, const float* queries, int n_queries,
+                            const int* prev, int* out_scan, int* out_pruned, int* out_evaluated) {
+  if (!orientations || n_views <= 0 || !queries || n_queries < 0 || !out_scan || !out_pruned) return M3TB_ERR_INVALID;
+  ViewClustersHost vc;
+  BuildViewClusters(orientations, n_views, vc);
+  for (int q = 0; q < n_queries; ++q) {
+    const float* o = queries + 3 * q;
+    // the reference's scan (region_model.cpp:121-128): closest_dot = -1, strict >, views_[0] otherwise
+    float best = -1.0f;
+    int idx = 0;
+    for (int v = 0; v < n_views; ++v) {
+      const float dot = o[0] * orientations[3 * v] + o[1] * orientations[3 * v + 1] + o[2] * orientations[3 * v + 2];
+      if (dot > best) { best = dot; idx = v; }
+    }
+    out_scan[q] = idx;
+    int ev = 0;
+    out_pruned[q] = ClosestViewPrunedHost(vc, orientations, n_views, o, prev ? prev[q] : 0, &ev);
+    if (out_evaluated) out_evaluated[q] = ev;
+  }
   return M3TB_OK;
 }
 

@@ -76,6 +76,10 @@ struct ModelDev {
   int set;
   const float* depth_offsets; // [n_views][n_points][30]: DataPoint::depth_offsets (measured occlusion handling)
   float stride_depth_offset, max_radius_depth_offset;  // Model::stride_depth_offset / max_radius_depth_offset
+  // pruned GetClosestView (m3t_b200_views.cuh): cluster bounds [n_clusters][2] and the views in cluster order
+  const float4* cluster_info;
+  const float4* sorted_views;
+  int n_clusters;
 };
 
 struct RegionParamsDev {

@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true")
     return ap.parse_args()
 
 
@@ -79,6 +80,73 @@ def workload_description(wl, args, per_gpu=None):
     return (f"{preset}: {per_gpu or wl.n_bodies} bodies/GPU x ({both}), one 640x480 "
             f"{'RGB-D pair' if wl.depth and wl.region else 'frame'} per body, "
             f"{wl.n_corr_iterations} corr x {wl.n_update_iterations} update iterations")
+
+
+def config_dict(wl, args, world, per_gpu):
+    """The `config` both arms print (identical dicts, so that the driver's same_config check reads true)."""
+    frame_mib = 0.0
+    if wl.color_frames is not None:
+        frame_mib += wl.color_frames[0].nbytes * per_gpu / 2 ** 20
+    if wl.depth_frames is not None:
+        frame_mib += wl.depth_frames[0].nbytes * per_gpu / 2 ** 20
+    return {"workload": workload_description(wl, args, per_gpu=per_gpu), "bodies_per_gpu": int(per_gpu),
+            "l2": f"flushed (256 MiB memset) between timed steps; each step's frames are {frame_mib:.0f} MiB/GPU (> L2)",
+            "timing": "GPU arm: CUDA events around each step on the launching stream, summed over K steps, max over ranks; "
+                      "CPU arm: steady_clock around each full step",
+            "parallelism": f"bodies sharded x{world}, no data-path collective"}
+
+
+def source_sha():
+    """sha256 over the CUDA sources: ties profiles/traffic.json (an ncu capture) to the kernel it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "3dobjecttracking_b200", "csrc")
+    for f in sorted(os.listdir(d)):
+        if f.endswith((".cu", ".cuh", ".h")):
+            h.update(open(os.path.join(d, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def parity_check(ctx, wl, n_sample=4):
+    """What was just timed, checked: the first n_sample bodies of the benchmarked batch against the CPU oracle
+    (reference-faithful mode: polar rotation(), Pade exp). (i) per correspondence iteration on identical inputs (both
+    sides enter every iteration with the oracle's pose) - the north_star gate of 1e-4 m / 1e-4 rad; (ii) the fused
+    whole-step launch free-running from the start poses. The oracle is the checker here, never the thing measured."""
+    if getattr(wl, "structures", None):
+        return {"skipped": "kinematic structures: covered by tests/test_gpu_structures.py"}
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py
+    n = min(n_sample, wl.n_bodies)
+    orc = oracle_py.OracleTracker(wl, rotation_mode=oracle_py.ROTATION_POLAR, exp_mode=oracle_py.EXP_PADE, n_threads=n)
+    orc.start_modalities(0)
+
+    def err(p, q):
+        p, q = np.asarray(p, np.float64).reshape(-1, 3, 4), np.asarray(q, np.float64).reshape(-1, 3, 4)
+        dt = np.linalg.norm(p[:, :, 3] - q[:, :, 3], axis=1)
+        R = np.einsum("bij,bkj->bik", p[:, :, :3], q[:, :, :3])
+        c = np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0)
+        sk = 0.5 * np.sqrt((R[:, 2, 1] - R[:, 1, 2]) ** 2 + (R[:, 0, 2] - R[:, 2, 0]) ** 2 + (R[:, 1, 0] - R[:, 0, 1]) ** 2)
+        return dt, np.arctan2(sk, c)
+
+    worst_m = worst_rad = 0.0
+    orc.set_poses(wl.start_body2world)
+    for corr in range(wl.n_corr_iterations):
+        ctx.set_poses(orc.get_poses())
+        ctx.corr_iteration(0, corr, wl.n_update_iterations)
+        orc.tracking_step(0, n_corr=corr + 1, corr_begin=corr, first=0, count=n)
+        dt, dr = err(ctx.get_poses(0, n), orc.get_poses()[:n])
+        worst_m, worst_rad = max(worst_m, float(dt.max())), max(worst_rad, float(dr.max()))
+    ctx.set_poses(wl.start_body2world)
+    ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
+    orc.set_poses(wl.start_body2world)
+    orc.tracking_step(0, first=0, count=n)
+    dt, dr = err(ctx.get_poses(0, n), orc.get_poses()[:n])
+    moved, _ = err(ctx.get_poses(0, n), wl.start_body2world[:n])
+    return {"bodies": int(n), "oracle": "CPU restatement, reference-faithful mode (polar rotation, Pade exp)",
+            "per_iteration_max_m": worst_m, "per_iteration_max_rad": worst_rad, "tolerance": 1e-4,
+            "ok": bool(worst_m < 1e-4 and worst_rad < 1e-4),
+            "free_running_step_max_m": float(dt.max()), "free_running_step_max_rad": float(dr.max()),
+            "pose_change_of_the_step_m": float(moved.min())}
 
 
 def build_workload(args, rank, n_shards=1):
@@ -246,8 +314,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_description(wl, args, per_gpu=wl.n_bodies // args.gpus),
-                   "note": f"CPU arm: the whole {args.gpus}-GPU job ({wl.n_bodies} bodies) on this host's cores, OpenMP over bodies"},
+        "config": config_dict(wl, args, args.gpus, wl.n_bodies // args.gpus),
+        "arm_note": f"CPU arm: the whole {args.gpus}-GPU job ({wl.n_bodies} bodies) on this host's cores, OpenMP over bodies",
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": sample,
                          "best_step_value": r["best_step_value"],
                          "phase_split_cpu_seconds": r["phase_split_cpu_seconds"]},
@@ -412,30 +480,38 @@ def run_b200(args):
         kernel_s = ms_per_step * 1e-3  # rigid bodies: one k_track launch per step, the events bracket exactly that launch
         # (kinematic structures: k_track + k_structure per update iteration; the roofline is then quoted on the whole step)
         achieved = total_b / kernel_s / 1e9
-        traffic = None
+        # DRAM traffic needs hardware counters (ncu); the capture is tied to the kernel sources it was taken from, so a
+        # number measured on an older kernel is reported as null instead of silently going stale
+        traffic, traffic_note = None, "no ncu capture on record for this workload"
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload if not args.bodies else f"{args.workload}-{args.bodies}")
+                tj = json.load(f)
+            key = args.workload if not args.bodies else f"{args.workload}-{args.bodies}"
+            if key in tj:
+                if tj.get("source_sha") == source_sha():
+                    traffic, traffic_note = tj[key], tj.get("note", "")
+                else:
+                    traffic_note = (f"stale: profiles/traffic.json was captured from sources {tj.get('source_sha')}, "
+                                    f"this build is {source_sha()} (last captured value {tj[key]:.4g} B/launch)")
         except Exception:
             pass
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_description(wl, args), "bodies_per_gpu": nb,
-                       "l2": "flushed (256 MiB memset) between timed steps; each step's frames are 189 MiB/GPU (> L2)",
-                       "timing": "CUDA events around each step on the launching stream, summed over K steps, max over ranks",
-                       "parallelism": f"bodies sharded x{world}, no data-path collective"},
+            "config": config_dict(wl, args, world, nb),
             "line_evals_per_s": world * line_evals / kernel_s,
             "depth_point_evals_per_s": world * point_evals / kernel_s,
             "roofline": {"bound": "hbm", "kernel": "k_track", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": total_b, "region_bytes": region_b, "depth_bytes": depth_b,
                          "launch_ms": ms_per_step},
             "clocks": clocks, "gpu_launches": int(launches),
         }
         if e2e:
             out["e2e"] = e2e
+        if not args.no_parity_check:
+            out["parity_check"] = parity_check(ctx, wl)
         if world == 1 and not args.no_cpu_baseline:
             n_cpu_steps = max(3, min(50, int(0.5 / max(1e-4, ms_per_step * 1e-3 * 20))))  # ~0.5 s of sustained CPU work
             r = cpu_reference_run(args, wl, steps=n_cpu_steps, warmup=1)

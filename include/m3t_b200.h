@@ -204,10 +204,16 @@ int m3tb_set_depth_camera(m3tb_ctx* ctx, int cam, const m3tb_intrinsics* intrins
  *    fetches, straight from the pinned frame over PCIe, only the rectangle each body can touch in this cycle
  *    (projected bounding sphere + longest correspondence line / widest depth window + motion margin); pixels
  *    outside it remain readable through the same zero-copy alias, so results never depend on the rectangle.
- *    The frame must stay unchanged until that work has completed (m3tb_synchronize / m3tb_get_poses), as for any
- *    asynchronous copy from pinned memory. */
+ *    LIFETIME (differs from Camera::UpdateImage, which copies): the camera keeps referring to the pinned frame.
+ *    Every later launch on that camera - the tracking step, m3tb_calculate_results, a re-run on the same frame, any
+ *    sample outside the fetched rectangle - may read it, so the frame must stay valid and unchanged until the NEXT
+ *    upload to that camera has replaced it, or until m3tb_detach_frames() has returned. */
 int m3tb_upload_color(m3tb_ctx* ctx, int cam, const uint8_t* bgr, size_t pitch);
 int m3tb_upload_depth(m3tb_ctx* ctx, int cam, const uint16_t* depth, size_t pitch);
+/* Gives the pinned frames back to the caller: every camera that still refers to a pinned host frame gets the whole
+ * frame copied into its device copy (on the context's stream, synchronised before returning) and forgets the host
+ * pointer. Afterwards the host buffers may be reused or freed; results of later calls are unchanged. */
+int m3tb_detach_frames(m3tb_ctx* ctx);
 /* Same, for frames that already live in device memory (device-resident pipelines, bench `value`). */
 int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch);
 int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch);
@@ -322,6 +328,13 @@ int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes);
  * boundaries of the last fused launch. Only available when the context was created with M3TB_TIMING=1 in the
  * environment. */
 int m3tb_debug_phase_clocks(m3tb_ctx* ctx, int body, long long* out, int capacity);
+
+/* Test aid (host only, no context, no GPU): RegionModel/DepthModel::GetClosestView (region_model.cpp:105-130) for
+ * `n_queries` orientation vectors (R^T normalize(t), 3 floats each) over `n_views` view orientations, once by the
+ * reference's full scan (`out_scan`) and once by the host restatement of the pruned search the kernels use
+ * (`out_pruned`, started from view `prev[q]`; `out_evaluated[q]` = views it looked at). The two must be equal. */
+int m3tb_debug_closest_view(const float* orientations, int n_views, const float* queries, int n_queries,
+                            const int* prev, int* out_scan, int* out_pruned, int* out_evaluated);
 
 #ifdef __cplusplus
 }
