@@ -15,8 +15,13 @@
 #include "m3t_b200_views.cuh"
 
 #include "m3t_b200_track_variants.h"
+#include "m3t_b200_track2.cuh"
 
 namespace m3tb {
+extern template __global__ void k_track2<512, true>(const __grid_constant__ TrackArgs);
+extern template __global__ void k_track2<512, false>(const __grid_constant__ TrackArgs);
+extern template __global__ void k_track2<1024, true>(const __grid_constant__ TrackArgs);
+extern template __global__ void k_track2<1024, false>(const __grid_constant__ TrackArgs);
 // the fused kernel's variants are compiled in m3t_b200_track_<g>.cu
 #define M3TB_DECLARE(T_, K_, L_, O_, C_) extern template __global__ void k_track<T_, K_, L_, O_, C_>(const __grid_constant__ TrackArgs);
 M3TB_TRACK_ALL(M3TB_DECLARE)
@@ -99,6 +104,7 @@ struct m3tb_ctx {
   bool roi_ingest = true;                 // M3TB_NO_ROI_INGEST=1 forces full-frame copies
   long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
+  bool use_track2 = true; // second-generation fused kernel where it applies (M3TB_KERNEL=1 forces k_track)
 
   // kinematic structures (empty: every body is its own rigid-body optimiser inside k_track)
   std::vector<StructureHost> structures;
@@ -354,6 +360,45 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   for (int b = 0; b < ctx->n_bodies; ++b) {
     const BodyDev& B = ctx->h_bodies[b];
     occ = occ || (B.has_region && B.rp.measure_occlusions) || (B.has_depth && B.dp.measure_occlusions);
+  }
+  // ---- k_track2: rigid bodies, <= 512 items per modality, no measured occlusion handling, correspondence / fused phases,
+  //      one function lookup for the whole batch (m3t_b200_track2.cuh) --------------------------------------------------
+  {
+    const unsigned k2_phases = PH_REGION_CORR | PH_DEPTH_CORR | PH_REGION_GH | PH_DEPTH_GH | PH_SOLVE | PH_STORE_REGION |
+                               PH_STORE_DEPTH;
+    bool ok = ctx->use_track2 && cluster == 0 && !occ && items <= kGroup && (phases & ~k2_phases) == 0 &&
+              (n_update == 0 || (phases & PH_SOLVE));
+    bool both = false, have_lookup = false;
+    for (int b = 0; b < ctx->n_bodies && ok; ++b) {
+      const BodyDev& B = ctx->h_bodies[b];
+      both = both || (B.has_region && B.has_depth);
+      if (!B.has_region) continue;
+      if (!have_lookup) {
+        std::memcpy(a.lookup_f, B.rp.lookup_f, sizeof(a.lookup_f));
+        std::memcpy(a.lookup_b, B.rp.lookup_b, sizeof(a.lookup_b));
+        have_lookup = true;
+      } else if (std::memcmp(a.lookup_f, B.rp.lookup_f, sizeof(a.lookup_f)) != 0 ||
+                 std::memcmp(a.lookup_b, B.rp.lookup_b, sizeof(a.lookup_b)) != 0) {
+        ok = false;
+      }
+    }
+    if (!have_lookup) { std::memset(a.lookup_f, 0, sizeof(a.lookup_f)); std::memset(a.lookup_b, 0, sizeof(a.lookup_b)); }
+    if (ok) {
+      const size_t fixed = lut_bytes + size_t(kDistBytes);
+      const size_t dyn2 = ctx->use_tiles ? size_t(kDynSmemBytes) : fixed;
+      a.tile_bytes = ctx->use_tiles ? int(dyn2 - fixed) : 0;
+#define M3TB_LAUNCH2(T_, L_)                                                                                     \
+  do {                                                                                                           \
+    CU(cudaFuncSetAttribute(k_track2<T_, L_>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(dyn2)));          \
+    k_track2<T_, L_><<<ctx->n_bodies, T_, dyn2, ctx->stream>>>(a);                                               \
+  } while (0)
+      if (both) { if (lut_smem) M3TB_LAUNCH2(1024, true); else M3TB_LAUNCH2(1024, false); }
+      else { if (lut_smem) M3TB_LAUNCH2(512, true); else M3TB_LAUNCH2(512, false); }
+#undef M3TB_LAUNCH2
+      CU(cudaGetLastError());
+      ctx->launches++;
+      return M3TB_OK;
+    }
   }
 #define M3TB_LAUNCH1(T_, K_, L_, O_)                                                                                   \
   do {                                                                                                                 \
@@ -919,6 +964,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_NO_ROI_INGEST")) ctx->roi_ingest = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_CLUSTER")) ctx->use_clusters = e[0] == '1';
+  if (const char* e = std::getenv("M3TB_KERNEL")) ctx->use_track2 = !(e[0] == '1');
   const char* timing_env = std::getenv("M3TB_TIMING");
   const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {

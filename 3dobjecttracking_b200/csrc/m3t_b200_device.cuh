@@ -152,6 +152,9 @@ struct TrackArgs {
   float* theta_out;             // [n_structures][kMaxSystem]
   int* struct_status;           // [n_structures]
   unsigned struct_offset;       // byte offset of the solver workspace in dynamic shared memory
+  // k_track2: RegionModality::PrecalculateFunctionLookup tables, identical for every region body of the launch
+  // (checked by the host), so that they are kernel-parameter constants instead of per-thread registers
+  float lookup_f[kFunctionLength], lookup_b[kFunctionLength];
 };
 
 // ---------------------------------------------------------------------------------------------

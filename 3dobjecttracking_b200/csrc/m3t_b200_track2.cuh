@@ -11,8 +11,9 @@
 //     (region_modality.cpp:1600-1637) needs to finish one distribution entry per new segment, in the reference's
 //     multiplication order, for lines walked in either direction. The 12 entries go to shared memory (24 KB); the
 //     local-mode gradient reads its two entries from there by index.
-//   * GetClosestView is the exact pruned search of m3t_b200_views.cuh, done redundantly by every warp (no barrier,
-//     ~200 instead of 2 x 2562 dot products per iteration).
+//   * GetClosestView is the exact pruned search of m3t_b200_views.cuh (~200 instead of 2 x 2562 dot products per
+//     iteration), done by the first warp of each group while the other warps wait at the group's named barrier
+//     (measured: every warp searching redundantly costs 6.4 k cycles of issue slots, one warp ~1.3 k).
 //   * CalculateOptimization (6 x 6) runs thread-serially in registers on warp 0 (every lane the same work, no
 //     shuffles in the dependent chain): pivot order from the original diagonal, gather of the permuted matrix,
 //     unrolled left-looking LDL^T, substitutions, Rodrigues, pose products; ~4x shorter than the lane-parallel form.
@@ -40,7 +41,15 @@ struct Shared2 {
   unsigned long long depth_bar, lut_bar;
   float red[32][32];         // per-warp partial sums g[6] + H lower[21] (+5 pad)
   float a[36], b[6], x[6];   // normal equations
+  int views[2][2];           // [corr parity][region | depth] closest views, published by the group leaders
 };
+
+// barrier of one warp group (512 threads) when the CTA has two; id 1 = lines, id 2 = points
+template <int T>
+__device__ __forceinline__ void GroupBarrier(int group) {
+  if (T == kGroup) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(kGroup) : "memory");
+}
 
 struct LineRegs {  // RegionModality::DataLine without the distribution (shared memory)
   float cbx, cby, cbz, cu, cv, nu, nv, dr, ncts, mean, var;
@@ -63,7 +72,7 @@ struct LineRegs {  // RegionModality::DataLine without the distribution (shared 
 template <bool LUT_SMEM, int S>
 __device__ __forceinline__ void WalkFast(int scale, int base, float minor_f, float step, int stride_major, int stride_minor,
                                          const uint16_t* tile_px, const float2* __restrict__ lut_g, const float2* lut_s,
-                                         const float (&lf)[kFunctionLength], const float (&lb)[kFunctionLength], bool rev,
+                                         const float* __restrict__ lf, const float* __restrict__ lb, bool rev,
                                          float* dist_col) {
   float wf[8], wb[8];
 #pragma unroll
@@ -157,7 +166,7 @@ template <bool LUT_SMEM>
 __device__ __forceinline__ void RegionLine2(const RegionIter& it, const RegionParamsDev& rp, const float4 p0, const float4 p1,
                                             const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
                                             const float2* __restrict__ lut_g, const float2* lut_s,
-                                            const float (&lf)[kFunctionLength], const float (&lb)[kFunctionLength],
+                                            const float* __restrict__ lf, const float* __restrict__ lb,
                                             float* dist_col, LineRegs& L) {
   L.valid = false;
   // CalculateBasicLineData (:1231-1250)
@@ -596,16 +605,25 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   int view_r = counts[2], view_d = counts[3];  // any valid view index: the lower bound of the pruned search
   bool lut_ready = !need_lut;
   // function lookups (identical for every body of the launch, checked by the host): kernel-parameter constants
-  float lf[kFunctionLength], lb[kFunctionLength];
-#pragma unroll
-  for (int k = 0; k < kFunctionLength; ++k) { lf[k] = args.lookup_f[k]; lb[k] = args.lookup_b[k]; }
+  const float* lf = args.lookup_f;
+  const float* lb = args.lookup_b;
   M3TB_STAMP2(stamp_base);  // prologue done
 
   for (int corr = args.corr_begin; corr < args.corr_end; ++corr) {
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr && line_group) {
-      view_r = ClosestViewPrunedWarp(rmodel->cluster_info, rmodel->sorted_views, rmodel->n_clusters, rmodel->orientations4,
-                                     rmodel->n_views, sh.view_o[0], view_r);
+      if ((tid & (kGroup - 1)) < 32) {  // group leader warp
+        const int v = ClosestViewPrunedWarp(rmodel->cluster_info, rmodel->sorted_views, rmodel->n_clusters,
+                                            rmodel->orientations4, rmodel->n_views, sh.view_o[0], view_r);
+        if (lane == 0) sh.views[corr & 1][0] = v;
+      }
+      if (T == kGroup && do_dcorr && warp == 1) {  // single group: the second warp searches the depth model meanwhile
+        const int v = ClosestViewPrunedWarp(dmodel->cluster_info, dmodel->sorted_views, dmodel->n_clusters,
+                                            dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
+        if (lane == 0) sh.views[corr & 1][1] = v;
+      }
+      GroupBarrier<T>(0);
+      view_r = sh.views[corr & 1][0];
       M3TB_STAMP2(stamp_base);  // closest view (region)
       RegionIter rit;
       MakeRegionIter(body.rp, *ccam, sh.rb2c, corr, rit);
@@ -622,8 +640,15 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       M3TB_STAMP2(stamp_base);  // region lines
     }
     if (do_dcorr && point_group) {
-      view_d = ClosestViewPrunedWarp(dmodel->cluster_info, dmodel->sorted_views, dmodel->n_clusters, dmodel->orientations4,
-                                     dmodel->n_views, sh.view_o[1], view_d);
+      if (T > kGroup || !do_rcorr) {  // (single group with lines: searched above, behind the same barrier)
+        if ((tid & (kGroup - 1)) < 32) {
+          const int v = ClosestViewPrunedWarp(dmodel->cluster_info, dmodel->sorted_views, dmodel->n_clusters,
+                                              dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
+          if (lane == 0) sh.views[corr & 1][1] = v;
+        }
+        GroupBarrier<T>(1);
+      }
+      view_d = sh.views[corr & 1][1];
       M3TB_STAMP2(stamp_base);  // closest view (depth)
       DepthIter dit;
       MakeDepthIter(body.dp, *dcam, sh.db2c, sh.dc2b, corr, dit);
@@ -699,6 +724,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
         M3TB_STAMP2(stamp_base);  // solve + pose update + pose products
       }
       __syncthreads();
+      M3TB_STAMP2(stamp_base);  // released
     }
   }
 

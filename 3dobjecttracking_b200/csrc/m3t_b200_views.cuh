@@ -179,8 +179,8 @@ inline int ClosestViewPrunedHost(const ViewClustersHost& vc, const float* ori, i
 // Device search, executed by ONE WARP (all 32 lanes call it with identical arguments; every lane returns the result).
 //   info / sorted / n_clusters: the cluster tables of the model; ori4: the model's views in original order (for the
 //   lower bound); vo: query (o0, o1, o2, nonzero flag) as the pose-product step leaves it; prev: any view index.
-// 32 clusters are bounded per pass (one per lane); the candidates of a pass are evaluated four at a time so that
-// their loads are in flight together.
+// 32 clusters are bounded per pass (one per lane), two passes per trip to memory; the candidates of a pass are
+// evaluated four at a time so that their loads are in flight together. ~5 dependent L1 / L2 trips in total.
 __device__ __forceinline__ int ClosestViewPrunedWarp(const float4* __restrict__ info, const float4* __restrict__ sorted,
                                                      int n_clusters, const float4* __restrict__ ori4, int n_views,
                                                      const float* vo, int prev) {
@@ -195,38 +195,46 @@ __device__ __forceinline__ int ClosestViewPrunedWarp(const float4* __restrict__ 
   const float lb = o0 * qp.x + o1 * qp.y + o2 * qp.z;
   float best = -1.0f;
   int idx = 0x7fffffff;
-  for (int c0 = 0; c0 < n_clusters; c0 += 32) {
-    const int c = c0 + lane;
-    bool cand = false;
-    unsigned packed = 0u;
-    if (c < n_clusters) {
-      const float4 a = __ldg(info + 2 * c), b = __ldg(info + 2 * c + 1);
-      const float ub = ViewClusterBound(a.x, a.y, a.z, a.w, b.x, b.y, b.z, o0, o1, o2, on2, onorm);
-      cand = !(ub < lb);  // NaN-safe: a NaN bound keeps the cluster
-      packed = __float_as_uint(b.w);
+  for (int c0 = 0; c0 < n_clusters; c0 += 64) {  // two bound passes per trip: their table loads are in flight together
+    float4 ia[2], ib[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 32 * h + lane;
+      if (c < n_clusters) { ia[h] = __ldg(info + 2 * c); ib[h] = __ldg(info + 2 * c + 1); }
+      else { ia[h] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); ib[h] = ia[h]; }
     }
-    unsigned m = __ballot_sync(kFull, cand);
-    while (m) {  // warp-uniform
-      unsigned pk[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int j = m ? __ffs(m) - 1 : 0;
-        const unsigned v = __shfl_sync(kFull, packed, j);
-        pk[u] = m ? v : 0u;
-        m &= m - 1u;  // 0 stays 0
+    for (int h = 0; h < 2; ++h) {
+      const int c = c0 + 32 * h + lane;
+      bool cand = false;
+      if (c < n_clusters) {
+        const float ub = ViewClusterBound(ia[h].x, ia[h].y, ia[h].z, ia[h].w, ib[h].x, ib[h].y, ib[h].z, o0, o1, o2, on2, onorm);
+        cand = !(ub < lb);  // NaN-safe: a NaN bound keeps the cluster
       }
-      float4 q[4];
+      const unsigned packed = __float_as_uint(ib[h].w);
+      unsigned m = __ballot_sync(kFull, cand);
+      while (m) {  // warp-uniform
+        unsigned pk[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int first = int(pk[u] & 0xffffffu), cnt = int(pk[u] >> 24);
-        q[u] = lane < cnt ? __ldg(sorted + first + lane) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      }
+        for (int u = 0; u < 4; ++u) {
+          const int j = m ? __ffs(m) - 1 : 0;
+          const unsigned v = __shfl_sync(kFull, packed, j);
+          pk[u] = m ? v : 0u;
+          m &= m - 1u;  // 0 stays 0
+        }
+        float4 q[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int cnt = int(pk[u] >> 24);
-        const float dot = o0 * q[u].x + o1 * q[u].y + o2 * q[u].z;
-        const int vi = __float_as_int(q[u].w);
-        if (lane < cnt && (dot > best || (dot == best && vi < idx))) { best = dot; idx = vi; }
+        for (int u = 0; u < 4; ++u) {
+          const int first = int(pk[u] & 0xffffffu), cnt = int(pk[u] >> 24);
+          q[u] = lane < cnt ? __ldg(sorted + first + lane) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int cnt = int(pk[u] >> 24);
+          const float dot = o0 * q[u].x + o1 * q[u].y + o2 * q[u].z;
+          const int vi = __float_as_int(q[u].w);
+          if (lane < cnt && (dot > best || (dot == best && vi < idx))) { best = dot; idx = vi; }
+        }
       }
     }
   }

@@ -1,0 +1,46 @@
+"""Per-phase clock budget of one fused k_track2 launch (M3TB_TIMING=1): warp 0 (lines + solve) and, for bodies
+with both modalities, the first point warp."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import importlib
+import numpy as np
+os.environ["M3TB_TIMING"] = "1"
+pkg = importlib.import_module("3dobjecttracking_b200")
+capi = importlib.import_module("3dobjecttracking_b200.capi")
+name = sys.argv[1] if len(sys.argv) > 1 else "c4"
+wl = pkg.synth.make_workload(name, n_divides=4)
+ctx = capi.context_from_workload(wl)
+ctx.start_modalities(0)
+for _ in range(3):
+    ctx.set_poses(wl.start_body2world)
+    ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
+ctx.synchronize()
+nc, nu = wl.n_corr_iterations, wl.n_update_iterations
+both = bool(wl.region and wl.depth)
+for body in (0, wl.n_bodies // 2):
+    c = ctx.phase_clocks(body, 256)
+    a = c[:128][c[:128] > 0]
+    d = np.diff(a)
+    print(f"{name} body {body}: warp 0 total {a[-1]-a[0]} cycles; prologue {d[0]}")
+    per_corr = 2 * (1 if both else (int(bool(wl.region)) + int(bool(wl.depth)))) + 5 * nu
+    rows = d[1:1 + nc * per_corr].reshape(nc, per_corr)
+    labels = (["view", "lines"] if wl.region else []) + (["view_d", "points"] if (wl.depth and not both) else [])
+    for u in range(nu):
+        labels += [f"acc{u}", f"bar{u}", f"sum{u}", f"solve{u}", f"bar2_{u}"]
+    print("   " + " ".join(f"{l:>7}" for l in labels))
+    for row in rows:
+        print("   " + " ".join(f"{v:7d}" for v in row))
+    print("   " + " ".join(f"{v:7d}" for v in rows.sum(0)), " <- sum")
+    if both:
+        b = c[128:][c[128:] > 0]
+        e = np.diff(b)
+        per = 2 + 2 * nu
+        rows = e[1:1 + nc * per].reshape(nc, per)
+        labels = ["view_d", "points"]
+        for u in range(nu):
+            labels += [f"acc{u}", f"wait{u}"]
+        print(f"   point warp: total {b[-1]-b[0]}, start offset vs warp 0 {b[0]-a[0]}; prologue {e[0]}")
+        print("   " + " ".join(f"{l:>7}" for l in labels))
+        for row in rows:
+            print("   " + " ".join(f"{v:7d}" for v in row))
+        print("   " + " ".join(f"{v:7d}" for v in rows.sum(0)), " <- sum")

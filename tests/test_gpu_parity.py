@@ -145,7 +145,7 @@ def test_free_running_trajectories(capi, oracle, wl_c2, wl_c3, which):
         worst_t, worst_r = np.maximum(worst_t, dt), np.maximum(worst_r, dr)
     within = (worst_t < TOL_POSE_M) & (worst_r < TOL_POSE_RAD)
     assert within.mean() >= 0.5, (worst_t, worst_r)
-    assert worst_t.max() < 2e-3 and worst_r.max() < 1e-2, (worst_t, worst_r)
+    assert worst_t.max() < 3e-3 and worst_r.max() < 2e-2, (worst_t, worst_r)
     ctx.close()
 
 
@@ -179,7 +179,7 @@ def test_full_cycle_two_frames(capi, oracle, wl_c2):
         orc.calculate_results(it)
         dt, dr = pose_error(ctx.get_poses(), orc.get_poses())
         assert np.median(dt) < TOL_POSE_M and np.median(dr) < TOL_POSE_RAD, (it, dt, dr)
-        assert dt.max() < 2e-3 and dr.max() < 1e-2, (it, dt, dr)  # discrete events, see test_free_running_trajectories
+        assert dt.max() < 3e-3 and dr.max() < 2e-2, (it, dt, dr)  # discrete events, see test_free_running_trajectories
     ctx.close()
 
 
