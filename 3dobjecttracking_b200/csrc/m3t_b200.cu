@@ -2,6 +2,8 @@
 // No CPU fallback anywhere: if CUDA is unusable every compute entry point returns M3TB_ERR_CUDA.
 #include "m3t_b200.h"
 
+#include <cudaTypedefs.h>  // PFN_cuTensorMapEncodeTiled
+
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -37,6 +39,17 @@ struct ImagePool {
   size_t frame_bytes = 0;
   unsigned pitch = 0;
   int width = 0, height = 0, capacity = 0;
+  // colour pools: the bin-index images (u16 per pixel), same slot order
+  uint16_t* bins = nullptr;
+  size_t bin_frame_bytes = 0;
+  unsigned bin_pitch = 0;
+};
+
+// TMA tensor maps over one pool ([camera][row][column] u16), one per tile width; cached per pool base address
+struct PoolMaps {
+  const void* base = nullptr;
+  bool ok = false;
+  CUtensorMap maps[kTileWidths];
 };
 
 // One m3t::Optimizer with more than a single free root link (host image; flattened into the device tables on demand)
@@ -105,6 +118,13 @@ struct m3tb_ctx {
   long long* d_phase_clock = nullptr;  // allocated when M3TB_TIMING=1
   bool use_tiles = true;  // stage ROI tiles in shared memory (M3TB_NO_TILES=1 in the environment disables it)
   bool use_track2 = true; // second-generation fused kernel where it applies (M3TB_KERNEL=1 forces k_track)
+  std::vector<char> bin_stale;            // per colour camera: the bin-index image does not match the frame copy
+  int bin_bitshift = -1;                  // what the bin-index images were built with
+  int* d_bin_ids = nullptr;               // staging for k_bin
+  std::vector<PoolMaps> pool_maps;        // tensor maps of the pools seen so far (current / alternate x bins / depth)
+  int tma_mode = 1;                       // M3TB_TMA: 0 legacy staging, 1 tensor maps in the kernel parameters, 2 in global memory
+  CUtensorMap* d_tmaps = nullptr;         // tma_mode 2: [2][kTileWidths]
+  const void* d_tmaps_bases[2] = {nullptr, nullptr};  // the pools d_tmaps currently describes
 
   // kinematic structures (empty: every body is its own rigid-body optimiser inside k_track)
   std::vector<StructureHost> structures;
@@ -294,6 +314,130 @@ int LaunchIngestIfPending(m3tb_ctx* ctx) {
 
 int SyncStructures(m3tb_ctx* ctx);
 
+// cuTensorMapEncodeTiled through the runtime (libcuda is not linked: the library must load on machines without a driver)
+PFN_cuTensorMapEncodeTiled_v12000 TensorMapEncoder() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = []() -> PFN_cuTensorMapEncodeTiled_v12000 {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }();
+  return fn;
+}
+
+// Tensor maps of a u16 image pool viewed as [n_frames][height][width], boxes of TileWidth(i) x kTileBoxRows x 1.
+const PoolMaps* GetPoolMaps(m3tb_ctx* ctx, void* base, int width, int height, unsigned pitch_bytes, size_t frame_bytes,
+                            int n_frames) {
+  for (const PoolMaps& m : ctx->pool_maps)
+    if (m.base == base) return m.ok ? &m : nullptr;
+  PoolMaps pm;
+  pm.base = base;
+  pm.ok = false;
+  auto encode = TensorMapEncoder();
+  if (encode && base && width >= 64 && height >= kTileBoxRows && (pitch_bytes & 15u) == 0 && (frame_bytes & 15u) == 0) {
+    pm.ok = true;
+    for (int i = 0; i < kTileWidths && pm.ok; ++i) {
+      const cuuint64_t dims[3] = {cuuint64_t(width), cuuint64_t(height), cuuint64_t(n_frames)};
+      const cuuint64_t strides[2] = {cuuint64_t(pitch_bytes), cuuint64_t(frame_bytes)};
+      const cuuint32_t box[3] = {cuuint32_t(TileWidth(i)), cuuint32_t(kTileBoxRows), 1u};
+      const cuuint32_t estr[3] = {1u, 1u, 1u};
+      const CUresult r = encode(&pm.maps[i], CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, base, dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) pm.ok = false;
+    }
+  }
+  if (ctx->pool_maps.size() >= 8) ctx->pool_maps.erase(ctx->pool_maps.begin());
+  ctx->pool_maps.push_back(pm);
+  return pm.ok ? &ctx->pool_maps.back() : nullptr;
+}
+
+// Can k_track2 stage its tiles with TMA for this batch? Every camera in use sits in its pool, the region bodies share one
+// histogram resolution (<= 32 bins: the index fits 16 bits); refreshes the bin-index images of frames that were copied in
+// full (k_bin) and fills the tensor maps of `a`.
+int PrepareTensorTiles(m3tb_ctx* ctx, TrackArgs& a, bool& usable) {
+  a.tma_mode = ctx->tma_mode;
+  a.tma_max_w = 256;
+  if (const char* e = std::getenv("M3TB_TMA_MAXW")) a.tma_max_w = std::max(64, std::min(256, std::atoi(e) / 32 * 32));
+  a.tmaps_global = ctx->d_tmaps;
+  if (ctx->tma_mode == 0) { usable = true; return M3TB_OK; }  // legacy staging needs neither maps nor bin images
+  usable = false;
+  int bitshift = -1, n_bins = 0;
+  bool any_region = false, any_depth = false;
+  for (int b = 0; b < ctx->n_bodies; ++b) {
+    const BodyDev& B = ctx->h_bodies[b];
+    if (B.has_region) {
+      any_region = true;
+      if (bitshift >= 0 && B.rp.bitshift != bitshift) return M3TB_OK;
+      bitshift = B.rp.bitshift;
+      n_bins = B.rp.n_bins;
+      if (n_bins > 32) return M3TB_OK;
+      const CameraDev& c = ctx->h_ccams[B.color_camera];
+      if (!ctx->color_pool.base || !ctx->color_pool.bins ||
+          c.image != ctx->color_pool.base + ctx->color_pool.frame_bytes * B.color_camera || !c.bins)
+        return M3TB_OK;
+    }
+    if (B.has_depth) {
+      any_depth = true;
+      const CameraDev& c = ctx->h_dcams[B.depth_camera];
+      if (!ctx->depth_pool.base || c.image != ctx->depth_pool.base + ctx->depth_pool.frame_bytes * B.depth_camera)
+        return M3TB_OK;
+    }
+  }
+  if (any_region) {
+    const ImagePool& p = ctx->color_pool;
+    const PoolMaps* m = GetPoolMaps(ctx, p.bins, p.width, p.height, p.bin_pitch, p.bin_frame_bytes, p.capacity);
+    if (!m) return M3TB_OK;
+    std::memcpy(a.bin_maps, m->maps, sizeof(a.bin_maps));
+    // frames that arrived by full copy: (re)build their bin-index images
+    if (ctx->bin_bitshift != bitshift) {
+      for (int i = 0; i < ctx->max_cameras; ++i)
+        if (!ctx->h_ccams[i].host_src) ctx->bin_stale[i] = 1;
+      ctx->bin_bitshift = bitshift;
+    }
+    std::vector<int> ids;
+    for (int i = 0; i < ctx->max_cameras; ++i) {
+      const CameraDev& c = ctx->h_ccams[i];
+      if (c.set && c.image && c.bins && !c.host_src && ctx->bin_stale[i]) ids.push_back(i);
+    }
+    if (!ids.empty()) {
+      CU(cudaMemcpyAsync(ctx->d_bin_ids, ids.data(), sizeof(int) * ids.size(), cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));  // `ids` is a temporary (set-up path, not per step)
+      BinArgs ba;
+      ba.cams = ctx->d_ccams;
+      ba.cam_ids = ctx->d_bin_ids;
+      ba.bitshift = bitshift;
+      ba.n_bins = n_bins;
+      k_bin<<<dim3(unsigned(std::min(p.height, 120)), unsigned(ids.size())), kBlockThreads, 0, ctx->stream>>>(ba);
+      CU(cudaGetLastError());
+      ctx->launches++;
+      for (int i : ids) ctx->bin_stale[i] = 0;
+    }
+  }
+  if (any_depth) {
+    const ImagePool& p = ctx->depth_pool;
+    const PoolMaps* m = GetPoolMaps(ctx, p.base, p.width, p.height, p.pitch, p.frame_bytes, p.capacity);
+    if (!m) return M3TB_OK;
+    std::memcpy(a.depth_maps, m->maps, sizeof(a.depth_maps));
+  }
+  if (ctx->tma_mode == 2) {  // descriptors in global memory: refresh when the pools behind them changed (prefetch swaps)
+    const void* bases[2] = {any_region ? static_cast<const void*>(ctx->color_pool.bins) : nullptr,
+                            any_depth ? static_cast<const void*>(ctx->depth_pool.base) : nullptr};
+    if (bases[0] != ctx->d_tmaps_bases[0] || bases[1] != ctx->d_tmaps_bases[1]) {
+      CU(cudaMemcpyAsync(ctx->d_tmaps, a.bin_maps, sizeof(CUtensorMap) * kTileWidths, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaMemcpyAsync(ctx->d_tmaps + kTileWidths, a.depth_maps, sizeof(CUtensorMap) * kTileWidths, cudaMemcpyHostToDevice,
+                         ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));  // `a` is a stack object
+      ctx->d_tmaps_bases[0] = bases[0];
+      ctx->d_tmaps_bases[1] = bases[1];
+    }
+  }
+  usable = true;
+  return M3TB_OK;
+}
+
 // cluster > 0: one thread-block cluster of `cluster` CTAs per kinematic structure (PH_CLUSTER_SOLVE)
 int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int n_update, int opt_base,
                 unsigned phases, int cluster = 0) {
@@ -312,7 +456,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
     CU(cudaEventRecord(ctx->ev_poses_snap, ctx->stream));
     ctx->poses_snap_valid = true;
   }
-  TrackArgs a;
+  TrackArgs a = {};
   a.bodies = ctx->d_bodies;
   a.poses = ctx->d_poses;
   a.color_cams = ctx->d_ccams;
@@ -352,7 +496,10 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   const size_t lut_bytes = lut_smem ? size_t(16 * 16 * 16) * sizeof(float2) : 0;
   // with cluster-fused structures the solver workspace sits at the end of the dynamic shared memory
   const size_t struct_bytes = cluster > 0 ? Align(ctx->struct_smem, 128) : 0;
-  const bool tiles = ctx->use_tiles && cluster == 0;
+  bool bins_fit_u16 = true;  // the colour tile holds 16-bit bin indices: 64 bins (18 bits) go without tiles
+  for (int b = 0; b < ctx->n_bodies; ++b)
+    if (ctx->h_bodies[b].has_region && ctx->h_bodies[b].rp.n_bins > 32) bins_fit_u16 = false;
+  const bool tiles = ctx->use_tiles && cluster == 0 && bins_fit_u16;
   const size_t dyn = tiles ? size_t(kDynSmemBytes) : lut_bytes + struct_bytes;
   a.tile_bytes = tiles ? int(dyn - lut_bytes - struct_bytes) : 0;
   a.struct_offset = unsigned(dyn - struct_bytes);
@@ -383,6 +530,10 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
       }
     }
     if (!have_lookup) { std::memset(a.lookup_f, 0, sizeof(a.lookup_f)); std::memset(a.lookup_b, 0, sizeof(a.lookup_b)); }
+    if (ok) {
+      int trc = PrepareTensorTiles(ctx, a, ok);
+      if (trc) return trc;
+    }
     if (ok) {
       const size_t fixed = lut_bytes + size_t(kDistBytes);
       const size_t dyn2 = ctx->use_tiles ? size_t(kDynSmemBytes) : fixed;
@@ -790,11 +941,22 @@ int EnsureImage(m3tb_ctx* ctx, bool color, int cam) {
     pool.frame_bytes = size_t(pitch) * c.height;
     pool.capacity = ctx->max_cameras;
     CU(cudaMalloc(&pool.base, pool.frame_bytes * pool.capacity));
+    if (color && (c.width & 3) == 0) {
+      pool.bin_pitch = unsigned(Align(size_t(c.width) * 2, 16));
+      pool.bin_frame_bytes = size_t(pool.bin_pitch) * c.height;
+      CU(cudaMalloc(&pool.bins, pool.bin_frame_bytes * pool.capacity));
+    }
   }
   if (pool.width == c.width && pool.height == c.height) {
     c.image = pool.base + pool.frame_bytes * cam;
     c.pitch = pool.pitch;
+    if (color && pool.bins) {
+      c.bins = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(pool.bins) + pool.bin_frame_bytes * cam);
+      c.bin_pitch = pool.bin_pitch;
+    }
   } else {
+    c.bins = nullptr;
+    c.bin_pitch = 0;
     uint8_t*& priv = (color ? ctx->private_color : ctx->private_depth)[cam];
     if (priv) cudaFree(priv);
     CU(cudaMalloc(&priv, size_t(pitch) * c.height));
@@ -832,10 +994,12 @@ int Upload(m3tb_ctx* ctx, bool color, int cam, const void* src, size_t pitch, cu
     c.host_src = pinned_alias;
     c.host_pitch = unsigned(pitch);
     ctx->ingest_pending = true;
+    if (color) ctx->bin_stale[cam] = 0;  // k_ingest writes the bin indices of every rectangle it fetches
     return M3TB_OK;
   }
   c.host_src = nullptr;
   c.host_pitch = 0;
+  if (color) ctx->bin_stale[cam] = 1;
   CU(cudaMemcpy2DAsync(const_cast<uint8_t*>(c.image), c.pitch, src, pitch, row, c.height, kind, ctx->stream));
   return M3TB_OK;
 }
@@ -862,6 +1026,7 @@ int UploadBatch(m3tb_ctx* ctx, bool color, int first, int count, const void* src
   for (int k = 0; k < count; ++k) {
     CameraDev& c = (color ? ctx->h_ccams : ctx->h_dcams)[first + k];
     c.host_src = nullptr; c.host_pitch = 0; c.generation = (c.generation + 1) & 0x3fffffff;
+    if (color) ctx->bin_stale[first + k] = 1;
   }
   ctx->cams_dirty = true;
   if (pooled && frame_stride == pitch * size_t(pool.height)) {
@@ -961,10 +1126,12 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   ctx->dmodel_alloc.assign(max_models, ModelAlloc());
   ctx->private_color.assign(max_cameras, nullptr);
   ctx->private_depth.assign(max_cameras, nullptr);
+  ctx->bin_stale.assign(max_cameras, 1);
   if (const char* e = std::getenv("M3TB_NO_TILES")) ctx->use_tiles = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_NO_ROI_INGEST")) ctx->roi_ingest = !(e[0] == '1');
   if (const char* e = std::getenv("M3TB_CLUSTER")) ctx->use_clusters = e[0] == '1';
   if (const char* e = std::getenv("M3TB_KERNEL")) ctx->use_track2 = !(e[0] == '1');
+  if (const char* e = std::getenv("M3TB_TMA")) ctx->tma_mode = (e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 1;
   const char* timing_env = std::getenv("M3TB_TIMING");
   const bool want_timing = timing_env && timing_env[0] == '1';
   auto alloc = [&]() -> int {
@@ -986,6 +1153,8 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
     CU(cudaMemset(ctx->d_gh_link, 0, sizeof(float) * 27 * max_bodies));
     CU(cudaMalloc(&ctx->d_roi, sizeof(RoiRecord) * 2 * max_bodies));
     CU(cudaMemset(ctx->d_roi, 0xff, sizeof(RoiRecord) * 2 * max_bodies));  // generation -1: nothing ingested yet
+    CU(cudaMalloc(&ctx->d_bin_ids, sizeof(int) * max_cameras));
+    CU(cudaMalloc(&ctx->d_tmaps, sizeof(CUtensorMap) * 2 * kTileWidths));
     CU(cudaMalloc(&ctx->d_ingest_bytes, sizeof(unsigned long long)));
     CU(cudaMemset(ctx->d_ingest_bytes, 0, sizeof(unsigned long long)));
     if (want_timing) {
@@ -1016,6 +1185,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   for (auto p : ctx->private_color) cudaFree(p);
   for (auto p : ctx->private_depth) cudaFree(p);
   cudaFree(ctx->color_pool.base); cudaFree(ctx->depth_pool.base);
+  cudaFree(ctx->color_pool.bins); cudaFree(ctx->color_pool_alt.bins); cudaFree(ctx->d_bin_ids); cudaFree(ctx->d_tmaps);
   cudaFree(ctx->d_bodies); cudaFree(ctx->d_ccams); cudaFree(ctx->d_dcams); cudaFree(ctx->d_rmodels);
   cudaFree(ctx->d_dmodels); cudaFree(ctx->d_poses); cudaFree(ctx->d_counts); cudaFree(ctx->d_gh_region);
   cudaFree(ctx->d_gh_depth); cudaFree(ctx->d_hist_f); cudaFree(ctx->d_hist_b); cudaFree(ctx->d_mem_f);
@@ -1612,12 +1782,18 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
     if (pool.base && !alt.base) {
       alt = pool;
       alt.base = nullptr;
+      alt.bins = nullptr;
       CU(cudaMalloc(&alt.base, alt.frame_bytes * alt.capacity));
+      if (pool.bins) CU(cudaMalloc(&alt.bins, alt.bin_frame_bytes * alt.capacity));
     }
     std::swap(pool, alt);
     std::vector<CameraDev>& cams = k == 0 ? ctx->h_ccams : ctx->h_dcams;
     for (int i = 0; i < ctx->max_cameras; ++i)
-      if (cams[i].set && cams[i].image) cams[i].image = pool.base + pool.frame_bytes * i;
+      if (cams[i].set && cams[i].image) {
+        cams[i].image = pool.base + pool.frame_bytes * i;
+        if (k == 0 && pool.bins)
+          cams[i].bins = reinterpret_cast<uint16_t*>(reinterpret_cast<uint8_t*>(pool.bins) + pool.bin_frame_bytes * i);
+      }
   }
   ctx->cams_dirty = false;   // the camera tables go to the alternate device copies below, on the side stream
   int rc = SyncTables(ctx);  // bodies / models only (main stream, small)
@@ -1669,6 +1845,7 @@ int m3tb_detach_frames(m3tb_ctx* ctx) {
                            cudaMemcpyHostToDevice, ctx->stream));
       c.host_src = nullptr;  // FrameView: the whole device copy is valid from now on
       c.host_pitch = 0;
+      if (k == 0) ctx->bin_stale[size_t(&c - cams.data())] = 1;
       any = true;
     }
   }

@@ -9,6 +9,7 @@
 // evaluation of the same expressions.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -18,6 +19,9 @@ constexpr int kFunctionLength = 8;       // region_modality.h:415
 constexpr int kDistributionLength = 12;  // region_modality.h:416
 constexpr int kLineSegments = kFunctionLength + kDistributionLength - 1;  // 19, region_modality.cpp:926
 constexpr int kMaxSchedule = 8;
+constexpr int kTileWidths = 7;    // tile widths 64, 96, .. 256 pixels (tensor-map box widths)
+constexpr int kTileBoxRows = 16;  // rows per TMA box
+__host__ __device__ constexpr int TileWidth(int i) { return 64 + 32 * i; }
 constexpr int kPhaseSlots = 256;
 constexpr int kBlockThreads = 256;
 constexpr int kWarps = kBlockThreads / 32;
@@ -51,6 +55,10 @@ struct CameraDev {
   unsigned host_pitch;
   int generation;        // bumped by every upload; k_ingest refreshes a body's ROI when it differs from the ROI's
   int set;
+  // colour cameras in the pool: histogram BIN-INDEX image (u16 per pixel, ColorHistograms::GetProbabilities index,
+  // color_histograms.cpp:97-99) written once per frame by k_bin / k_ingest; the source of k_track2's colour tiles
+  uint16_t* bins;
+  unsigned bin_pitch;    // bytes
 };
 
 // How one body sees one camera frame. The device copy is valid inside [x0,x1) x [y0,y1); everything else is read
@@ -152,6 +160,13 @@ struct TrackArgs {
   float* theta_out;             // [n_structures][kMaxSystem]
   int* struct_status;           // [n_structures]
   unsigned struct_offset;       // byte offset of the solver workspace in dynamic shared memory
+  // k_track2: TMA tensor maps over the image pools ([camera][row][column] u16), one per tile width; the box is
+  // kTileBoxRows rows high. tma_ok = 0: the pools cannot be described (private images): k_track2 is not launched.
+  CUtensorMap bin_maps[kTileWidths];
+  CUtensorMap depth_maps[kTileWidths];
+  const CUtensorMap* tmaps_global;  // the same 2 x kTileWidths maps in global memory (tma_mode 2)
+  int tma_max_w;                    // widest tile (debug knob M3TB_TMA_MAXW; 256)
+  int tma_mode;                     // 0: legacy staging without tensor maps, 1: maps in the kernel parameters, 2: in global memory
   // k_track2: RegionModality::PrecalculateFunctionLookup tables, identical for every region body of the launch
   // (checked by the host), so that they are kernel-parameter constants instead of per-thread registers
   float lookup_f[kFunctionLength], lookup_b[kFunctionLength];

@@ -1491,6 +1491,108 @@ __device__ __forceinline__ void IngestRect(const CameraDev& cam, const Tile& t, 
   if (threadIdx.x == 0) atomicAdd(bytes, static_cast<unsigned long long>(row_bytes) * t.h);
 }
 
+__device__ __forceinline__ unsigned BinOf(unsigned b, unsigned g, unsigned r, int bs, unsigned nb) {
+  return ((b >> bs) * nb + (g >> bs)) * nb + (r >> bs);  // color_histograms.cpp:97-99, BGR memory order
+}
+// 16 pixels = 48 bytes (three 16-byte words) -> 16 bin indices (two 16-byte words)
+__device__ __forceinline__ void Bins16(const uint4 (&w)[3], int bs, unsigned nb, uint4& lo, uint4& hi) {
+  unsigned char px[48];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned v[4] = {w[k].x, w[k].y, w[k].z, w[k].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) px[16 * k + 4 * q + b] = (unsigned char)((v[q] >> (8 * b)) & 0xffu);
+  }
+  unsigned o[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const unsigned a = BinOf(px[6 * i], px[6 * i + 1], px[6 * i + 2], bs, nb);
+    const unsigned c = BinOf(px[6 * i + 3], px[6 * i + 4], px[6 * i + 5], bs, nb);
+    o[i] = a | (c << 16);
+  }
+  lo = make_uint4(o[0], o[1], o[2], o[3]);
+  hi = make_uint4(o[4], o[5], o[6], o[7]);
+}
+
+// Colour ROI ingest that also writes the bin-index image (source of k_track2's TMA colour tiles): x0 and w are
+// multiples of 16 pixels, so a work item is 48 bytes in, 48 + 32 bytes out.
+__device__ __forceinline__ void IngestColorRect(const CameraDev& cam, const Tile& t, int bs, unsigned nb, unsigned long long* bytes) {
+  if (t.w <= 0 || t.h <= 0) return;
+  const unsigned row_bytes = unsigned(t.w) * 3u;
+  const uint8_t* src0 = cam.host_src + size_t(t.y0) * cam.host_pitch + size_t(t.x0) * 3u;
+  uint8_t* dst0 = const_cast<uint8_t*>(cam.image) + size_t(t.y0) * cam.pitch + size_t(t.x0) * 3u;
+  uint8_t* bin0 = reinterpret_cast<uint8_t*>(cam.bins) + size_t(t.y0) * cam.bin_pitch + size_t(t.x0) * 2u;
+  const bool vec16 = ((reinterpret_cast<size_t>(src0) | cam.host_pitch) & 15u) == 0 && (t.w & 15) == 0 && (t.x0 & 15) == 0;
+  if (vec16) {
+    const int per_row = t.w >> 4;
+    const int total = per_row * t.h;
+    for (int c0 = threadIdx.x; c0 < total; c0 += 2 * blockDim.x) {  // six 16-byte PCIe reads in flight per thread
+      uint4 v[2][3];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < total) {
+          const int r = c / per_row, k = c - r * per_row;
+          const uint4* s = reinterpret_cast<const uint4*>(src0 + size_t(r) * cam.host_pitch) + 3 * k;
+          v[u][0] = __ldg(s); v[u][1] = __ldg(s + 1); v[u][2] = __ldg(s + 2);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = c0 + u * blockDim.x;
+        if (c < total) {
+          const int r = c / per_row, k = c - r * per_row;
+          uint4* d = reinterpret_cast<uint4*>(dst0 + size_t(r) * cam.pitch) + 3 * k;
+          d[0] = v[u][0]; d[1] = v[u][1]; d[2] = v[u][2];
+          uint4 lo, hi;
+          Bins16(v[u], bs, nb, lo, hi);
+          uint4* b = reinterpret_cast<uint4*>(bin0 + size_t(r) * cam.bin_pitch) + 2 * k;
+          b[0] = lo; b[1] = hi;
+        }
+      }
+    }
+  } else {
+    const int total = t.w * t.h;
+    for (int c = threadIdx.x; c < total; c += blockDim.x) {
+      const int r = c / t.w, k = c - r * t.w;
+      const uint8_t* s = src0 + size_t(r) * cam.host_pitch + 3 * k;
+      uint8_t* d = dst0 + size_t(r) * cam.pitch + 3 * k;
+      const unsigned b0 = __ldg(s), b1 = __ldg(s + 1), b2 = __ldg(s + 2);
+      d[0] = (uint8_t)b0; d[1] = (uint8_t)b1; d[2] = (uint8_t)b2;
+      reinterpret_cast<uint16_t*>(bin0 + size_t(r) * cam.bin_pitch)[k] = (uint16_t)BinOf(b0, b1, b2, bs, nb);
+    }
+  }
+  if (threadIdx.x == 0) atomicAdd(bytes, static_cast<unsigned long long>(row_bytes) * t.h);
+}
+
+// k_bin: bin-index image of whole colour frames (frames that were copied in full; grid = (rows, cameras)).
+struct BinArgs {
+  const CameraDev* cams;
+  const int* cam_ids;   // cameras to convert
+  int bitshift, n_bins;
+};
+__global__ void __launch_bounds__(kBlockThreads) k_bin(BinArgs args) {
+  const CameraDev& cam = args.cams[args.cam_ids[blockIdx.y]];
+  if (!cam.bins || !cam.image) return;
+  const int groups = (cam.width + 3) >> 2;  // 4 pixels = 12 bytes = three aligned words (pitch is a multiple of 16)
+  for (int y = blockIdx.x; y < cam.height; y += gridDim.x) {
+    const unsigned* src = reinterpret_cast<const unsigned*>(cam.image + size_t(y) * cam.pitch);
+    uint2* dst = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(cam.bins) + size_t(y) * cam.bin_pitch);
+    for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+      const unsigned w0 = __ldg(src + 3 * g), w1 = __ldg(src + 3 * g + 1), w2 = __ldg(src + 3 * g + 2);
+      const unsigned nb = unsigned(args.n_bins);
+      const int bs = args.bitshift;
+      const unsigned i0 = BinOf(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu, bs, nb);
+      const unsigned i1 = BinOf(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu, bs, nb);
+      const unsigned i2 = BinOf((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu, bs, nb);
+      const unsigned i3 = BinOf((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24, bs, nb);
+      dst[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
   const int body_id = blockIdx.x;
   const BodyDev& body = args.bodies[body_id];
@@ -1540,7 +1642,11 @@ __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
     }
   }
   __syncthreads();
-  if (todo[0]) IngestRect(args.color_cams[body.color_camera], rect[0], 3u, args.bytes);
+  if (todo[0]) {
+    const CameraDev& cc = args.color_cams[body.color_camera];
+    if (cc.bins && body.rp.n_bins <= 32) IngestColorRect(cc, rect[0], body.rp.bitshift, unsigned(body.rp.n_bins), args.bytes);
+    else IngestRect(cc, rect[0], 3u, args.bytes);
+  }
   if (todo[1]) IngestRect(args.depth_cams[body.depth_camera], rect[1], 2u, args.bytes);
 }
 

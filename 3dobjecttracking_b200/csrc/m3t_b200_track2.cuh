@@ -38,7 +38,7 @@ struct Shared2 {
   float cw2c[12], dw2c[12];  // world2camera
   float view_o[2][4];        // GetClosestView queries, [3] = 1 if |t| > 0
   Tile ctile, dtile;
-  unsigned long long depth_bar, lut_bar;
+  unsigned long long depth_bar, lut_bar, ctile_bar;
   float red[32][32];         // per-warp partial sums g[6] + H lower[21] (+5 pad)
   float a[36], b[6], x[6];   // normal equations
   int views[2][2];           // [corr parity][region | depth] closest views, published by the group leaders
@@ -297,6 +297,50 @@ __device__ __forceinline__ void RegionGradient2(const RegionIter& it, const Regi
 }
 
 // ---------------------------------------------------------------------------------------------
+// TMA tensor tiles
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void TensorCopyG2S(void* dst_smem, const CUtensorMap* map, int x, int y, int z,
+                                              unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          SmemAddr(dst_smem)),
+      "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(z), "r"(SmemAddr(bar))
+      : "memory");
+}
+
+// Fits the wanted rectangle `t` to what a stack of TMA boxes can deliver: a width from {64, 96, .. 256}, a height that
+// is a multiple of kTileBoxRows, inside the region where the device copy of the frame is valid (`f`), at most `budget`
+// bytes. Wider / taller than wanted is fine (more samples take the fast path); smaller is clipped symmetrically, the
+// samples outside go through the frame in global memory. No tile (w = h = 0) if even the smallest box does not fit.
+__device__ __forceinline__ void SnapTile(Tile& t, const FrameView& f, int budget, int max_w = 256) {
+  const int vx0 = f.x0, vx1 = f.x1, vy0 = f.y0, vy1 = f.y1;
+  if (t.w <= 0 || t.h <= 0 || vx1 - vx0 < 64 || vy1 - vy0 < kTileBoxRows || budget < 64 * kTileBoxRows * 2) {
+    t.w = t.h = t.pitch = 0;
+    return;
+  }
+  int w = min(max_w, (max(t.w, 64) + 31) / 32 * 32);         // smallest box width that covers the rectangle
+  w = min(w, (vx1 - vx0) / 32 * 32);                         // ... that fits the valid columns
+  w = max(w, 64);
+  if (w > vx1 - vx0) { t.w = t.h = t.pitch = 0; return; }
+  int h = (t.h + kTileBoxRows - 1) / kTileBoxRows * kTileBoxRows;
+  h = min(h, (vy1 - vy0) / kTileBoxRows * kTileBoxRows);
+  while (w * h * 2 > budget) {                               // over budget: shrink the longer side first
+    if (h >= w && h > kTileBoxRows) h -= kTileBoxRows;
+    else if (w > 64) w -= 32;
+    else if (h > kTileBoxRows) h -= kTileBoxRows;
+    else { t.w = t.h = t.pitch = 0; return; }
+  }
+  // centre on the wanted rectangle, then push back inside the valid region. The first column is a multiple of 8 pixels:
+  // TMA needs the global address of a box (base + 2 * x0) 16-byte aligned (an unaligned x0 traps as "illegal
+  // instruction", measured with scripts/probes/tma_probe.cu).
+  int x0 = (t.x0 + (t.w - w) / 2) & ~7, y0 = t.y0 + (t.h - h) / 2;
+  x0 = max((vx0 + 7) & ~7, min(x0, (vx1 - w) & ~7));
+  y0 = max(vy0, min(y0, vy1 - h));
+  if (x0 < vx0 || x0 + w > vx1) { t.w = t.h = t.pitch = 0; return; }
+  t.x0 = x0; t.y0 = y0; t.w = w; t.h = h; t.pitch = w;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Pose products, thread-serial (every calling lane computes everything; lane 0 publishes). Expressions are those of
 // PoseMul / PoseInverse / ViewOrientation, i.e. of PoseProductsWarp in k_track.
 // ---------------------------------------------------------------------------------------------
@@ -496,6 +540,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   if (tid == 0) {
     if (LUT_SMEM) MbarInit(&sh.lut_bar, 1);
     MbarInit(&sh.depth_bar, 1);
+    MbarInit(&sh.ctile_bar, 1);
   }
   __syncthreads();
   if (warp == 0) {
@@ -509,91 +554,144 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     MbarExpectTx(&sh.lut_bar, bytes);
     BulkCopyG2S(dyn, lut_g, bytes, &sh.lut_bar);
   }
-  if (tid == 32 % T) {
-    Tile ct, dt;
-    ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kDistBytes;
-    dt = ct;
-    if (args.tile_bytes > 0) {
-      float b2c[12];
-      if (do_rcorr) {
-        int s_max = 1;
-        for (int c = args.corr_begin; c < args.corr_end; ++c) s_max = max(s_max, LastValid(body.rp.scales, body.rp.n_scales, c));
-        PoseMul(ccam->w2c, sh.pose, b2c);
-        RoiRect(b2c, ccam->fu, ccam->fv, ccam->ppu, ccam->ppv, ccam->width, ccam->height, rmodel->radius,
-                0.5f * float(kLineSegments * s_max) + 2.0f + 12.0f, 4, ct);
+  const bool tma = args.tma_mode != 0;
+  if (tma) {
+    // ROI tiles: one thread sizes them and issues the TMA tensor copies (cp.async.bulk.tensor.3d, SASS UTMALDG): the
+    // colour tile comes from the camera's BIN-INDEX image (u16 per pixel, written once per frame by k_bin / k_ingest),
+    // the depth tile from the raw U16 frame; boxes of kTileBoxRows rows x the tile width, stacked -> row-major tile.
+    if (tid == 32 % T) {
+      Tile ct, dt;
+      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kDistBytes;
+      dt = ct;
+      if (args.tile_bytes > 0) {
+        float b2c[12];
+        if (do_rcorr) {
+          int s_max = 1;
+          for (int c = args.corr_begin; c < args.corr_end; ++c) s_max = max(s_max, LastValid(body.rp.scales, body.rp.n_scales, c));
+          PoseMul(ccam->w2c, sh.pose, b2c);
+          RoiRect(b2c, ccam->fu, ccam->fv, ccam->ppu, ccam->ppv, ccam->width, ccam->height, rmodel->radius,
+                  0.5f * float(kLineSegments * s_max) + 2.0f + 12.0f, 1, ct);
+        }
+        if (do_dcorr) {
+          float d_max = 0.0f;
+          for (int c = args.corr_begin; c < args.corr_end; ++c)
+            d_max = fmaxf(d_max, LastValid(body.dp.considered_distances, body.dp.n_considered_distances, c));
+          PoseMul(dcam->w2c, sh.pose, b2c);
+          const float z = b2c[11];
+          const float reach = (z > 2.0f * dmodel->radius) ? d_max * dcam->fu / (z - dmodel->radius) + 2.0f + 8.0f : 0.0f;
+          RoiRect(b2c, dcam->fu, dcam->fv, dcam->ppu, dcam->ppv, dcam->width, dcam->height, dmodel->radius, reach, 1, dt);
+        }
+        // split the budget: the depth tile is the smaller one, give it what it asks for up to 40 %
+        const int budget = args.tile_bytes - 256;
+        SnapTile(dt, dframe, budget * 2 / 5, args.tma_max_w);
+        const int dbytes = dt.w * dt.h * 2;
+        SnapTile(ct, cframe, budget - dbytes, args.tma_max_w);
+        dt.offset = lut_bytes + kDistBytes + unsigned(ct.w * ct.h * 2);
       }
-      if (do_dcorr) {
-        float d_max = 0.0f;
-        for (int c = args.corr_begin; c < args.corr_end; ++c)
-          d_max = fmaxf(d_max, LastValid(body.dp.considered_distances, body.dp.n_considered_distances, c));
-        PoseMul(dcam->w2c, sh.pose, b2c);
-        const float z = b2c[11];
-        const float reach = (z > 2.0f * dmodel->radius) ? d_max * dcam->fu / (z - dmodel->radius) + 2.0f + 8.0f : 0.0f;
-        RoiRect(b2c, dcam->fu, dcam->fv, dcam->ppu, dcam->ppv, dcam->width, dcam->height, dmodel->radius, reach, 8, dt);
+      sh.ctile = ct;
+      sh.dtile = dt;
+      if (ct.w > 0) {
+        const CUtensorMap* map = (args.tma_mode == 2 ? args.tmaps_global : args.bin_maps) + ((ct.w - 64) >> 5);
+        MbarExpectTx(&sh.ctile_bar, unsigned(ct.w * ct.h * 2));
+        for (int r = 0; r < ct.h; r += kTileBoxRows)
+          TensorCopyG2S(dyn + ct.offset + size_t(r) * ct.w * 2, map, ct.x0, ct.y0 + r, body.color_camera, &sh.ctile_bar);
       }
-      ClipTile(ct, cframe, 4);
-      ClipTile(dt, dframe, 8);
-      int budget = args.tile_bytes - 256;
-      FitTile(dt, budget * 2 / 5, 8);
-      const int dbytes = (dt.w * dt.h * 2 + 127) / 128 * 128;
-      FitTile(ct, budget - dbytes, 4);
-      const int cbytes = (ct.w * ct.h * 2 + 127) / 128 * 128;
-      dt.offset = lut_bytes + kDistBytes + unsigned(cbytes);
+      if (dt.w > 0) {
+        const CUtensorMap* map = (args.tma_mode == 2 ? args.tmaps_global + kTileWidths : args.depth_maps) + ((dt.w - 64) >> 5);
+        MbarExpectTx(&sh.depth_bar, unsigned(dt.w * dt.h * 2));
+        for (int r = 0; r < dt.h; r += kTileBoxRows)
+          TensorCopyG2S(dyn + dt.offset + size_t(r) * dt.w * 2, map, dt.x0, dt.y0 + r, body.depth_camera, &sh.depth_bar);
+      }
     }
-    sh.ctile = ct;
-    sh.dtile = dt;
+  } else {  // legacy staging (tma_mode 0): depth rows by 1-D bulk copies, colour bins converted from the BGR frame
+    if (tid == 32 % T) {
+      Tile ct, dt;
+      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kDistBytes;
+      dt = ct;
+      if (args.tile_bytes > 0) {
+        float b2c[12];
+        if (do_rcorr) {
+          int s_max = 1;
+          for (int c = args.corr_begin; c < args.corr_end; ++c) s_max = max(s_max, LastValid(body.rp.scales, body.rp.n_scales, c));
+          PoseMul(ccam->w2c, sh.pose, b2c);
+          RoiRect(b2c, ccam->fu, ccam->fv, ccam->ppu, ccam->ppv, ccam->width, ccam->height, rmodel->radius,
+                  0.5f * float(kLineSegments * s_max) + 2.0f + 12.0f, 4, ct);
+        }
+        if (do_dcorr) {
+          float d_max = 0.0f;
+          for (int c = args.corr_begin; c < args.corr_end; ++c)
+            d_max = fmaxf(d_max, LastValid(body.dp.considered_distances, body.dp.n_considered_distances, c));
+          PoseMul(dcam->w2c, sh.pose, b2c);
+          const float z = b2c[11];
+          const float reach = (z > 2.0f * dmodel->radius) ? d_max * dcam->fu / (z - dmodel->radius) + 2.0f + 8.0f : 0.0f;
+          RoiRect(b2c, dcam->fu, dcam->fv, dcam->ppu, dcam->ppv, dcam->width, dcam->height, dmodel->radius, reach, 8, dt);
+        }
+        ClipTile(ct, cframe, 4);
+        ClipTile(dt, dframe, 8);
+        int budget = args.tile_bytes - 256;
+        FitTile(dt, budget * 2 / 5, 8);
+        const int dbytes = (dt.w * dt.h * 2 + 127) / 128 * 128;
+        FitTile(ct, budget - dbytes, 4);
+        const int cbytes = (ct.w * ct.h * 2 + 127) / 128 * 128;
+        dt.offset = lut_bytes + kDistBytes + unsigned(cbytes);
+      }
+      sh.ctile = ct;
+      sh.dtile = dt;
+    }
   }
-  __syncthreads();
+  __syncthreads();  // tiles sized (TMA copies in flight); also orders the initial pose products before their first readers
   const Tile ctile = sh.ctile, dtile = sh.dtile;
   const uint16_t* ctile_px = reinterpret_cast<const uint16_t*>(dyn + ctile.offset);
   const uint16_t* dtile_px = reinterpret_cast<const uint16_t*>(dyn + dtile.offset);
-  bool depth_ready = true;
-  if (dtile.w > 0) {
-    depth_ready = false;
-    if (warp == kW - 1) {  // a point warp issues the depth rows while the others convert the colour tile
-      const unsigned row_bytes = unsigned(dtile.w) * 2u;
-      if (lane == 0) MbarExpectTx(&sh.depth_bar, row_bytes * unsigned(dtile.h));
-      __syncwarp();
-      for (int r = lane; r < dtile.h; r += 32)
-        BulkCopyG2S(dyn + dtile.offset + size_t(r) * row_bytes,
-                    dcam->image + size_t(dtile.y0 + r) * dcam->pitch + size_t(dtile.x0) * 2u, row_bytes, &sh.depth_bar);
-    }
-  }
-  if (ctile.w > 0) {
-    const int groups_per_row = ctile.w >> 2;
-    const int n_groups = groups_per_row * ctile.h;
-    const int bs = body.rp.bitshift, nb = body.rp.n_bins;
-    uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
-    auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
-      return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
-    };
-    for (int g0 = tid; g0 < n_groups; g0 += 4 * T) {
-      unsigned w[4][3];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int g = g0 + u * T;
-        if (g < n_groups) {
-          const int r = g / groups_per_row, c = g - r * groups_per_row;
-          const unsigned* src = reinterpret_cast<const unsigned*>(ccam->image + size_t(ctile.y0 + r) * ccam->pitch +
-                                                                  size_t(ctile.x0 + 4 * c) * 3u);
-          w[u][0] = __ldg(src); w[u][1] = __ldg(src + 1); w[u][2] = __ldg(src + 2);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int g = g0 + u * T;
-        if (g < n_groups) {
-          const unsigned w0 = w[u][0], w1 = w[u][1], w2 = w[u][2];
-          const unsigned i0 = bin(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
-          const unsigned i1 = bin(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
-          const unsigned i2 = bin((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
-          const unsigned i3 = bin((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
-          out[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
-        }
+  bool depth_ready = dtile.w <= 0;
+  bool ctile_ready = ctile.w <= 0 || !tma;
+  if (!tma) {
+    if (dtile.w > 0) {
+      if (warp == kW - 1) {  // a point warp issues the depth rows while the others convert the colour tile
+        const unsigned row_bytes = unsigned(dtile.w) * 2u;
+        if (lane == 0) MbarExpectTx(&sh.depth_bar, row_bytes * unsigned(dtile.h));
+        __syncwarp();
+        for (int r = lane; r < dtile.h; r += 32)
+          BulkCopyG2S(dyn + dtile.offset + size_t(r) * row_bytes,
+                      dcam->image + size_t(dtile.y0 + r) * dcam->pitch + size_t(dtile.x0) * 2u, row_bytes, &sh.depth_bar);
       }
     }
+    if (ctile.w > 0) {
+      const int groups_per_row = ctile.w >> 2;
+      const int n_groups = groups_per_row * ctile.h;
+      const int bs = body.rp.bitshift, nb = body.rp.n_bins;
+      uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
+      auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
+        return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
+      };
+      for (int g0 = tid; g0 < n_groups; g0 += 4 * T) {
+        unsigned w[4][3];
+  #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u * T;
+          if (g < n_groups) {
+            const int r = g / groups_per_row, c = g - r * groups_per_row;
+            const unsigned* src = reinterpret_cast<const unsigned*>(ccam->image + size_t(ctile.y0 + r) * ccam->pitch +
+                                                                    size_t(ctile.x0 + 4 * c) * 3u);
+            w[u][0] = __ldg(src); w[u][1] = __ldg(src + 1); w[u][2] = __ldg(src + 2);
+          }
+        }
+  #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int g = g0 + u * T;
+          if (g < n_groups) {
+            const unsigned w0 = w[u][0], w1 = w[u][1], w2 = w[u][2];
+            const unsigned i0 = bin(w0 & 0xffu, (w0 >> 8) & 0xffu, (w0 >> 16) & 0xffu);
+            const unsigned i1 = bin(w0 >> 24, w1 & 0xffu, (w1 >> 8) & 0xffu);
+            const unsigned i2 = bin((w1 >> 16) & 0xffu, w1 >> 24, w2 & 0xffu);
+            const unsigned i3 = bin((w2 >> 8) & 0xffu, (w2 >> 16) & 0xffu, w2 >> 24);
+            out[g] = make_uint2(i0 | (i1 << 16), i2 | (i3 << 16));
+          }
+        }
+      }
+    }
+    __syncthreads();  // colour tile complete
   }
-  __syncthreads();  // colour tile complete; also orders the initial pose products before their first readers
 
   LineRegs L;
   PointState P;
@@ -631,6 +729,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
                               __ldg(rmodel->view_scalars + view_r), rmodel->max_view_scalar, rmodel->n_points);
       n_lines = min(n_lines, min(lcap, kGroup));
       if (!lut_ready) { MbarWait(&sh.lut_bar, 0); lut_ready = true; }
+      if (!ctile_ready) { MbarWait(&sh.ctile_bar, 0); ctile_ready = true; }
       const float4* pts = rmodel->points + size_t(view_r) * rmodel->n_points * 2;
       L.valid = false;
       if (item < n_lines) {
@@ -761,6 +860,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   }
   if (need_lut && !lut_ready) MbarWait(&sh.lut_bar, 0);  // never leave with a bulk copy in flight
   if (!depth_ready) MbarWait(&sh.depth_bar, 0);
+  if (!ctile_ready) MbarWait(&sh.ctile_bar, 0);
 }
 
 }  // namespace m3tb

@@ -149,6 +149,30 @@ def parity_check(ctx, wl, n_sample=4):
             "pose_change_of_the_step_m": float(moved.min())}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's host threads (and therefore, by first touch, the pinned frame buffers it allocates next) to the
+    NUMA node its GPU hangs off. Unbound, the 8 ranks' zero-copy frame reads cross the socket interconnect for half of
+    the GPUs (GPUs 0-3 on node 0, 4-7 on node 1 on the 8-GPU boxes) and the end-to-end step time rises from 0.71 to
+    0.99 ms at N = 8 (SCALE_r01). Returns a description for the JSON line."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "note": "single NUMA node / not reported"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:  # no sysfs, no permission: run unbound
+        return {"numa_node": None, "note": f"unbound ({type(e).__name__})"}
+
+
 def build_workload(args, rank, n_shards=1):
     """Bodies [rank*nb, (rank+n_shards)*nb) of the weak-scaled job (nb bodies per GPU)."""
     pkg = importlib.import_module("3dobjecttracking_b200")
@@ -339,6 +363,7 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device - the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else {"numa_node": None, "note": "single rank: unbound"}
 
     def barrier():
         if world > 1:
@@ -409,9 +434,11 @@ def run_b200(args):
         d2h = nb * 48
         out_poses = torch.empty((nb, 12), dtype=torch.float32).pin_memory()
         gathered = None
-        if world > 1:  # persistent buffers of the per-frame pose all-gather
+        if world > 1:  # persistent buffers of the per-frame pose all-gather, on its own stream: the
+            # tracking stream never queues behind the collective (r01: it was enqueued on the compute stream)
             poses_dev = torch.empty((nb, 12), dtype=torch.float32, device=dev)
             gathered = torch.empty((world * nb, 12), dtype=torch.float32, device=dev)
+            gather_stream = torch.cuda.Stream(device=dev)
 
         def hand_over_frames():
             # Camera::UpdateImage for every camera (pinned frames: pointers only) + the optional prefetch: the ROI
@@ -431,8 +458,9 @@ def run_b200(args):
             hand_over_frames()
             ctx._ck(ctx.L.m3tb_get_poses(ctx.h, 0, nb, capi._p(out_poses.numpy())))  # synchronises the stream
             if world > 1:  # publish: NCCL all-gather of the solved poses, once per frame, not waited for by the next step
-                poses_dev.copy_(out_poses, non_blocking=True)
-                dist.all_gather_into_tensor(gathered, poses_dev)
+                with torch.cuda.stream(gather_stream):
+                    poses_dev.copy_(out_poses, non_blocking=True)  # out_poses is complete: m3tb_get_poses synchronised
+                    dist.all_gather_into_tensor(gathered, poses_dev)
 
         hand_over_frames()  # frame 0
         for _ in range(max(args.warmup, 3)):
@@ -446,6 +474,8 @@ def run_b200(args):
             e2e_step()
             step_ms.append(1e3 * (time.perf_counter() - ts))
         ctx.synchronize()  # includes the side stream: K steps tracked, K frame sets ingested inside the timed region
+        if world > 1:
+            gather_stream.synchronize()  # ... and K pose all-gathers completed
         if os.environ.get("BENCH_DEBUG_E2E"):
             print(f"[e2e debug] rank {rank}: per-step ms " + " ".join(f"{v:.2f}" for v in step_ms), file=sys.stderr, flush=True)
         torch.cuda.synchronize(dev)
@@ -460,7 +490,7 @@ def run_b200(args):
             h2d = moved + nb * 48
         e2e = {"value": world * its_per_step / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
-               "host_frame_bytes_per_step": int(full_frame_bytes),
+               "host_frame_bytes_per_step": int(full_frame_bytes), "host_binding": numa,
                "ingest": ("pinned frames, ROI-only zero-copy fetch (k_ingest): only the rectangle each body can touch "
                           "crosses PCIe; prefetched one frame ahead on a side stream (m3tb_prefetch_frames), so the copy "
                           "of step t+1's frames overlaps the tracking of step t" if moved > 0 else "full-frame copies")}
