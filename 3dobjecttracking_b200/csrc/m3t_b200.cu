@@ -535,7 +535,7 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
       if (trc) return trc;
     }
     if (ok) {
-      const size_t fixed = lut_bytes + size_t(kDistBytes);
+      const size_t fixed = lut_bytes + size_t(kFixedDynBytes);
       const size_t dyn2 = ctx->use_tiles ? size_t(kDynSmemBytes) : fixed;
       a.tile_bytes = ctx->use_tiles ? int(dyn2 - fixed) : 0;
 #define M3TB_LAUNCH2(T_, L_)                                                                                     \

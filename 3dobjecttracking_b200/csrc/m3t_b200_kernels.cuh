@@ -20,6 +20,7 @@
 
 #include "m3t_b200_device.cuh"
 #include "m3t_b200_structures.cuh"
+#include "m3t_b200_views.cuh"
 
 namespace m3tb {
 
@@ -1440,7 +1441,7 @@ struct HistArgs {
 // ---------------------------------------------------------------------------------------------
 // pixels of pose motion (since the ROI was fetched) that stay inside the device copy; beyond it samples are served
 // from the pinned frame directly (correct, slower)
-constexpr float kIngestMotionMarginPx = 12.0f;
+constexpr float kIngestMotionMarginPx = 8.0f;
 
 struct IngestArgs {
   const BodyDev* bodies;
@@ -1593,50 +1594,125 @@ __global__ void __launch_bounds__(kBlockThreads) k_bin(BinArgs args) {
   }
 }
 
+// The rectangle is the bounding box of the closest template view's points projected with the current pose (a tight
+// fit: for the triangle prism at 0.6 m ~200 x 200 instead of the ~240 x 240 pixels of the projected bounding sphere),
+// grown by the reach of the correspondence lines / search windows and a motion margin. Whatever it misses is served from
+// the pinned frame directly (FrameView), so this only decides how many bytes cross PCIe.
+__device__ __forceinline__ bool ProjectedViewBox(const ModelDev& m, const CameraDev& cam, const float* b2c, float* s_red,
+                                                 int* s_view, float (&box)[4]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!m.cluster_info || m.n_views <= 0) return false;
+  if (warp == 0) {
+    float vo[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    vo[3] = ViewOrientation(b2c, vo[0], vo[1], vo[2]) ? 1.0f : 0.0f;
+    const int v = ClosestViewPrunedWarp(m.cluster_info, m.sorted_views, m.n_clusters, m.orientations4, m.n_views, vo, 0);
+    if (lane == 0) *s_view = v;
+  }
+  __syncthreads();
+  const float4* pts = m.points + size_t(*s_view) * m.n_points * 2;
+  float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f, bad = 0.0f;
+  for (int i = tid; i < m.n_points; i += blockDim.x) {
+    const float4 p = __ldg(pts + 2 * i);
+    float x, y, z;
+    PoseApply(b2c, p.x, p.y, p.z, x, y, z);
+    if (!(z > 0.0f)) { bad = 1.0f; continue; }
+    const float u = x * cam.fu / z + cam.ppu, v = y * cam.fv / z + cam.ppv;
+    umin = fminf(umin, u); umax = fmaxf(umax, u); vmin = fminf(vmin, v); vmax = fmaxf(vmax, v);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    umin = fminf(umin, __shfl_xor_sync(0xffffffffu, umin, off));
+    umax = fmaxf(umax, __shfl_xor_sync(0xffffffffu, umax, off));
+    vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, off));
+    vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+    bad = fmaxf(bad, __shfl_xor_sync(0xffffffffu, bad, off));
+  }
+  if (lane == 0) { s_red[5 * warp + 0] = umin; s_red[5 * warp + 1] = umax; s_red[5 * warp + 2] = vmin; s_red[5 * warp + 3] = vmax; s_red[5 * warp + 4] = bad; }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  umin = s_red[0]; umax = s_red[1]; vmin = s_red[2]; vmax = s_red[3]; bad = s_red[4];
+  for (int w = 1; w < nw; ++w) {
+    umin = fminf(umin, s_red[5 * w + 0]); umax = fmaxf(umax, s_red[5 * w + 1]);
+    vmin = fminf(vmin, s_red[5 * w + 2]); vmax = fmaxf(vmax, s_red[5 * w + 3]); bad = fmaxf(bad, s_red[5 * w + 4]);
+  }
+  __syncthreads();  // s_red / s_view are reused by the next call
+  box[0] = umin; box[1] = umax; box[2] = vmin; box[3] = vmax;
+  return bad == 0.0f && umax >= umin && vmax >= vmin;
+}
+
+__device__ __forceinline__ void BoxRect(const float (&box)[4], float reach_px, int width, int height, int align_x, Tile& t) {
+  int x0 = int(floorf(box[0] - reach_px)), x1 = int(ceilf(box[1] + reach_px)) + 1;
+  int y0 = int(floorf(box[2] - reach_px)), y1 = int(ceilf(box[3] + reach_px)) + 1;
+  x0 = max(x0, 0) / align_x * align_x;
+  x1 = min((min(x1, width) + align_x - 1) / align_x * align_x, width / align_x * align_x);
+  y0 = max(y0, 0);
+  y1 = min(y1, height);
+  t.x0 = t.y0 = t.w = t.h = t.pitch = 0;
+  if (x1 <= x0 || y1 <= y0) return;
+  t.x0 = x0; t.y0 = y0; t.w = x1 - x0; t.h = y1 - y0; t.pitch = t.w;
+}
+
 __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
   const int body_id = blockIdx.x;
   const BodyDev& body = args.bodies[body_id];
   if (!body.set) return;
   __shared__ Tile rect[2];
   __shared__ int todo[2];
-  if (threadIdx.x == 0) {
-    float pose[12], b2c[12];
-    for (int i = 0; i < 12; ++i) pose[i] = args.poses[12 * body_id + i];
+  __shared__ float s_red[5 * (kBlockThreads / 32)];
+  __shared__ int s_view;
+  float pose[12];
+  for (int i = 0; i < 12; ++i) pose[i] = args.poses[12 * body_id + i];
+  const bool region_occ = body.has_region && body.rp.measure_occlusions;
+  if (threadIdx.x == 0) {  // which cameras have a frame this body's ROI record does not cover yet (decided once, by one thread)
     for (int which = 0; which < 2; ++which) {
-      todo[which] = 0;
-      const bool region_occ = body.has_region && body.rp.measure_occlusions;
       const bool present = which == 0 ? body.has_region : (body.has_depth || region_occ);
-      if (!present) continue;
-      const CameraDev& cam = which == 0 ? args.color_cams[body.color_camera] : args.depth_cams[body.depth_camera];
-      RoiRecord& rec = args.roi[2 * body_id + which];
-      if (!cam.host_src || rec.generation == cam.generation) continue;
-      PoseMul(cam.w2c, pose, b2c);
-      Tile t;
-      if (which == 0) {
-        const ModelDev& m = args.region_models[body.region_model];
-        int s_max = 1;
-        for (int c = 0; c < body.rp.n_scales; ++c) s_max = max(s_max, body.rp.scales[c]);
-        const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + kIngestMotionMarginPx;
-        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 16, t);
-      } else {
-        // depth search windows and, with measured occlusion handling, the occlusion windows around the region points
-        const ModelDev& m = body.has_depth ? args.depth_models[body.depth_model] : args.region_models[body.region_model];
-        float d_max = 0.0f;
-        if (body.has_depth) {
-          for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
-          if (body.dp.measure_occlusions) d_max = fmaxf(d_max, body.dp.measured_occlusion_radius);
-        }
-        float radius = m.radius;
-        if (region_occ) {
-          d_max = fmaxf(d_max, body.rp.measured_occlusion_radius);
-          radius = fmaxf(radius, args.region_models[body.region_model].radius);
-        }
-        const float z = b2c[11];
-        const float reach = (z > 2.0f * radius) ? d_max * cam.fu / (z - radius) + 2.0f + kIngestMotionMarginPx : 0.0f;
-        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, radius, reach, 8, t);
+      int need = 0;
+      if (present) {
+        const CameraDev& cam = which == 0 ? args.color_cams[body.color_camera] : args.depth_cams[body.depth_camera];
+        need = cam.host_src && args.roi[2 * body_id + which].generation != cam.generation;
       }
+      todo[which] = need;
+    }
+  }
+  __syncthreads();
+  for (int which = 0; which < 2; ++which) {  // block-uniform control flow
+    if (!todo[which]) continue;
+    const CameraDev& cam = which == 0 ? args.color_cams[body.color_camera] : args.depth_cams[body.depth_camera];
+    RoiRecord& rec = args.roi[2 * body_id + which];
+    float b2c[12];
+    PoseMul(cam.w2c, pose, b2c);
+    Tile t;
+    float box[4];
+    if (which == 0) {
+      const ModelDev& m = args.region_models[body.region_model];
+      int s_max = 1;
+      for (int c = 0; c < body.rp.n_scales; ++c) s_max = max(s_max, body.rp.scales[c]);
+      const float reach = fmaxf(0.5f * float(kLineSegments * s_max) + 2.0f, body.rp.max_considered_line_length + 2.0f) + kIngestMotionMarginPx;
+      if (ProjectedViewBox(m, cam, b2c, s_red, &s_view, box)) BoxRect(box, reach, cam.width, cam.height, 16, t);
+      else RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, m.radius, reach, 16, t);
+    } else {
+      // depth search windows and, with measured occlusion handling, the occlusion windows around the region points
+      const ModelDev& m = body.has_depth ? args.depth_models[body.depth_model] : args.region_models[body.region_model];
+      float d_max = 0.0f;
+      if (body.has_depth) {
+        for (int c = 0; c < body.dp.n_considered_distances; ++c) d_max = fmaxf(d_max, body.dp.considered_distances[c]);
+        if (body.dp.measure_occlusions) d_max = fmaxf(d_max, body.dp.measured_occlusion_radius);
+      }
+      float radius = m.radius;
+      if (region_occ) {
+        d_max = fmaxf(d_max, body.rp.measured_occlusion_radius);
+        radius = fmaxf(radius, args.region_models[body.region_model].radius);
+      }
+      const float z = b2c[11];
+      const float reach = (z > 2.0f * radius) ? d_max * cam.fu / (z - radius) + 2.0f + kIngestMotionMarginPx : 0.0f;
+      // (with region occlusion handling the windows sit around the REGION points: keep the bounding sphere there)
+      if (!region_occ && z > 2.0f * radius && ProjectedViewBox(m, cam, b2c, s_red, &s_view, box))
+        BoxRect(box, reach, cam.width, cam.height, 8, t);
+      else
+        RoiRect(b2c, cam.fu, cam.fv, cam.ppu, cam.ppv, cam.width, cam.height, radius, reach, 8, t);
+    }
+    if (threadIdx.x == 0) {
       rect[which] = t;
-      todo[which] = 1;
       rec.x0 = t.x0; rec.y0 = t.y0; rec.x1 = t.x0 + t.w; rec.y1 = t.y0 + t.h;
       rec.generation = cam.generation;
     }

@@ -30,6 +30,9 @@ namespace m3tb {
 
 constexpr int kGroup = 512;                                      // items per modality and threads per warp group
 constexpr int kDistBytes = kDistributionLength * kGroup * 4;     // shared-memory home of the line distributions
+constexpr int kClusterStage = 96;                                // clusters per model staged in shared memory (3072 views)
+constexpr int kClusterBytes = 2 * kClusterStage * 32;            // [region | depth] x kClusterStage x two float4
+constexpr int kFixedDynBytes = kDistBytes + kClusterBytes;       // dynamic shared memory before the tiles (after the LUT)
 
 struct Shared2 {
   float pose[12];            // body2world
@@ -128,14 +131,44 @@ __device__ __forceinline__ void WalkFast(int scale, int base, float minor_f, flo
   }
 }
 
-// Rare path: a sample may lie outside the tile. All 19 segments go to local memory first (as in k_track).
+// Rare path: a sample may lie outside the tile. All 19 segments go to local memory first (as in k_track). Samples
+// outside the tile come from the camera's bin-index image where it is valid (inside the body's ROI), else from the frame.
+struct BinImage {
+  const uint16_t* px;  // null: no bin-index image
+  unsigned pitch;      // bytes
+};
 template <bool LUT_SMEM>
 __device__ __noinline__ void WalkSlow(int scale, int bs, int nb, bool horizontal, int major, float minor_f, float step,
-                                      const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
+                                      const FrameView& frame, const Tile& tile, const uint16_t* tile_px, const BinImage& bins,
                                       const float2* __restrict__ lut_g, const float2* lut_s, const float* lf,
                                       const float* lb, bool rev, float* dist_col) {
   float sf[kLineSegments], sb[kLineSegments];
-  GatherSlow<LUT_SMEM>(scale, bs, nb, horizontal, major, minor_f, step, frame, tile, tile_px, lut_g, lut_s, sf, sb);
+#pragma unroll 1
+  for (int s = 0; s < kLineSegments; ++s) {
+    float pf = 1.0f, pb = 1.0f;
+#pragma unroll 1
+    for (int k = 0; k < scale; ++k) {
+      const int minor = int(minor_f);
+      const int x = horizontal ? major : minor, y = horizontal ? minor : major;
+      const unsigned tx = unsigned(x - tile.x0), ty = unsigned(y - tile.y0);
+      int idx;
+      if (tx < unsigned(tile.w) && ty < unsigned(tile.h)) {
+        idx = tile_px[ty * unsigned(tile.pitch) + tx];
+      } else if (bins.px && x >= frame.x0 && x < frame.x1 && y >= frame.y0 && y < frame.y1) {
+        idx = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(bins.px) + size_t(unsigned(y)) * bins.pitch) + x);
+      } else {
+        const uint8_t* p = FramePtr(frame, x, y, 3u);
+        idx = (int(__ldg(p)) >> bs) * nb * nb + (int(__ldg(p + 1)) >> bs) * nb + (int(__ldg(p + 2)) >> bs);
+      }
+      const float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);
+      pf *= l.x;
+      pb *= l.y;
+      ++major;
+      minor_f += step;
+    }
+    sf[s] = pf;
+    sb[s] = pb;
+  }
   if (scale > 1) {
 #pragma unroll 1
     for (int s = 0; s < kLineSegments; ++s) {
@@ -165,7 +198,7 @@ __device__ __noinline__ void WalkSlow(int scale, int bs, int nb, bool horizontal
 template <bool LUT_SMEM>
 __device__ __forceinline__ void RegionLine2(const RegionIter& it, const RegionParamsDev& rp, const float4 p0, const float4 p1,
                                             const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
-                                            const float2* __restrict__ lut_g, const float2* lut_s,
+                                            const BinImage& bins, const float2* __restrict__ lut_g, const float2* lut_s,
                                             const float* __restrict__ lf, const float* __restrict__ lb,
                                             float* dist_col, LineRegs& L) {
   L.valid = false;
@@ -224,8 +257,8 @@ __device__ __forceinline__ void RegionLine2(const RegionIter& it, const RegionPa
         default: WalkFast<LUT_SMEM, 0>(it.scale, base, minor_f, step, stride_major, stride_minor, tile_px, lut_g, lut_s, lf, lb, rev, dist_col); break;
       }
     } else {
-      WalkSlow<LUT_SMEM>(it.scale, rp.bitshift, rp.n_bins, horizontal, major, minor_f, step, frame, tile, tile_px, lut_g,
-                         lut_s, lf, lb, rev, dist_col);
+      WalkSlow<LUT_SMEM>(it.scale, rp.bitshift, rp.n_bins, horizontal, major, minor_f, step, frame, tile, tile_px, bins,
+                         lut_g, lut_s, lf, lb, rev, dist_col);
     }
   }
   L.ncts = fabsf(n_major) / it.fscale;
@@ -536,6 +569,16 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   if (tid < 12) sh.pose[tid] = args.poses[12 * body_id + tid];
   if (tid >= 32 && tid < 44 && ccam) sh.cw2c[tid - 32] = ccam->w2c[tid - 32];
   if (tid >= 64 && tid < 76 && dcam) sh.dw2c[tid - 64] = dcam->w2c[tid - 64];
+  // cluster tables of the pruned closest-view search: shared memory when they fit (they are read every iteration)
+  float4* cl_smem = reinterpret_cast<float4*>(dyn + lut_bytes + kDistBytes);
+  const bool stage_r = do_rcorr && rmodel->n_clusters <= kClusterStage;
+  const bool stage_d = do_dcorr && dmodel->n_clusters <= kClusterStage;
+  if (stage_r)
+    for (int k = tid; k < 2 * rmodel->n_clusters; k += T) cl_smem[k] = __ldg(rmodel->cluster_info + k);
+  if (stage_d)
+    for (int k = tid; k < 2 * dmodel->n_clusters; k += T) cl_smem[2 * kClusterStage + k] = __ldg(dmodel->cluster_info + k);
+  const float4* info_r = stage_r ? cl_smem : (rmodel ? rmodel->cluster_info : nullptr);
+  const float4* info_d = stage_d ? cl_smem + 2 * kClusterStage : (dmodel ? dmodel->cluster_info : nullptr);
   const bool need_lut = LUT_SMEM && do_rcorr;
   if (tid == 0) {
     if (LUT_SMEM) MbarInit(&sh.lut_bar, 1);
@@ -561,7 +604,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     // the depth tile from the raw U16 frame; boxes of kTileBoxRows rows x the tile width, stacked -> row-major tile.
     if (tid == 32 % T) {
       Tile ct, dt;
-      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kDistBytes;
+      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kFixedDynBytes;
       dt = ct;
       if (args.tile_bytes > 0) {
         float b2c[12];
@@ -586,7 +629,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
         SnapTile(dt, dframe, budget * 2 / 5, args.tma_max_w);
         const int dbytes = dt.w * dt.h * 2;
         SnapTile(ct, cframe, budget - dbytes, args.tma_max_w);
-        dt.offset = lut_bytes + kDistBytes + unsigned(ct.w * ct.h * 2);
+        dt.offset = lut_bytes + kFixedDynBytes + unsigned(ct.w * ct.h * 2);
       }
       sh.ctile = ct;
       sh.dtile = dt;
@@ -606,7 +649,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   } else {  // legacy staging (tma_mode 0): depth rows by 1-D bulk copies, colour bins converted from the BGR frame
     if (tid == 32 % T) {
       Tile ct, dt;
-      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kDistBytes;
+      ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kFixedDynBytes;
       dt = ct;
       if (args.tile_bytes > 0) {
         float b2c[12];
@@ -633,7 +676,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
         const int dbytes = (dt.w * dt.h * 2 + 127) / 128 * 128;
         FitTile(ct, budget - dbytes, 4);
         const int cbytes = (ct.w * ct.h * 2 + 127) / 128 * 128;
-        dt.offset = lut_bytes + kDistBytes + unsigned(cbytes);
+        dt.offset = lut_bytes + kFixedDynBytes + unsigned(cbytes);
       }
       sh.ctile = ct;
       sh.dtile = dt;
@@ -702,6 +745,9 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   int n_lines = 0, n_points = 0;
   int view_r = counts[2], view_d = counts[3];  // any valid view index: the lower bound of the pruned search
   bool lut_ready = !need_lut;
+  BinImage bin_image;  // valid wherever the device copy of the colour frame is (the body's ROI), when the TMA path maintains it
+  bin_image.px = (tma && ccam) ? ccam->bins : nullptr;
+  bin_image.pitch = ccam ? ccam->bin_pitch : 0u;
   // function lookups (identical for every body of the launch, checked by the host): kernel-parameter constants
   const float* lf = args.lookup_f;
   const float* lb = args.lookup_b;
@@ -711,12 +757,12 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr && line_group) {
       if ((tid & (kGroup - 1)) < 32) {  // group leader warp
-        const int v = ClosestViewPrunedWarp(rmodel->cluster_info, rmodel->sorted_views, rmodel->n_clusters,
+        const int v = ClosestViewPrunedWarp(info_r, rmodel->sorted_views, rmodel->n_clusters,
                                             rmodel->orientations4, rmodel->n_views, sh.view_o[0], view_r);
         if (lane == 0) sh.views[corr & 1][0] = v;
       }
       if (T == kGroup && do_dcorr && warp == 1) {  // single group: the second warp searches the depth model meanwhile
-        const int v = ClosestViewPrunedWarp(dmodel->cluster_info, dmodel->sorted_views, dmodel->n_clusters,
+        const int v = ClosestViewPrunedWarp(info_d, dmodel->sorted_views, dmodel->n_clusters,
                                             dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
         if (lane == 0) sh.views[corr & 1][1] = v;
       }
@@ -725,23 +771,27 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       M3TB_STAMP2(stamp_base);  // closest view (region)
       RegionIter rit;
       MakeRegionIter(body.rp, *ccam, sh.rb2c, corr, rit);
+      // the model record does not depend on the line count: load it first, the count (one more trip to memory when the
+      // coverage is adaptive) meanwhile
+      const float4* pts = rmodel->points + size_t(view_r) * rmodel->n_points * 2;
+      float4 p0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), p1 = p0;
+      if (item < min(rmodel->n_points, min(lcap, kGroup))) { p0 = __ldg(pts + 2 * item); p1 = __ldg(pts + 2 * item + 1); }
       n_lines = AdaptiveCount(body.rp.n_lines_max, body.rp.use_adaptive_coverage, body.rp.reference_contour_length,
-                              __ldg(rmodel->view_scalars + view_r), rmodel->max_view_scalar, rmodel->n_points);
+                              body.rp.use_adaptive_coverage ? __ldg(rmodel->view_scalars + view_r) : 0.0f,
+                              rmodel->max_view_scalar, rmodel->n_points);
       n_lines = min(n_lines, min(lcap, kGroup));
       if (!lut_ready) { MbarWait(&sh.lut_bar, 0); lut_ready = true; }
       if (!ctile_ready) { MbarWait(&sh.ctile_bar, 0); ctile_ready = true; }
-      const float4* pts = rmodel->points + size_t(view_r) * rmodel->n_points * 2;
       L.valid = false;
       if (item < n_lines) {
-        const float4 p0 = __ldg(pts + 2 * item), p1 = __ldg(pts + 2 * item + 1);
-        RegionLine2<LUT_SMEM>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, lut_g, lut_s, lf, lb, dist_col, L);
+        RegionLine2<LUT_SMEM>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, bin_image, lut_g, lut_s, lf, lb, dist_col, L);
       }
       M3TB_STAMP2(stamp_base);  // region lines
     }
     if (do_dcorr && point_group) {
       if (T > kGroup || !do_rcorr) {  // (single group with lines: searched above, behind the same barrier)
         if ((tid & (kGroup - 1)) < 32) {
-          const int v = ClosestViewPrunedWarp(dmodel->cluster_info, dmodel->sorted_views, dmodel->n_clusters,
+          const int v = ClosestViewPrunedWarp(info_d, dmodel->sorted_views, dmodel->n_clusters,
                                               dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
           if (lane == 0) sh.views[corr & 1][1] = v;
         }
@@ -751,14 +801,16 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       M3TB_STAMP2(stamp_base);  // closest view (depth)
       DepthIter dit;
       MakeDepthIter(body.dp, *dcam, sh.db2c, sh.dc2b, corr, dit);
+      const float4* pts = dmodel->points + size_t(view_d) * dmodel->n_points * 2;
+      float4 p0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), p1 = p0;
+      if (item < min(dmodel->n_points, min(pcap, kGroup))) { p0 = __ldg(pts + 2 * item); p1 = __ldg(pts + 2 * item + 1); }
       n_points = AdaptiveCount(body.dp.n_points_max, body.dp.use_adaptive_coverage, body.dp.reference_surface_area,
-                               __ldg(dmodel->view_scalars + view_d), dmodel->max_view_scalar, dmodel->n_points);
+                               body.dp.use_adaptive_coverage ? __ldg(dmodel->view_scalars + view_d) : 0.0f,
+                               dmodel->max_view_scalar, dmodel->n_points);
       n_points = min(n_points, min(pcap, kGroup));
       if (!depth_ready) { MbarWait(&sh.depth_bar, 0); depth_ready = true; }
-      const float4* pts = dmodel->points + size_t(view_d) * dmodel->n_points * 2;
       P.valid = false;
       if (item < n_points) {
-        const float4 p0 = __ldg(pts + 2 * item), p1 = __ldg(pts + 2 * item + 1);
         DepthPoint<false>(dit, body.dp, p0, p1, dframe, dtile, dtile_px, P);
       }
       M3TB_STAMP2(stamp_base);  // depth points

@@ -118,7 +118,12 @@ def parity_check(ctx, wl, n_sample=4):
     import oracle_py
     n = min(n_sample, wl.n_bodies)
     orc = oracle_py.OracleTracker(wl, rotation_mode=oracle_py.ROTATION_POLAR, exp_mode=oracle_py.EXP_PADE, n_threads=n)
+    # second realisation of the same algorithm (linear rotation block, Rodrigues): where the two oracle modes end an
+    # iteration more than the tolerance apart, a 1e-7 difference has flipped an integer decision of the algorithm (an
+    # int() of a line coordinate, a histogram bin pair, a template view) and the pair says nothing about the CUDA path
+    alt = oracle_py.OracleTracker(wl, rotation_mode=oracle_py.ROTATION_LINEAR, exp_mode=oracle_py.EXP_RODRIGUES, n_threads=n)
     orc.start_modalities(0)
+    alt.start_modalities(0)
 
     def err(p, q):
         p, q = np.asarray(p, np.float64).reshape(-1, 3, 4), np.asarray(q, np.float64).reshape(-1, 3, 4)
@@ -129,13 +134,22 @@ def parity_check(ctx, wl, n_sample=4):
         return dt, np.arctan2(sk, c)
 
     worst_m = worst_rad = 0.0
+    compared = excluded = 0
     orc.set_poses(wl.start_body2world)
     for corr in range(wl.n_corr_iterations):
-        ctx.set_poses(orc.get_poses())
+        start = orc.get_poses()
+        alt.set_poses(start)
+        ctx.set_poses(start)
         ctx.corr_iteration(0, corr, wl.n_update_iterations)
         orc.tracking_step(0, n_corr=corr + 1, corr_begin=corr, first=0, count=n)
+        alt.tracking_step(0, n_corr=corr + 1, corr_begin=corr, first=0, count=n)
+        st, sr = err(alt.get_poses()[:n], orc.get_poses()[:n])
+        ok = (st < 1e-4) & (sr < 1e-4)
         dt, dr = err(ctx.get_poses(0, n), orc.get_poses()[:n])
-        worst_m, worst_rad = max(worst_m, float(dt.max())), max(worst_rad, float(dr.max()))
+        compared += int(ok.sum())
+        excluded += int((~ok).sum())
+        if ok.any():
+            worst_m, worst_rad = max(worst_m, float(dt[ok].max())), max(worst_rad, float(dr[ok].max()))
     ctx.set_poses(wl.start_body2world)
     ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
     orc.set_poses(wl.start_body2world)
@@ -144,33 +158,10 @@ def parity_check(ctx, wl, n_sample=4):
     moved, _ = err(ctx.get_poses(0, n), wl.start_body2world[:n])
     return {"bodies": int(n), "oracle": "CPU restatement, reference-faithful mode (polar rotation, Pade exp)",
             "per_iteration_max_m": worst_m, "per_iteration_max_rad": worst_rad, "tolerance": 1e-4,
-            "ok": bool(worst_m < 1e-4 and worst_rad < 1e-4),
+            "body_iterations_compared": compared, "body_iterations_excluded_oracle_modes_disagree": excluded,
+            "ok": bool(compared > 0 and worst_m < 1e-4 and worst_rad < 1e-4),
             "free_running_step_max_m": float(dt.max()), "free_running_step_max_rad": float(dr.max()),
             "pose_change_of_the_step_m": float(moved.min())}
-
-
-def bind_to_gpu_numa_node(torch, local_rank):
-    """Pin this rank's host threads (and therefore, by first touch, the pinned frame buffers it allocates next) to the
-    NUMA node its GPU hangs off. Unbound, the 8 ranks' zero-copy frame reads cross the socket interconnect for half of
-    the GPUs (GPUs 0-3 on node 0, 4-7 on node 1 on the 8-GPU boxes) and the end-to-end step time rises from 0.71 to
-    0.99 ms at N = 8 (SCALE_r01). Returns a description for the JSON line."""
-    try:
-        prop = torch.cuda.get_device_properties(local_rank)
-        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
-        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
-        if node < 0:
-            return {"numa_node": None, "note": "single NUMA node / not reported"}
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            a, _, b = part.partition("-")
-            cpus.update(range(int(a), int(b or a) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return {"numa_node": node, "note": "no allowed CPU on that node"}
-        os.sched_setaffinity(0, cpus)
-        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
-    except Exception as e:  # no sysfs, no permission: run unbound
-        return {"numa_node": None, "note": f"unbound ({type(e).__name__})"}
 
 
 def build_workload(args, rank, n_shards=1):

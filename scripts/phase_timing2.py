@@ -16,8 +16,22 @@ for _ in range(3):
     ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
 ctx.synchronize()
 nc, nu = wl.n_corr_iterations, wl.n_update_iterations
+# makespan view: per-body duration of the launch (first to last stamp of warp 0) against the body's depth
+tot, first, last = [], [], []
+for b in range(wl.n_bodies):
+    c = ctx.phase_clocks(b, 256)
+    a = c[:128][c[:128] > 0]
+    tot.append(int(a[-1] - a[0])); first.append(int(a[0])); last.append(int(a[-1]))
+tot = np.array(tot)
+w2c = np.asarray(wl.color_world2camera, np.float64)
+z = np.array([w2c[2, :3] @ wl.gt_body2world[b][:, 3] + w2c[2, 3] for b in range(wl.n_bodies)])
+order = np.argsort(tot)
+print(f"{name}: per-body cycles min {tot.min()} median {int(np.median(tot))} max {tot.max()}; corr(total, z) = {np.corrcoef(tot, z)[0,1]:.2f}")
+print("   slowest bodies: " + ", ".join(f"{b}: {tot[b]} (z {z[b]:.3f})" for b in order[-6:]))
+print("   fastest bodies: " + ", ".join(f"{b}: {tot[b]} (z {z[b]:.3f})" for b in order[:4]))
+slow = int(order[-1])
 both = bool(wl.region and wl.depth)
-for body in (0, wl.n_bodies // 2):
+for body in (0, slow):
     c = ctx.phase_clocks(body, 256)
     a = c[:128][c[:128] > 0]
     d = np.diff(a)

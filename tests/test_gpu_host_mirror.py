@@ -24,8 +24,8 @@ def test_cpp_tracker_fused_and_object_wise_agree(pkg):
     start = np.array(out["start"], np.float32).reshape(-1, 3, 4)
     # Tracker::ExecuteTrackingStep = 1 fused launch (+ StartModalities + CalculateResults histogram launches);
     # the object-wise path issues one batched launch per phase, not one per object
-    assert out["launches_fused"] == 3
-    assert out["launches_object_wise"] == 2 + 7 * (2 + 2 * 3)
+    assert out["launches_fused"] in (3, 4)   # + k_bin (bin-index images of the freshly copied frames) on the k_track2 path
+    assert out["launches_object_wise"] in (2 + 7 * (2 + 2 * 3), 3 + 7 * (2 + 2 * 3))
     dt, dr = pose_error(fused, obj)
     assert dt.max() < 1e-5 and dr.max() < 1e-5, (dt, dr)
     moved_t, moved_r = pose_error(fused, start)
