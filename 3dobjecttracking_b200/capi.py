@@ -98,9 +98,11 @@ def lib():
     """Loads libm3t_b200.so; builds it in-tree with nvcc when it is missing. When the sources are newer than the
     library it is rebuilt only with M3TB_AUTO_REBUILD=1 (never under torchrun: ranks would race) - otherwise a
     warning is printed, because a stale binary silently running is worse than a loud one. Raises if loading fails."""
-    global _lib
+    global _lib, LIB_PATH
     if _lib is not None:
         return _lib
+    if os.environ.get("M3TB_LIB"):  # A/B experiments: another build of the same library
+        LIB_PATH = os.environ["M3TB_LIB"]
     if not os.path.exists(LIB_PATH):
         _build.build_cuda()
     elif _build._stale(LIB_PATH, _build.cuda_sources()):

@@ -3,8 +3,8 @@
 // Same arithmetic as k_track (m3t_b200_kernels.cuh: every per-line / per-point expression is evaluated in the
 // reference's order, so the stored state is bit-identical to the oracle), different execution shape:
 //
-//   * 1024 threads per body when a body carries both modalities: warps 0-15 own the correspondence LINES, warps
-//     16-31 the depth POINTS, one item per thread, so the two correspondence phases and the two gradient passes of
+//   * 1024 threads per body when a body carries both modalities: warps 16-31 own the correspondence LINES, warps
+//     0-15 the depth POINTS, one item per thread, so the two correspondence phases and the two gradient passes of
 //     an iteration run concurrently (32 resident warps instead of 16; 64 registers per thread).
 //   * 64 registers: the 2 x 19 segment products of a line are never held at once. A line is walked segment by
 //     segment; a sliding window of the last 8 segments (16 registers) is all CalculateDistribution
@@ -12,7 +12,7 @@
 //     multiplication order, for lines walked in either direction. The 12 entries go to shared memory (24 KB); the
 //     local-mode gradient reads its two entries from there by index.
 //   * GetClosestView is the exact pruned search of m3t_b200_views.cuh (~200 instead of 2 x 2562 dot products per
-//     iteration), done by the first warp of each group while the other warps wait at the group's named barrier
+//     iteration), done by the last warp of each group while the other warps wait at the group's named barrier
 //     (measured: every warp searching redundantly costs 6.4 k cycles of issue slots, one warp ~1.3 k).
 //   * CalculateOptimization (6 x 6) runs thread-serially in registers on warp 0 (every lane the same work, no
 //     shuffles in the dependent chain): pivot order from the original diagonal, gather of the permuted matrix,
@@ -532,8 +532,12 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   if (!body.set) return;
   const bool has_region = body.has_region, has_depth = body.has_depth;
   const int item = tid & (kGroup - 1);
-  const bool line_group = T == kGroup || tid < kGroup;
-  const bool point_group = T == kGroup || tid >= kGroup;
+  // Warp priority: an SM sub-partition issues from its highest-numbered eligible warp first. The lines are the critical
+  // path of every iteration (the points finish earlier and wait), so they get the HIGH warps, and the single-warp
+  // sections (view search, solve) run on the last warp of their group.
+  const bool line_group = T == kGroup || tid >= kGroup;
+  const bool point_group = T == kGroup || tid < kGroup;
+  const bool group_leader = (tid & (kGroup - 1)) >= kGroup - 32;
   const int lcap = args.line_cap, pcap = args.point_cap;
   float* g_rst = args.region_state + size_t(body_id) * RF_COUNT * lcap;
   float* g_dst = args.depth_state + size_t(body_id) * DF_COUNT * pcap;
@@ -543,11 +547,11 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   constexpr unsigned lut_bytes = LUT_SMEM ? unsigned(16 * 16 * 16 * sizeof(float2)) : 0u;
   float* dist_col = reinterpret_cast<float*>(dyn + lut_bytes) + item;
 
-  // profiling aid: warp 0 stamps slots [0, 128), the first point warp slots [128, 256)
+  // profiling aid: the solver warp (last warp) stamps slots [0, 128), the point group's leader warp slots [128, 256)
   long long* stamp_ptr = nullptr;
   int stamp_i = 0;
-  const int stamp_base = (T > kGroup && tid >= kGroup) ? kPhaseSlots / 2 : 0;
-  if (args.phase_clock && (warp == 0 || (T > kGroup && warp == kGroup / 32)))
+  const int stamp_base = (T > kGroup && tid < kGroup) ? kPhaseSlots / 2 : 0;
+  if (args.phase_clock && (warp == kW - 1 || (T > kGroup && warp == kGroup / 32 - 1)))
     stamp_ptr = args.phase_clock + size_t(body_id) * kPhaseSlots;
   M3TB_STAMP2(stamp_base);
 
@@ -586,7 +590,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     MbarInit(&sh.ctile_bar, 1);
   }
   __syncthreads();
-  if (warp == 0) {
+  if (warp == kW - 1) {
     float pose[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) pose[i] = sh.pose[i];
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   bool ctile_ready = ctile.w <= 0 || !tma;
   if (!tma) {
     if (dtile.w > 0) {
-      if (warp == kW - 1) {  // a point warp issues the depth rows while the others convert the colour tile
+      if (warp == 0) {  // a point warp issues the depth rows while the others convert the colour tile
         const unsigned row_bytes = unsigned(dtile.w) * 2u;
         if (lane == 0) MbarExpectTx(&sh.depth_bar, row_bytes * unsigned(dtile.h));
         __syncwarp();
@@ -756,12 +760,12 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   for (int corr = args.corr_begin; corr < args.corr_end; ++corr) {
     // ---------------- CalculateCorrespondences -------------------------------------------------
     if (do_rcorr && line_group) {
-      if ((tid & (kGroup - 1)) < 32) {  // group leader warp
+      if (group_leader) {
         const int v = ClosestViewPrunedWarp(info_r, rmodel->sorted_views, rmodel->n_clusters,
                                             rmodel->orientations4, rmodel->n_views, sh.view_o[0], view_r);
         if (lane == 0) sh.views[corr & 1][0] = v;
       }
-      if (T == kGroup && do_dcorr && warp == 1) {  // single group: the second warp searches the depth model meanwhile
+      if (T == kGroup && do_dcorr && warp == kW - 2) {  // single group: another warp searches the depth model meanwhile
         const int v = ClosestViewPrunedWarp(info_d, dmodel->sorted_views, dmodel->n_clusters,
                                             dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
         if (lane == 0) sh.views[corr & 1][1] = v;
@@ -790,7 +794,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     }
     if (do_dcorr && point_group) {
       if (T > kGroup || !do_rcorr) {  // (single group with lines: searched above, behind the same barrier)
-        if ((tid & (kGroup - 1)) < 32) {
+        if (group_leader) {
           const int v = ClosestViewPrunedWarp(info_d, dmodel->sorted_views, dmodel->n_clusters,
                                               dmodel->orientations4, dmodel->n_views, sh.view_o[1], view_d);
           if (lane == 0) sh.views[corr & 1][1] = v;
@@ -851,7 +855,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       M3TB_STAMP2(stamp_base);  // accumulate + warp reduce
       __syncthreads();
       M3TB_STAMP2(stamp_base);  // all warps arrived
-      if (warp == 0) {
+      if (warp == kW - 1) {
         const int l = lane < 27 ? lane : 26;
         // cross-warp sum, four interleaved partial sums (fixed order: deterministic)
         float s4[4] = {0.0f, 0.0f, 0.0f, 0.0f};

@@ -196,48 +196,6 @@ __device__ __forceinline__ int ClosestViewPrunedWarp(const float4* info, const f
   const float lb = o0 * qp.x + o1 * qp.y + o2 * qp.z;
   float best = -1.0f;
   int idx = 0x7fffffff;
-  if (n_clusters <= 96) {
-    // common case (<= 3072 views; k_track2 stages these tables in shared memory): bound all clusters first, then fetch
-    // the members of up to eight candidate clusters in ONE trip to memory
-    unsigned m[3], pk[3];
-#pragma unroll
-    for (int h = 0; h < 3; ++h) {
-      const int c = 32 * h + lane;
-      bool cand = false;
-      pk[h] = 0u;
-      if (c < n_clusters) {
-        const float4 a = info[2 * c], b = info[2 * c + 1];
-        const float ub = ViewClusterBound(a.x, a.y, a.z, a.w, b.x, b.y, b.z, o0, o1, o2, on2, onorm);
-        cand = !(ub < lb);
-        pk[h] = __float_as_uint(b.w);
-      }
-      m[h] = __ballot_sync(kFull, cand);
-    }
-    while (m[0] | m[1] | m[2]) {  // warp-uniform; one pass unless more than eight clusters qualify
-      unsigned cp[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        unsigned v = 0u;
-        if (m[0]) { v = __shfl_sync(kFull, pk[0], __ffs(m[0]) - 1); m[0] &= m[0] - 1u; }
-        else if (m[1]) { v = __shfl_sync(kFull, pk[1], __ffs(m[1]) - 1); m[1] &= m[1] - 1u; }
-        else if (m[2]) { v = __shfl_sync(kFull, pk[2], __ffs(m[2]) - 1); m[2] &= m[2] - 1u; }
-        cp[u] = v;
-      }
-      float4 q[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int first = int(cp[u] & 0xffffffu), cnt = int(cp[u] >> 24);
-        q[u] = lane < cnt ? __ldg(sorted + first + lane) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int cnt = int(cp[u] >> 24);
-        const float dot = o0 * q[u].x + o1 * q[u].y + o2 * q[u].z;
-        const int vi = __float_as_int(q[u].w);
-        if (lane < cnt && (dot > best || (dot == best && vi < idx))) { best = dot; idx = vi; }
-      }
-    }
-  } else
   for (int c0 = 0; c0 < n_clusters; c0 += 64) {  // two bound passes per trip: their table loads are in flight together
     float4 ia[2], ib[2];
 #pragma unroll
