@@ -35,7 +35,10 @@ class RegionParams(C.Structure):
                 ("unconsidered_line_length", C.c_float), ("max_considered_line_length", C.c_float),
                 ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
                 ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
-                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32)]
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32),
+                ("model_occlusions", C.c_int32), ("modeled_depth_offset_radius", C.c_float),
+                ("modeled_occlusion_radius", C.c_float), ("modeled_occlusion_threshold", C.c_float),
+                ("use_region_checking", C.c_int32)]
 
 
 class DepthParams(C.Structure):
@@ -45,7 +48,17 @@ class DepthParams(C.Structure):
                 ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
                 ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
                 ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
-                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32)]
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32),
+                ("model_occlusions", C.c_int32), ("modeled_depth_offset_radius", C.c_float),
+                ("modeled_occlusion_radius", C.c_float), ("modeled_occlusion_threshold", C.c_float),
+                ("use_silhouette_checking", C.c_int32)]
+
+
+class RenderingArg(C.Structure):
+    """m3tb_rendering"""
+    _fields_ = [("image", C.c_void_p), ("image_size", C.c_int32), ("pitch", C.c_size_t), ("corner_u", C.c_float),
+                ("corner_v", C.c_float), ("scale", C.c_float), ("projection_term_a", C.c_float),
+                ("projection_term_b", C.c_float), ("id", C.c_int32), ("visible", C.c_int32)]
 
 
 class OptimizerParams(C.Structure):
@@ -88,7 +101,7 @@ SYMBOLS = [
     "m3tb_debug_phase_clocks", "m3tb_last_ingest_bytes", "m3tb_set_structure", "m3tb_clear_structures",
     "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
     "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses", "m3tb_prefetch_frames", "m3tb_detach_frames",
-    "m3tb_debug_closest_view",
+    "m3tb_debug_closest_view", "m3tb_upload_depth_rendering", "m3tb_upload_silhouette_rendering",
 ]
 
 _lib = None
@@ -159,6 +172,8 @@ def lib():
     L.m3tb_reset_joint_poses.argtypes = [vp]
     L.m3tb_prefetch_frames.argtypes = [vp]
     L.m3tb_detach_frames.argtypes = [vp]
+    L.m3tb_upload_depth_rendering.argtypes = [vp, ci, ci, C.POINTER(RenderingArg)]
+    L.m3tb_upload_silhouette_rendering.argtypes = [vp, ci, ci, C.POINTER(RenderingArg)]
     ip = C.POINTER(C.c_int)
     L.m3tb_debug_closest_view.argtypes = [fp, ci, fp, ci, ip, ip, ip, ip]
     L.m3tb_get_link_poses.argtypes = [vp, ci, fp, fp, fp]
@@ -185,8 +200,11 @@ def region_params(settings=None) -> RegionParams:
               "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
               "unconsidered_line_length", "max_considered_line_length", "reference_contour_length",
               "measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
-              "n_unoccluded_iterations", "min_n_unoccluded_lines"):
+              "n_unoccluded_iterations", "min_n_unoccluded_lines", "modeled_depth_offset_radius",
+              "modeled_occlusion_radius", "modeled_occlusion_threshold"):
         setattr(p, k, getattr(settings, k))
+    p.model_occlusions = int(settings.model_occlusions)
+    p.use_region_checking = int(settings.use_region_checking)
     p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
     p.measure_occlusions = int(settings.measure_occlusions)
     p.n_scales = len(settings.scales)
@@ -210,8 +228,11 @@ def depth_params(settings=None) -> DepthParams:
     p.use_depth_scaling = int(settings.use_depth_scaling)
     p.measure_occlusions = int(settings.measure_occlusions)
     for k in ("measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
-              "n_unoccluded_iterations", "min_n_unoccluded_points"):
+              "n_unoccluded_iterations", "min_n_unoccluded_points", "modeled_depth_offset_radius",
+              "modeled_occlusion_radius", "modeled_occlusion_threshold"):
         setattr(p, k, getattr(settings, k))
+    p.model_occlusions = int(settings.model_occlusions)
+    p.use_silhouette_checking = int(settings.use_silhouette_checking)
     p.n_considered_distances = len(settings.considered_distances)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.considered_distances):
@@ -302,6 +323,19 @@ class Context:
 
     def detach_frames(self):
         self._ck(self.L.m3tb_detach_frames(self.h))
+
+    def upload_rendering(self, body, key, r):
+        """key: "region_depth" | "region_silhouette" | "depth_depth" | "depth_silhouette"; r: synth.Rendering."""
+        a = RenderingArg()
+        a.image = r.image.ctypes.data
+        a.image_size = r.image.shape[0]
+        a.pitch = r.image.strides[0]
+        a.corner_u, a.corner_v, a.scale = r.corner_u, r.corner_v, r.scale
+        a.projection_term_a, a.projection_term_b = r.projection_term_a, r.projection_term_b
+        a.id, a.visible = int(r.id), int(r.visible)
+        modality = 0 if key.startswith("region") else 1
+        f = self.L.m3tb_upload_depth_rendering if key.endswith("depth") else self.L.m3tb_upload_silhouette_rendering
+        self._ck(f(self.h, body, modality, C.byref(a)))
 
     def set_body(self, body, region, depth, optimizer, region_model=0, depth_model=0, color_camera=0, depth_camera=0):
         self._ck(self.L.m3tb_set_body(self.h, body, C.byref(region) if region is not None else None,
@@ -495,6 +529,10 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
             ctx.upload_depth_batch(0, wl.depth_frames[first:first + count])
     for b in range(count):
         ctx.set_body(b, rp, dp, op, 0, 0, b, b)
+    for b, per in (getattr(wl, "renderings", None) or {}).items():  # FocusedRenderer outputs, where the workload has them
+        if first <= b < first + count:
+            for key, r in per.items():
+                ctx.upload_rendering(b - first, key, r)
     ctx.set_poses(wl.start_body2world[first:first + count])
     if getattr(wl, "structures", None):  # structures whose bodies all lie inside [first, first+count)
         k = 0

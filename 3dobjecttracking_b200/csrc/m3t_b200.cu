@@ -121,6 +121,7 @@ struct m3tb_ctx {
   std::vector<char> bin_stale;            // per colour camera: the bin-index image does not match the frame copy
   int bin_bitshift = -1;                  // what the bin-index images were built with
   int* d_bin_ids = nullptr;               // staging for k_bin
+  std::vector<uint8_t*> rendering_allocs; // device copies of the renderer images (m3tb_upload_*_rendering)
   std::vector<PoolMaps> pool_maps;        // tensor maps of the pools seen so far (current / alternate x bins / depth)
   int tma_mode = 1;                       // M3TB_TMA: 0 legacy staging, 1 tensor maps in the kernel parameters, 2 in global memory
   CUtensorMap* d_tmaps = nullptr;         // tma_mode 2: [2][kTileWidths]
@@ -278,6 +279,9 @@ int ValidateBodies(m3tb_ctx* ctx) {
         if (B.rp.measured_depth_offset_radius > ctx->h_rmodels[B.region_model].max_radius_depth_offset)
           return Fail(ctx, M3TB_ERR_INVALID, "Measured depth offset radius too large");
       }
+      if (B.rp.model_occlusions &&  // region_modality.cpp:979-991
+          B.rp.modeled_depth_offset_radius > ctx->h_rmodels[B.region_model].max_radius_depth_offset)
+        return Fail(ctx, M3TB_ERR_INVALID, "Modeled depth offset radius too large");
     }
     if (B.has_depth) {
       if (!ctx->h_dmodels[B.depth_model].set) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "depth model not set");
@@ -507,6 +511,9 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   for (int b = 0; b < ctx->n_bodies; ++b) {
     const BodyDev& B = ctx->h_bodies[b];
     occ = occ || (B.has_region && B.rp.measure_occlusions) || (B.has_depth && B.dp.measure_occlusions);
+    // the renderer-image checks live in the same kernel variants
+    occ = occ || (B.has_region && (B.rp.model_occlusions || B.rp.use_region_checking)) ||
+          (B.has_depth && (B.dp.model_occlusions || B.dp.use_silhouette_checking));
   }
   // ---- k_track2: rigid bodies, <= 512 items per modality, no measured occlusion handling, correspondence / fused phases,
   //      one function lookup for the whole batch (m3t_b200_track2.cuh) --------------------------------------------------
@@ -1076,6 +1083,9 @@ void m3tb_region_params_default(m3tb_region_params* p) {
   p->measured_occlusion_threshold = 0.03f;
   p->n_unoccluded_iterations = 10;
   p->min_n_unoccluded_lines = 0;
+  p->modeled_depth_offset_radius = 0.01f;
+  p->modeled_occlusion_radius = 0.01f;
+  p->modeled_occlusion_threshold = 0.03f;
 }
 
 void m3tb_depth_params_default(m3tb_depth_params* p) {
@@ -1092,6 +1102,9 @@ void m3tb_depth_params_default(m3tb_depth_params* p) {
   p->measured_occlusion_threshold = 0.03f;
   p->n_unoccluded_iterations = 10;
   p->min_n_unoccluded_points = 0;
+  p->modeled_depth_offset_radius = 0.01f;
+  p->modeled_occlusion_radius = 0.01f;
+  p->modeled_occlusion_threshold = 0.03f;
 }
 
 void m3tb_optimizer_params_default(m3tb_optimizer_params* p) {
@@ -1182,6 +1195,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
       cudaFree(a.orientations); cudaFree(a.view_scalars); cudaFree(a.points); cudaFree(a.depth_offsets);
       cudaFree(a.cluster_info); cudaFree(a.sorted_views);
     }
+  for (auto p : ctx->rendering_allocs) cudaFree(p);
   for (auto p : ctx->private_color) cudaFree(p);
   for (auto p : ctx->private_depth) cudaFree(p);
   cudaFree(ctx->color_pool.base); cudaFree(ctx->depth_pool.base);
@@ -1285,6 +1299,7 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
   BodyDev B;
   std::memset(&B, 0, sizeof(B));
   B.first_iteration = ctx->h_bodies[body].first_iteration;
+  std::memcpy(B.rend, ctx->h_bodies[body].rend, sizeof(B.rend));  // uploaded renderer images stay with the body
   m3tb_optimizer_params op;
   m3tb_optimizer_params_default(&op);
   if (optimizer) op = *optimizer;
@@ -1309,6 +1324,11 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
     r.measured_depth_offset_radius = region->measured_depth_offset_radius;
     r.measured_occlusion_radius = region->measured_occlusion_radius;
     r.measured_occlusion_threshold = region->measured_occlusion_threshold;
+    r.model_occlusions = region->model_occlusions ? 1 : 0;
+    r.use_region_checking = region->use_region_checking ? 1 : 0;
+    r.modeled_depth_offset_radius = region->modeled_depth_offset_radius;
+    r.modeled_occlusion_radius = region->modeled_occlusion_radius;
+    r.modeled_occlusion_threshold = region->modeled_occlusion_threshold;
     r.n_lines_max = region->n_lines_max;
     r.use_adaptive_coverage = region->use_adaptive_coverage;
     r.reference_contour_length = region->reference_contour_length;
@@ -1373,6 +1393,11 @@ int m3tb_set_body(m3tb_ctx* ctx, int body, const m3tb_region_params* region, con
     d.measured_depth_offset_radius = depth->measured_depth_offset_radius;
     d.measured_occlusion_radius = depth->measured_occlusion_radius;
     d.measured_occlusion_threshold = depth->measured_occlusion_threshold;
+    d.model_occlusions = depth->model_occlusions ? 1 : 0;
+    d.use_silhouette_checking = depth->use_silhouette_checking ? 1 : 0;
+    d.modeled_depth_offset_radius = depth->modeled_depth_offset_radius;
+    d.modeled_occlusion_radius = depth->modeled_occlusion_radius;
+    d.modeled_occlusion_threshold = depth->modeled_occlusion_threshold;
     d.n_points_max = depth->n_points_max;
     d.use_adaptive_coverage = depth->use_adaptive_coverage;
     d.use_depth_scaling = depth->use_depth_scaling;
@@ -1830,6 +1855,51 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
   ctx->prefetched = true;
   ctx->prefetch_enabled = true;
   return M3TB_OK;
+}
+
+static int UploadRendering(m3tb_ctx* ctx, int body, int slot, const m3tb_rendering* r, int bytes_per_pixel) {
+  if (body < 0 || body >= ctx->max_bodies || !r || !r->image || r->image_size <= 0 ||
+      r->pitch < size_t(r->image_size) * bytes_per_pixel || !(r->scale > 0.0f))
+    return Fail(ctx, M3TB_ERR_INVALID, "bad rendering arguments");
+  RenderingDev& d = ctx->h_bodies[body].rend[slot];
+  const unsigned pitch = unsigned(Align(size_t(r->image_size) * bytes_per_pixel, 16));
+  if (!d.image || d.image_size != r->image_size) {
+    if (d.image) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      uint8_t* old = const_cast<uint8_t*>(d.image);
+      for (auto& q : ctx->rendering_allocs)
+        if (q == old) q = nullptr;
+      cudaFree(old);
+      d.image = nullptr;
+    }
+    uint8_t* p = nullptr;
+    CU(cudaMalloc(&p, size_t(pitch) * r->image_size));
+    ctx->rendering_allocs.push_back(p);
+    d.image = p;
+  }
+  CU(cudaMemcpy2DAsync(const_cast<uint8_t*>(d.image), pitch, r->image, r->pitch, size_t(r->image_size) * bytes_per_pixel,
+                       r->image_size, cudaMemcpyDefault, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));  // Camera::UpdateImage-style copy semantics: the caller's image is free again
+  d.image_size = r->image_size;
+  d.pitch = pitch;
+  d.corner_u = r->corner_u; d.corner_v = r->corner_v; d.scale = r->scale;
+  d.projection_term_a = r->projection_term_a; d.projection_term_b = r->projection_term_b;
+  d.id = r->id;
+  d.visible = r->visible ? 1 : 0;
+  ctx->bodies_dirty = true;
+  return M3TB_OK;
+}
+
+int m3tb_upload_depth_rendering(m3tb_ctx* ctx, int body, int modality, const m3tb_rendering* rendering) {
+  CHECK_CTX();
+  if (modality != 0 && modality != 1) return Fail(ctx, M3TB_ERR_INVALID, "modality must be 0 (region) or 1 (depth)");
+  return UploadRendering(ctx, body, modality == 0 ? RS_REGION_DEPTH : RS_DEPTH_DEPTH, rendering, 2);
+}
+
+int m3tb_upload_silhouette_rendering(m3tb_ctx* ctx, int body, int modality, const m3tb_rendering* rendering) {
+  CHECK_CTX();
+  if (modality != 0 && modality != 1) return Fail(ctx, M3TB_ERR_INVALID, "modality must be 0 (region) or 1 (depth)");
+  return UploadRendering(ctx, body, modality == 0 ? RS_REGION_SILHOUETTE : RS_DEPTH_SILHOUETTE, rendering, 1);
 }
 
 int m3tb_detach_frames(m3tb_ctx* ctx) {

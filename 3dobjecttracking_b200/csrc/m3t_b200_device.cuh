@@ -105,6 +105,9 @@ struct RegionParamsDev {
   // measured occlusion handling (region_modality.h:432-443)
   int measure_occlusions, n_unoccluded_iterations, min_n_unoccluded_lines;
   float measured_depth_offset_radius, measured_occlusion_radius, measured_occlusion_threshold;
+  // checks on renderer images (region_modality.h:424-431)
+  int model_occlusions, use_region_checking;
+  float modeled_depth_offset_radius, modeled_occlusion_radius, modeled_occlusion_threshold;
 };
 
 struct DepthParamsDev {
@@ -117,7 +120,25 @@ struct DepthParamsDev {
   // measured occlusion handling (depth_modality.h:313-321)
   int measure_occlusions, n_unoccluded_iterations, min_n_unoccluded_points;
   float measured_depth_offset_radius, measured_occlusion_radius, measured_occlusion_threshold;
+  // checks on renderer images (depth_modality.h:305-312)
+  int model_occlusions, use_silhouette_checking;
+  float modeled_depth_offset_radius, modeled_occlusion_radius, modeled_occlusion_threshold;
 };
+
+// One FocusedRenderer output of one body (renderer.h:156-230), device copy: focused depth image (u16) or focused
+// silhouette image (u8)
+struct RenderingDev {
+  const uint8_t* image;  // null: not uploaded
+  int image_size;
+  unsigned pitch;        // bytes
+  float corner_u, corner_v, scale;
+  float projection_term_a, projection_term_b;
+  int id;
+  int visible;
+};
+enum RenderingSlot { RS_REGION_DEPTH = 0, RS_REGION_SILHOUETTE, RS_DEPTH_DEPTH, RS_DEPTH_SILHOUETTE, RS_COUNT };
+constexpr int kNRegionStride = 5;      // region_modality.h:146
+constexpr float kRegionOffset = 2.0f;  // region_modality.h:147
 
 constexpr int kDepthOffsets = 30;        // DataPoint::depth_offsets (region_model.h:97, depth_model.h:74)
 constexpr int kMaxNOcclusionStrides = 5; // region_modality.h:145, depth_modality.h:113
@@ -130,6 +151,7 @@ struct BodyDev {
   int set;
   RegionParamsDev rp;
   DepthParamsDev dp;
+  RenderingDev rend[RS_COUNT];
 };
 
 struct TrackArgs {

@@ -304,6 +304,130 @@ __device__ __forceinline__ bool LineUnoccludedMeasured(const RegionOcclusion& o,
                           (z - depth_offset - o.threshold) / o.depth_scale);
 }
 
+// ---- checks on renderer images (modeled occlusion handling, region checking, silhouette checking) ----------
+// The strided minimum scan of RegionModality::IsLineUnoccludedModeled (region_modality.cpp:1391-1431) and
+// DepthModality::IsPointUnoccludedModeled (depth_modality.cpp:778-824) in the focused depth rendering.
+static __device__ __noinline__ bool ModeledWindowUnoccluded(const RenderingDev& r, float center_u, float center_v, float diameter,
+                                                            float min_allowed_depth) {
+  const int stride = int(diameter / float(kMaxNOcclusionStrides) + 1.0f);
+  const int n_strides = int(diameter / float(stride) + 0.5f);
+  const int rounded_diameter = n_strides * stride;
+  const float rounded_radius = 0.5f * float(rounded_diameter);
+  const float focused_center_u = (center_u - r.corner_u) * r.scale;
+  const float focused_center_v = (center_v - r.corner_v) * r.scale;
+  int u_min = int(focused_center_u - rounded_radius + 0.5f);
+  int v_min = int(focused_center_v - rounded_radius + 0.5f);
+  int u_max = u_min + rounded_diameter;
+  int v_max = v_min + rounded_diameter;
+  u_min = max(u_min, 0);
+  v_min = max(v_min, 0);
+  u_max = min(u_max, r.image_size - 1);
+  v_max = min(v_max, r.image_size - 1);
+  unsigned min_depth_value = 65535u;
+  for (int v = v_min; v <= v_max; v += stride) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(r.image + size_t(v) * r.pitch);
+    for (int u = u_min; u <= u_max; u += stride) min_depth_value = min(min_depth_value, unsigned(__ldg(row + u)));
+  }
+  const float min_depth = r.projection_term_a / (r.projection_term_b - float(min_depth_value));  // FocusedDepthRenderer::Depth
+  return min_depth > min_allowed_depth;
+}
+
+__device__ __forceinline__ unsigned SilhouetteAt(const RenderingDev& r, int v, int u) {
+  return __ldg(r.image + size_t(v) * r.pitch + size_t(u));
+}
+
+// RegionModality::IsDynamicLineRegionSufficient (region_modality.cpp:1293-1341); a foreground sample outside the focused
+// image (undefined behaviour in the reference) counts as "not this region", as in the oracle
+static __device__ __noinline__ bool DynamicLineRegionSufficient(const RenderingDev& r, float min_continuous_distance, float fscale,
+                                                                float center_u, float center_v, float normal_u, float normal_v) {
+  const unsigned region_id = unsigned(r.id) & 0xffu;
+  const float fsize = float(r.image_size);
+  const float focused_min_continuous_distance = min_continuous_distance * fscale * r.scale;
+  const float focused_stride = fmaxf((focused_min_continuous_distance - kRegionOffset) / float(kNRegionStride), 0.0f);
+  const float stride_u = focused_stride * normal_u;
+  const float stride_v = focused_stride * normal_v;
+  const float offset_u = kRegionOffset * normal_u;
+  const float offset_v = kRegionOffset * normal_v;
+  const float focused_center_u = 0.5f + (center_u - r.corner_u) * r.scale;
+  const float focused_center_v = 0.5f + (center_v - r.corner_v) * r.scale;
+  float u = focused_center_u - offset_u;
+  float v = focused_center_v - offset_v;
+  for (int i = 0; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) return false;
+    if (SilhouetteAt(r, int(v), int(u)) != region_id) return false;
+    u -= stride_u;
+    v -= stride_v;
+  }
+  u = focused_center_u + offset_u;
+  v = focused_center_v + offset_v;
+  for (int i = 0; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) break;
+    if (SilhouetteAt(r, int(v), int(u)) == region_id) return false;
+    u += stride_u;
+    v += stride_v;
+  }
+  return true;
+}
+
+// RegionModality::DynamicRegionDistance (region_modality.cpp:1157-1223), quirk of :1218 included
+static __device__ __noinline__ void DynamicRegionDistance(const RenderingDev& r, float max_considered_line_length,
+                                                          float unconsidered_line_length, float center_u, float center_v,
+                                                          float normal_u, float normal_v, float& dynamic_foreground_distance,
+                                                          float& dynamic_background_distance) {
+  const unsigned region_id = unsigned(r.id) & 0xffu;
+  const float fsize = float(r.image_size);
+  const float stride = max_considered_line_length / float(kNRegionStride);
+  const float focused_stride = stride * r.scale;
+  const float focused_stride_u = focused_stride * normal_u;
+  const float focused_stride_v = focused_stride * normal_v;
+  const float delta_start = kRegionOffset / r.scale - unconsidered_line_length;
+  const int i_start = max(int(delta_start / stride + 1.0f), 0);
+  const float offset = unconsidered_line_length + float(i_start) * stride;
+  const float focused_offset = offset * r.scale;
+  const float focused_offset_u = focused_offset * normal_u;
+  const float focused_offset_v = focused_offset * normal_v;
+  const float focused_center_u = 0.5f + (center_u - r.corner_u) * r.scale;
+  const float focused_center_v = 0.5f + (center_v - r.corner_v) * r.scale;
+  float u = focused_center_u - focused_offset_u;
+  float v = focused_center_v - focused_offset_v;
+  for (int i = i_start; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) {
+      dynamic_foreground_distance = stride * float(i);
+      break;
+    }
+    if (SilhouetteAt(r, int(v), int(u)) != region_id) {
+      dynamic_foreground_distance = i == i_start ? 0.0f : stride * float(i);
+      break;
+    }
+    u -= focused_stride_u;
+    v -= focused_stride_v;
+  }
+  u = focused_center_u + focused_offset_u;
+  v = focused_center_v + focused_offset_v;
+  for (int i = i_start; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) {
+      dynamic_background_distance = max_considered_line_length;
+      break;
+    }
+    if (SilhouetteAt(r, int(v), int(u)) == region_id) {
+      if (i == i_start) dynamic_background_distance = 0.0f;
+      else dynamic_foreground_distance = stride * float(i);  // sic (:1218)
+      break;
+    }
+    u += focused_stride_u;
+    v += focused_stride_v;
+  }
+}
+
+// What RegionLine / DepthPoint need for the renderer-image checks of one pass
+struct RenderChecks {
+  const RenderingDev* silhouette;  // region checking / silhouette checking (both passes), or null
+  const RenderingDev* depth;       // modeled occlusion handling (first pass only), or null
+  const float* offsets;            // depth offsets of the closest view: [n_points][30]
+  int modeled_offset_id;           // region: modeled_depth_offset_id_
+  float radius, threshold, offset_radius;
+};
+
 template <bool LUT_SMEM>
 __device__ __forceinline__ float2 LutFetch(const float2* __restrict__ lut_g, const float2* lut_s, int idx) {
   if (LUT_SMEM) return lut_s[idx];
@@ -377,7 +501,8 @@ __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionPar
                                            const float4 p1, const FrameView& frame,
                                            const Tile& tile, const uint16_t* tile_px,
                                            const float2* __restrict__ lut_g, const float2* lut_s, LineState& L,
-                                           const RegionOcclusion* occ = nullptr, int point = 0) {
+                                           const RegionOcclusion* occ = nullptr, int point = 0,
+                                           const RenderChecks* rc = nullptr) {
   L.valid = false;
   // CalculateBasicLineData (:1231-1250)
   float x, y, z;
@@ -398,8 +523,17 @@ __device__ __forceinline__ void RegionLine(const RegionIter& it, const RegionPar
   if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
   if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
-  if (OCC) {  // measured occlusions (:1274-1281)
+  if (OCC) {  // region checking (:1269-1274), measured occlusions (:1274-1281), modeled occlusions (:1283-1289)
+    if (rc && rc->silhouette &&
+        !DynamicLineRegionSufficient(*rc->silhouette, rp.min_continuous_distance, it.fscale, center_u, center_v, nu, nv))
+      return;
     if (occ && !LineUnoccludedMeasured(*occ, p0.x, p0.y, p0.z, point)) return;
+    if (rc && rc->depth) {
+      const float meter_to_pixel = (it.fu / z) * rc->depth->scale;
+      const float diameter = 2.0f * rc->radius * meter_to_pixel;
+      const float depth_offset = __ldg(rc->offsets + size_t(point) * kDepthOffsets + rc->modeled_offset_id);
+      if (!ModeledWindowUnoccluded(*rc->depth, center_u, center_v, diameter, z - depth_offset - rc->threshold)) return;
+    }
   }
 
   // CalculateSegmentProbabilities (:1433-1573); horizontal / vertical cases folded into major / minor axes
@@ -596,7 +730,8 @@ static __device__ __noinline__ void DepthSearchSlow(const DepthIter& it, int u_m
 template <bool OCC = false>
 __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParamsDev& dp, const float4 p0, const float4 p1,
                                            const FrameView& frame, const Tile& tile, const uint16_t* tile_px,
-                                           PointState& P, const float* offsets = nullptr, float stride_depth_offset = 1.0f) {
+                                           PointState& P, const float* offsets = nullptr, float stride_depth_offset = 1.0f,
+                                           const RenderChecks* rc = nullptr) {
   P.valid = false;
   float x, y, z;
   PoseApply(it.b2c, p0.x, p0.y, p0.z, x, y, z);
@@ -608,6 +743,15 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
   if (z <= 0.0f) return;
   int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
   if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) return;
+  if (OCC) {  // IsPointOnValidSilhouette (:728-734) via FocusedSilhouetteRenderer::SilhouetteValue
+    if (rc && rc->silhouette) {
+      const RenderingDev& sr = *rc->silhouette;
+      const int su = int((float(icu) - sr.corner_u) * sr.scale + 0.5f);
+      const int sv = int((float(icv) - sr.corner_v) * sr.scale + 0.5f);
+      if (su < 0 || su >= sr.image_size || sv < 0 || sv >= sr.image_size) return;
+      if (SilhouetteAt(sr, sv, su) != (unsigned(sr.id) & 0xffu)) return;
+    }
+  }
   if (OCC) {  // IsPointUnoccludedMeasured (:736-776), depth offset selected as in CalculateBasicPointData (:669-681)
     if (offsets) {
       float radius = dp.measured_depth_offset_radius;
@@ -622,6 +766,21 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
       if (!WindowUnoccluded(tile, tile_px, frame, it.w_m1, it.h_m1, center_u, center_v, diameter,
                             (z - measured_depth_offset - threshold) / it.depth_scale))
         return;
+    }
+  }
+  if (OCC) {  // IsPointUnoccludedModeled (:778-824), depth offset as in CalculateBasicPointData (:682-693)
+    if (rc && rc->depth) {
+      float radius = rc->offset_radius;
+      if (dp.use_depth_scaling) radius *= z;
+      int id = int(radius / stride_depth_offset + 0.5f);
+      if (id >= kDepthOffsets) id = kDepthOffsets - 1;
+      const float modeled_depth_offset = __ldg(rc->offsets + id);
+      float meter_to_pixel = it.fu * rc->depth->scale;
+      if (!dp.use_depth_scaling) meter_to_pixel /= z;
+      const float diameter = 2.0f * rc->radius * meter_to_pixel;
+      float threshold = rc->threshold;
+      if (dp.use_depth_scaling) threshold *= z;
+      if (!ModeledWindowUnoccluded(*rc->depth, center_u, center_v, diameter, z - modeled_depth_offset - threshold)) return;
     }
   }
   // FindCorrespondence (:826-884)
@@ -1165,6 +1324,23 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
             rocc.frame = &dframe; rocc.tile = &dtile; rocc.tile_px = dtile_px;
           }
         }
+        // checks on renderer images: region checking in both passes (:402-408), modeled occlusions in the first (:447)
+        RenderChecks rchk;
+        bool use_rchk = false, handle_modeled = false;
+        if (OCC) {
+          const RenderingDev& sr = body.rend[RS_REGION_SILHOUETTE];
+          const RenderingDev& dr = body.rend[RS_REGION_DEPTH];
+          rchk.silhouette = (body.rp.use_region_checking && sr.image && sr.visible) ? &sr : nullptr;
+          handle_modeled = body.rp.model_occlusions && dr.image && dr.visible && rmodel->depth_offsets != nullptr &&
+                           (args.iteration - body.first_iteration) >= body.rp.n_unoccluded_iterations;
+          rchk.depth = handle_modeled ? &dr : nullptr;
+          rchk.offsets = rmodel->depth_offsets ? rmodel->depth_offsets + size_t(view_r) * rmodel->n_points * kDepthOffsets : nullptr;
+          rchk.modeled_offset_id = int(body.rp.modeled_depth_offset_radius / rmodel->stride_depth_offset + 0.5f);
+          rchk.radius = body.rp.modeled_occlusion_radius;
+          rchk.threshold = body.rp.modeled_occlusion_threshold;
+          rchk.offset_radius = body.rp.modeled_depth_offset_radius;
+          use_rchk = rchk.silhouette != nullptr || rchk.depth != nullptr;
+        }
         for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
@@ -1173,15 +1349,18 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
             if (i < n_lines) {
               float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
               RegionLine<LUT_SMEM, OCC>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, lut_g, lut_s, L[k],
-                                        handle ? &rocc : nullptr, i);
+                                        handle ? &rocc : nullptr, i, use_rchk ? &rchk : nullptr);
             }
           }
-          if (!OCC || !handle) break;
+          if (!OCC || !(handle || handle_modeled)) break;
           int survivors = 0;
 #pragma unroll
           for (int k = 0; k < K; ++k) survivors += __syncthreads_count(L[k].valid);
           if (survivors >= body.rp.min_n_unoccluded_lines) break;
           handle = false;
+          handle_modeled = false;
+          rchk.depth = nullptr;
+          use_rchk = rchk.silhouette != nullptr;
         }
       }
       M3TB_STAMP();  // region lines (thread 0's own line)
@@ -1201,6 +1380,22 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
                    (args.iteration - body.first_iteration) >= body.dp.n_unoccluded_iterations;
           if (handle) offs = dmodel->depth_offsets + size_t(view_d) * dmodel->n_points * kDepthOffsets;
         }
+        RenderChecks dchk;  // silhouette checking in both passes (:264-270), modeled occlusions in the first
+        bool use_dchk = false, handle_modeled = false;
+        if (OCC) {
+          const RenderingDev& sr = body.rend[RS_DEPTH_SILHOUETTE];
+          const RenderingDev& dr = body.rend[RS_DEPTH_DEPTH];
+          dchk.silhouette = (body.dp.use_silhouette_checking && sr.image && sr.visible) ? &sr : nullptr;
+          handle_modeled = body.dp.model_occlusions && dr.image && dr.visible && dmodel->depth_offsets != nullptr &&
+                           (args.iteration - body.first_iteration) >= body.dp.n_unoccluded_iterations;
+          dchk.depth = handle_modeled ? &dr : nullptr;
+          dchk.offsets = nullptr;
+          dchk.modeled_offset_id = 0;
+          dchk.radius = body.dp.modeled_occlusion_radius;
+          dchk.threshold = body.dp.modeled_occlusion_threshold;
+          dchk.offset_radius = body.dp.modeled_depth_offset_radius;
+          use_dchk = dchk.silhouette != nullptr || dchk.depth != nullptr;
+        }
         for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
           for (int k = 0; k < K; ++k) {
@@ -1208,16 +1403,23 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
             P[k].valid = false;
             if (i < n_points) {
               float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
+              RenderChecks mine = dchk;  // per-point depth offsets
+              if (OCC && dmodel->depth_offsets)
+                mine.offsets = dmodel->depth_offsets + (size_t(view_d) * dmodel->n_points + i) * kDepthOffsets;
               DepthPoint<OCC>(dit, body.dp, p0, p1, dframe, dtile, dtile_px, P[k],
-                              handle ? offs + size_t(i) * kDepthOffsets : nullptr, dmodel->stride_depth_offset);
+                              handle ? offs + size_t(i) * kDepthOffsets : nullptr, dmodel->stride_depth_offset,
+                              use_dchk ? &mine : nullptr);
             }
           }
-          if (!OCC || !handle) break;
+          if (!OCC || !(handle || handle_modeled)) break;
           int survivors = 0;
 #pragma unroll
           for (int k = 0; k < K; ++k) survivors += __syncthreads_count(P[k].valid);
           if (survivors >= body.dp.min_n_unoccluded_points) break;
           handle = false;
+          handle_modeled = false;
+          dchk.depth = nullptr;
+          use_dchk = dchk.silhouette != nullptr;
         }
       }
     }
@@ -1780,6 +1982,12 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     occ.radius = rp.measured_occlusion_radius; occ.threshold = rp.measured_occlusion_threshold;
     occ.frame = &dframe; occ.tile = &no_tile; occ.tile_px = nullptr;
   }
+  // renderer-image checks (:1031-1043): modeled occlusions with handle_occlusions, region checking always
+  const RenderingDev& rdep = body.rend[RS_REGION_DEPTH];
+  const RenderingDev& rsil = body.rend[RS_REGION_SILHOUETTE];
+  const bool model_on = handle_occlusions && rp.model_occlusions && rdep.image && rdep.visible && model.depth_offsets != nullptr;
+  const bool region_checking = rp.use_region_checking && rsil.image && rsil.visible;
+  const int modeled_offset_id = int(rp.modeled_depth_offset_radius / model.stride_depth_offset + 0.5f);
   for (int i = tid; i < n_lines; i += kBlockThreads) {
     float4 p0 = __ldg(pts + 2 * i), p1 = __ldg(pts + 2 * i + 1);
     float x, y, z;
@@ -1789,8 +1997,22 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     float center_v = y * it.fv / z + it.ppv;
     int icu = int(center_u + 0.5f), icv = int(center_v + 0.5f);
     if (icu < 0 || icu > it.w_m1 || icv < 0 || icv > it.h_m1) continue;
+    if (model_on) {  // :1079-1084
+      const float meter_to_pixel = (it.fu / z) * rdep.scale;
+      const float diameter = 2.0f * rp.modeled_occlusion_radius * meter_to_pixel;
+      const float depth_offset = __ldg(model.depth_offsets + (size_t(view) * model.n_points + i) * kDepthOffsets + modeled_offset_id);
+      if (!ModeledWindowUnoccluded(rdep, center_u, center_v, diameter, z - depth_offset - rp.modeled_occlusion_threshold)) continue;
+    }
     if (occ_on && !LineUnoccludedMeasured(occ, p0.x, p0.y, p0.z, i)) continue;  // :1086-1089
     float length_f = rp.max_considered_line_length, length_b = rp.max_considered_line_length;
+    if (region_checking) {  // :1092-1099
+      float rnu = it.b2c[0] * p0.w + it.b2c[1] * p1.x + it.b2c[2] * p1.y;
+      float rnv = it.b2c[4] * p0.w + it.b2c[5] * p1.x + it.b2c[6] * p1.y;
+      const float zz = rnu * rnu + rnv * rnv;
+      if (zz > 0.0f) { const float n = sqrtf(zz); rnu /= n; rnv /= n; }
+      DynamicRegionDistance(rsil, rp.max_considered_line_length, rp.unconsidered_line_length, center_u, center_v, rnu, rnv,
+                            length_f, length_b);
+    }
     float l_f = p1.z * it.fu / z;
     float l_b = p1.w * it.fu / z;
     length_f = fminf(length_f, l_f - 2.0f * rp.unconsidered_line_length);

@@ -177,6 +177,12 @@ class RegionSettings:
     measured_occlusion_threshold: float = 0.03
     n_unoccluded_iterations: int = 10
     min_n_unoccluded_lines: int = 0
+    # checks on renderer images (region_modality.h:424-431)
+    model_occlusions: bool = False
+    modeled_depth_offset_radius: float = 0.01
+    modeled_occlusion_radius: float = 0.01
+    modeled_occlusion_threshold: float = 0.03
+    use_region_checking: bool = False
 
 
 @dataclass
@@ -195,6 +201,27 @@ class DepthSettings:
     measured_occlusion_threshold: float = 0.03
     n_unoccluded_iterations: int = 10
     min_n_unoccluded_points: int = 0
+    # checks on renderer images (depth_modality.h:305-312)
+    model_occlusions: bool = False
+    modeled_depth_offset_radius: float = 0.01
+    modeled_occlusion_radius: float = 0.01
+    modeled_occlusion_threshold: float = 0.03
+    use_silhouette_checking: bool = False
+
+
+@dataclass
+class Rendering:
+    """One FocusedRenderer output for one body in one camera (renderer.h:156-230): `image` is the focused depth image
+    (u16, depth = a / (b - value), renderer.cpp:511-513) or the focused silhouette image (u8 ids); the focused image
+    shows the square [corner, corner + image_size / scale) of the camera image."""
+    image: np.ndarray
+    corner_u: float
+    corner_v: float
+    scale: float
+    projection_term_a: float = 0.0
+    projection_term_b: float = 0.0
+    id: int = 0
+    visible: bool = True
 
 
 @dataclass
@@ -221,6 +248,7 @@ class Workload:
     seed: int = 0
     notes: dict = field(default_factory=dict)
     structures: list | None = None          # [StructureSpec] (kinematic structures, config 5); None = rigid bodies
+    renderings: dict | None = None          # {body: {"region_depth" | "region_silhouette" | "depth_depth" | "depth_silhouette": Rendering}}
 
     @property
     def lines_per_body(self):
@@ -345,6 +373,49 @@ def add_occluder(wl: Workload, body: int, side="left", cover=0.45, gap_m=0.12, c
         z = P[..., 2] + rng.normal(0.0, 0.001, size=P.shape[:2])
         wl.depth_frames[body][m] = np.clip(np.rint(z[m] / wl.depth_scale), 1, 65535).astype(np.uint16)
     wl.notes.setdefault("occluders", []).append(dict(body=body, side=side, cover=cover, z=z_occ))
+
+
+def add_renderings(wl: Workload, image_size=200, z_min=0.02, z_max=5.0, occluder_bodies=(), region_id=7, seed=0):
+    """Synthetic stand-ins for what FocusedDepthRenderer / FocusedSilhouetteRenderer hand to the modalities (the
+    OpenGL renderers stay with the caller): for every body and both cameras a focused depth image and a focused
+    silhouette image of the body AT ITS START POSE, computed by the same ray caster that makes the frames, with
+    FocusedRenderer's geometry (corner, scale: renderer.cpp:385-395; projection terms: :568-569). For bodies listed
+    in occluder_bodies a nearer fronto-parallel plane covers the left part of the focused images (another body's id in
+    the silhouette, its depth in the depth rendering), so that the checks reject some lines / points."""
+    wl.renderings = {}
+    a = z_max * z_min * 65535.0 / (z_max - z_min)
+    b = z_max * 65535.0 / (z_max - z_min)
+    for body in range(wl.n_bodies):
+        per = {}
+        for kind, intr, w2c in (("region", wl.color_intrinsics, wl.color_world2camera),
+                                ("depth", wl.depth_intrinsics, wl.depth_world2camera)):
+            if (kind == "region" and not wl.region) or (kind == "depth" and not wl.depth):
+                continue
+            b2c = pose_mul(w2c, wl.start_body2world[body])
+            z = float(b2c[2, 3])
+            cu, cv = b2c[0, 3] * intr.fu / z + intr.ppu, b2c[1, 3] * intr.fv / z + intr.ppv
+            r = 0.05  # a little more than the prism's circumradius (renderer.cpp: 2 r fu / z = the focused square)
+            d = 2.0 * r * intr.fu / z
+            corner_u, corner_v, scale = float(cu - 0.5 * d), float(cv - 0.5 * d), float(image_size / d)
+            # the focused image is a pinhole image with intrinsics (f * scale, (pp - corner) * scale)
+            fi = Intrinsics(intr.fu * scale, intr.fv * scale, (intr.ppu - corner_u) * scale, (intr.ppv - corner_v) * scale,
+                            image_size, image_size)
+            depth_mm = render_depth(fi, b2c, seed * 7919 + body, background_z=0.0, noise_sigma=0.0, invalid_fraction=0.0,
+                                    depth_scale=0.0001)  # 0.1 mm units, 0 = background
+            zmap = depth_mm.astype(np.float64) * 0.0001
+            on_body = depth_mm > 0
+            zmap[~on_body] = z_max
+            sil = np.where(on_body, region_id, 0).astype(np.uint8)
+            if body in occluder_bodies:
+                cols = slice(0, int(image_size * 0.45))
+                zmap[:, cols] = np.minimum(zmap[:, cols], z - 0.15)
+                sil[:, cols] = region_id + 1
+            value = np.clip(np.rint(b - a / zmap), 0, 65535).astype(np.uint16)
+            per[f"{kind}_depth"] = Rendering(np.ascontiguousarray(value), corner_u, corner_v, scale, float(np.float32(a)),
+                                             float(np.float32(b)), 0, True)
+            per[f"{kind}_silhouette"] = Rendering(np.ascontiguousarray(sil), corner_u, corner_v, scale, 0.0, 0.0, region_id, True)
+        wl.renderings[body] = per
+    return wl
 
 
 PRESETS = {

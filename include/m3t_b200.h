@@ -84,6 +84,12 @@ typedef struct m3tb_region_params {
   float measured_occlusion_threshold; /* 0.03 */
   int32_t n_unoccluded_iterations; /* 10 */
   int32_t min_n_unoccluded_lines;  /* 0 */
+  /* checks that read renderer images (handed over with m3tb_upload_*_rendering), region_modality.h:424-431 */
+  int32_t model_occlusions;        /* 0  RegionModality::ModelOcclusions (focused depth rendering) */
+  float modeled_depth_offset_radius;  /* 0.01 */
+  float modeled_occlusion_radius;     /* 0.01 */
+  float modeled_occlusion_threshold;  /* 0.03 */
+  int32_t use_region_checking;     /* 0  RegionModality::UseRegionChecking (focused silhouette rendering) */
 } m3tb_region_params;
 
 /* Parameters of m3t::DepthModality, defaults depth_modality.h:302-321 */
@@ -103,6 +109,12 @@ typedef struct m3tb_depth_params {
   float measured_occlusion_threshold; /* 0.03 */
   int32_t n_unoccluded_iterations; /* 10 */
   int32_t min_n_unoccluded_points; /* 0 */
+  /* checks that read renderer images, depth_modality.h:305-312 */
+  int32_t model_occlusions;        /* 0  DepthModality::ModelOcclusions (focused depth rendering) */
+  float modeled_depth_offset_radius;  /* 0.01 */
+  float modeled_occlusion_radius;     /* 0.01 */
+  float modeled_occlusion_threshold;  /* 0.03 */
+  int32_t use_silhouette_checking; /* 0  DepthModality::UseSilhouetteChecking (focused silhouette rendering) */
 } m3tb_depth_params;
 
 /* Parameters of m3t::Optimizer, defaults optimizer.h:52-53 */
@@ -217,6 +229,28 @@ int m3tb_detach_frames(m3tb_ctx* ctx);
 /* Same, for frames that already live in device memory (device-resident pipelines, bench `value`). */
 int m3tb_upload_color_device(m3tb_ctx* ctx, int cam, const void* dev_bgr, size_t pitch);
 int m3tb_upload_depth_device(m3tb_ctx* ctx, int cam, const void* dev_depth, size_t pitch);
+
+/* Renderer images for the checks that need them (the renderers themselves - OpenGL - stay with the caller):
+ * FocusedDepthRenderer::focused_depth_image() for modeled occlusion handling (region_modality.cpp:1391-1431,
+ * depth_modality.cpp:778-824) and FocusedSilhouetteRenderer::focused_silhouette_image() for region checking
+ * (region_modality.cpp:1157-1223,1293-1341) / silhouette checking (depth_modality.cpp:728-734).
+ * `modality`: 0 = the body's RegionModality (renderers of the colour camera), 1 = its DepthModality (depth camera).
+ * image_size x image_size pixels, `pitch` bytes per row, host or device memory; corner_u / corner_v / scale as
+ * FocusedRenderer reports them (renderer.h:195-197), projection terms as FocusedDepthRenderer::Depth uses them
+ * (renderer.cpp:511-513: depth = a / (b - value)), `id` = Body::region_id() (region) / Body::body_id() (depth) the
+ * silhouette is compared with, `visible` = FocusedRenderer::IsBodyVisible (0: the check is skipped, as in the
+ * reference). The image is copied; call again whenever the renderer has produced a new one. */
+typedef struct m3tb_rendering {
+  const void* image;
+  int32_t image_size;
+  size_t pitch;
+  float corner_u, corner_v, scale;
+  float projection_term_a, projection_term_b; /* depth renderings only */
+  int32_t id;                                 /* silhouette renderings only */
+  int32_t visible;
+} m3tb_rendering;
+int m3tb_upload_depth_rendering(m3tb_ctx* ctx, int body, int modality, const m3tb_rendering* rendering);
+int m3tb_upload_silhouette_rendering(m3tb_ctx* ctx, int body, int modality, const m3tb_rendering* rendering);
 
 /* Loader-style batch ingest: `count` frames for cameras [first_cam, first_cam+count), frame k at
  * base + k*frame_stride bytes. Cameras of equal size share one device pool, so this is a single

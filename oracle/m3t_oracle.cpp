@@ -679,6 +679,9 @@ void orc_region_params_default(orc_region_params* p) {  // region_modality.h:411
   p->measured_occlusion_threshold = 0.03f;
   p->n_unoccluded_iterations = 10;
   p->min_n_unoccluded_lines = 0;
+  p->modeled_depth_offset_radius = 0.01f;
+  p->modeled_occlusion_radius = 0.01f;
+  p->modeled_occlusion_threshold = 0.03f;
 }
 
 void orc_depth_params_default(orc_depth_params* p) {  // depth_modality.h:302-321
@@ -695,6 +698,9 @@ void orc_depth_params_default(orc_depth_params* p) {  // depth_modality.h:302-32
   p->measured_occlusion_threshold = 0.03f;
   p->n_unoccluded_iterations = 10;
   p->min_n_unoccluded_points = 0;
+  p->modeled_depth_offset_radius = 0.01f;
+  p->modeled_occlusion_radius = 0.01f;
+  p->modeled_occlusion_threshold = 0.03f;
 }
 
 void orc_pose_multiply(const float a[12], const float b[12], float out[12]) { PoseMul(a, b, out); }
@@ -798,6 +804,138 @@ int RegionOffsetId(const orc_region_params* p, const orc_model* model) {
   if (p->measured_depth_offset_radius > model->max_radius_depth_offset) return -1;
   return int(p->measured_depth_offset_radius / model->stride_depth_offset + 0.5f);
 }
+// modeled_depth_offset_id_ (region_modality.cpp:979-991)
+int RegionModeledOffsetId(const orc_region_params* p, const orc_model* model) {
+  if (p->modeled_depth_offset_radius > model->max_radius_depth_offset) return -1;
+  return int(p->modeled_depth_offset_radius / model->stride_depth_offset + 0.5f);
+}
+
+constexpr int kNRegionStride = 5;      // region_modality.h:146
+constexpr float kRegionOffset = 2.0f;  // region_modality.h:147
+
+inline uint8_t SilhouetteAt(const orc_rendering* r, int v, int u) {
+  return reinterpret_cast<const uint8_t*>(r->image)[size_t(v) * r->pitch + size_t(u)];
+}
+
+// The strided minimum scan shared by RegionModality::IsLineUnoccludedModeled (region_modality.cpp:1391-1431) and
+// DepthModality::IsPointUnoccludedModeled (depth_modality.cpp:778-824), in the focused depth rendering.
+bool ModeledWindowUnoccluded(const orc_rendering* r, float center_u, float center_v, float diameter, float min_allowed_depth) {
+  int stride = int(diameter / kMaxNOcclusionStrides + 1.0f);
+  int n_strides = int(diameter / stride + 0.5f);
+  int rounded_diameter = n_strides * stride;
+  float rounded_radius = 0.5f * float(rounded_diameter);
+  float focused_center_u = (center_u - r->corner_u) * r->scale;
+  float focused_center_v = (center_v - r->corner_v) * r->scale;
+  int u_min = int(focused_center_u - rounded_radius + 0.5f);
+  int v_min = int(focused_center_v - rounded_radius + 0.5f);
+  int u_max = u_min + rounded_diameter;
+  int v_max = v_min + rounded_diameter;
+  u_min = std::max(u_min, 0);
+  v_min = std::max(v_min, 0);
+  u_max = std::min(u_max, r->image_size - 1);
+  v_max = std::min(v_max, r->image_size - 1);
+  uint16_t min_depth_value = 65535;
+  for (int v = v_min; v <= v_max; v += stride) {
+    const uint16_t* row = reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(r->image) + size_t(v) * r->pitch);
+    for (int u = u_min; u <= u_max; u += stride) min_depth_value = std::min(min_depth_value, row[u]);
+  }
+  float min_depth = r->projection_term_a / (r->projection_term_b - float(min_depth_value));  // FocusedDepthRenderer::Depth
+  return min_depth > min_allowed_depth;
+}
+
+// RegionModality::IsLineUnoccludedModeled (region_modality.cpp:1391-1431)
+bool LineUnoccludedModeled(const orc_region_params* p, const orc_rendering* r, float fu, float center_u, float center_v,
+                           float depth, float depth_offset) {
+  float meter_to_pixel = (fu / depth) * r->scale;
+  float diameter = 2.0f * p->modeled_occlusion_radius * meter_to_pixel;
+  return ModeledWindowUnoccluded(r, center_u, center_v, diameter, depth - depth_offset - p->modeled_occlusion_threshold);
+}
+
+// RegionModality::IsDynamicLineRegionSufficient (region_modality.cpp:1293-1341)
+bool DynamicLineRegionSufficient(const orc_region_params* p, const orc_rendering* r, float fscale, float center_u,
+                                 float center_v, float normal_u, float normal_v) {
+  const uint8_t region_id = uint8_t(r->id);
+  const float fsize = float(r->image_size);
+  float focused_min_continuous_distance = p->min_continuous_distance * fscale * r->scale;
+  float focused_stride = std::max((focused_min_continuous_distance - kRegionOffset) / float(kNRegionStride), 0.0f);
+  float stride_u = focused_stride * normal_u;
+  float stride_v = focused_stride * normal_v;
+  float offset_u = kRegionOffset * normal_u;
+  float offset_v = kRegionOffset * normal_v;
+  float focused_center_u = 0.5f + (center_u - r->corner_u) * r->scale;
+  float focused_center_v = 0.5f + (center_v - r->corner_v) * r->scale;
+  // foreground region. The reference reads silhouette_image.at<uchar>(int(v), int(u)) without a bounds test here; a
+  // sample outside the focused image is undefined behaviour there - it is treated as "not this region" on both sides.
+  float u = focused_center_u - offset_u;
+  float v = focused_center_v - offset_v;
+  for (int i = 0; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) return false;
+    if (SilhouetteAt(r, int(v), int(u)) != region_id) return false;
+    u -= stride_u;
+    v -= stride_v;
+  }
+  // background region
+  u = focused_center_u + offset_u;
+  v = focused_center_v + offset_v;
+  for (int i = 0; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) break;
+    if (SilhouetteAt(r, int(v), int(u)) == region_id) return false;
+    u += stride_u;
+    v += stride_v;
+  }
+  return true;
+}
+
+// RegionModality::DynamicRegionDistance (region_modality.cpp:1157-1223), including its quirk: a background sample of
+// the own region at i > i_start overwrites the FOREGROUND distance (:1218)
+void DynamicRegionDistance(const orc_region_params* p, const orc_rendering* r, float center_u, float center_v,
+                           float normal_u, float normal_v, float* dynamic_foreground_distance,
+                           float* dynamic_background_distance) {
+  const uint8_t region_id = uint8_t(r->id);
+  const float fsize = float(r->image_size);
+  float stride = p->max_considered_line_length / float(kNRegionStride);
+  float focused_stride = stride * r->scale;
+  float focused_stride_u = focused_stride * normal_u;
+  float focused_stride_v = focused_stride * normal_v;
+  float delta_start = kRegionOffset / r->scale - p->unconsidered_line_length;
+  int i_start = std::max(int(delta_start / stride + 1.0f), 0);
+  float offset = p->unconsidered_line_length + float(i_start) * stride;
+  float focused_offset = offset * r->scale;
+  float focused_offset_u = focused_offset * normal_u;
+  float focused_offset_v = focused_offset * normal_v;
+  float focused_center_u = 0.5f + (center_u - r->corner_u) * r->scale;
+  float focused_center_v = 0.5f + (center_v - r->corner_v) * r->scale;
+  float u = focused_center_u - focused_offset_u;
+  float v = focused_center_v - focused_offset_v;
+  for (int i = i_start; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) {
+      *dynamic_foreground_distance = stride * float(i);
+      break;
+    }
+    if (SilhouetteAt(r, int(v), int(u)) != region_id) {
+      if (i == i_start) *dynamic_foreground_distance = 0.0f;
+      else *dynamic_foreground_distance = stride * float(i);
+      break;
+    }
+    u -= focused_stride_u;
+    v -= focused_stride_v;
+  }
+  u = focused_center_u + focused_offset_u;
+  v = focused_center_v + focused_offset_v;
+  for (int i = i_start; i <= kNRegionStride; ++i) {
+    if (u >= fsize || u < 0.0f || v >= fsize || v < 0.0f) {
+      *dynamic_background_distance = p->max_considered_line_length;
+      break;
+    }
+    if (SilhouetteAt(r, int(v), int(u)) == region_id) {
+      if (i == i_start) *dynamic_background_distance = 0.0f;
+      else *dynamic_foreground_distance = stride * float(i);  // sic (:1218)
+      break;
+    }
+    u += focused_stride_u;
+    v += focused_stride_v;
+  }
+}
 }  // namespace
 extern "C" {
 
@@ -817,6 +955,12 @@ void orc_region_add_line_pixels_occ(const orc_region_params* p, const orc_model*
     PoseMul(occlusion_depth->world2camera, body2world, body2depth_camera);  // region_modality.cpp:1003-1005
     offset_id = std::max(0, RegionOffsetId(p, model));
   }
+  // renderer-image checks (:1031-1043): modeled occlusions only with handle_occlusions, region checking always
+  const orc_rendering* dr = c->depth_rendering;
+  const orc_rendering* sr = c->silhouette_rendering;
+  const bool model_occ = handle_occlusions && p->model_occlusions && dr && dr->visible;
+  const bool region_checking = p->use_region_checking && sr && sr->visible;
+  const int modeled_offset_id = std::max(0, RegionModeledOffsetId(p, model));
   RegionVars v;
   RegionPrecalc(p, c, body2world, 0, rotation_mode, &v);
   int view = ClosestView(model, v.body2camera, rotation_mode);
@@ -837,10 +981,18 @@ void orc_region_add_line_pixels_occ(const orc_region_params* p, const orc_model*
     int i_center_u = int(center_u + 0.5f);
     int i_center_v = int(center_v + 0.5f);
     if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+    if (model_occ && !LineUnoccludedModeled(p, dr, v.fu, center_u, center_v, cc[2], dp[8 + modeled_offset_id]))
+      continue;  // :1079-1084
     if (occ && !LineUnoccludedMeasured(p, occlusion_depth, body2depth_camera, center_f_body, dp[8 + offset_id]))
       continue;  // :1086-1089
     float length_f = p->max_considered_line_length;
     float length_b = p->max_considered_line_length;
+    if (region_checking) {  // :1092-1099
+      float nrm[2] = {v.rot[0] * normal_f_body[0] + v.rot[1] * normal_f_body[1] + v.rot[2] * normal_f_body[2],
+                      v.rot[3] * normal_f_body[0] + v.rot[4] * normal_f_body[1] + v.rot[5] * normal_f_body[2]};
+      Normalize2(nrm);
+      DynamicRegionDistance(p, sr, center_u, center_v, nrm[0], nrm[1], &length_f, &length_b);
+    }
     float l_f = foreground_distance * v.fu / cc[2];
     float l_b = background_distance * v.fu / cc[2];
     length_f = std::fmin(length_f, l_f - 2.0f * p->unconsidered_line_length);
@@ -905,12 +1057,18 @@ int orc_region_correspondences(const orc_region_params* p, const orc_model* mode
     PoseMul(occlusion_depth->world2camera, body2world, body2depth_camera);
     offset_id = std::max(0, RegionOffsetId(p, model));
   }
+  const orc_rendering* dr = c->depth_rendering;
+  const orc_rendering* sr = c->silhouette_rendering;
+  const bool can_model = p->model_occlusions && dr && dr->visible;            // :397-401
+  const bool region_checking = p->use_region_checking && sr && sr->visible;   // :402-408, both passes
+  const int modeled_offset_id = std::max(0, RegionModeledOffsetId(p, model));
   // Two passes (:435-463): the first handles occlusions once the modality has run n_unoccluded_iterations; if too
   // few lines survive, everything is recomputed without occlusion handling. Without an occlusion source the two
   // passes are identical, so one suffices.
   for (int j = 0; j < 2; ++j) {
     const bool handle_occlusions = j == 0 && (iteration - first_iteration) >= p->n_unoccluded_iterations;
     const bool occ = handle_occlusions && can_measure;
+    const bool mocc = handle_occlusions && can_model;
     int survivors = 0;
     for (int i = 0; i < n_lines; ++i) {
       const float* dp = pts + size_t(i) * ORC_REGION_POINT_FLOATS;
@@ -935,7 +1093,12 @@ int orc_region_correspondences(const orc_region_params* p, const orc_model* mode
       int i_center_u = int(L.center_u + 0.5f);
       int i_center_v = int(L.center_v + 0.5f);
       if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+      if (region_checking &&
+          !DynamicLineRegionSufficient(p, sr, v.fscale, L.center_u, L.center_v, L.normal_u, L.normal_v))
+        continue;  // :1269-1274
       if (occ && !LineUnoccludedMeasured(p, occlusion_depth, body2depth_camera, dp, dp[8 + offset_id])) continue;
+      if (mocc && !LineUnoccludedModeled(p, dr, v.fu, L.center_u, L.center_v, cc[2], dp[8 + modeled_offset_id]))
+        continue;  // :1283-1289
       if (!SegmentProbabilities(v, c, hist_f, hist_b, L.center_u, L.center_v, L.normal_u, L.normal_v, sf, sb,
                                 &L.normal_component_to_scale, &L.delta_r))
         continue;
@@ -944,7 +1107,7 @@ int orc_region_correspondences(const orc_region_params* p, const orc_model* mode
       L.valid = 1;
       survivors++;
     }
-    if (!occ || survivors >= p->min_n_unoccluded_lines) break;
+    if (!(occ || mocc) || survivors >= p->min_n_unoccluded_lines) break;
   }
   return n_lines;
 }
@@ -1010,8 +1173,14 @@ int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model,
                                model->view_scalars ? model->view_scalars[view] : 0.0f, model->max_view_scalar,
                                model->n_points);
   const float* pts = model->points + size_t(view) * model->n_points * ORC_DEPTH_POINT_FLOATS;
+  const orc_rendering* dr = f->depth_rendering;
+  const orc_rendering* sr = f->silhouette_rendering;
+  const bool can_model = p->model_occlusions && dr && dr->visible;              // :259-263
+  const bool silhouette_checking = p->use_silhouette_checking && sr && sr->visible;  // :264-270, both passes
   for (int j = 0; j < 2; ++j) {  // :295-313
-    const bool occ = j == 0 && (iteration - first_iteration) >= p->n_unoccluded_iterations && p->measure_occlusions;
+    const bool handle = j == 0 && (iteration - first_iteration) >= p->n_unoccluded_iterations;
+    const bool occ = handle && p->measure_occlusions;
+    const bool mocc = handle && can_model;
     int survivors = 0;
     for (int i = 0; i < n_points; ++i) {
       const float* dp = pts + size_t(i) * ORC_DEPTH_POINT_FLOATS;
@@ -1030,6 +1199,13 @@ int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model,
       int i_center_u = int(center_u + 0.5f);
       int i_center_v = int(center_v + 0.5f);
       if (i_center_u < 0 || i_center_u > v.w_m1 || i_center_v < 0 || i_center_v > v.h_m1) continue;
+      if (silhouette_checking) {  // IsPointOnValidSilhouette (:728-734) via FocusedSilhouetteRenderer::SilhouetteValue
+        int su = int((float(i_center_u) - sr->corner_u) * sr->scale + 0.5f);
+        int sv = int((float(i_center_v) - sr->corner_v) * sr->scale + 0.5f);
+        // (outside the focused image the reference reads out of bounds; treated as "another body" on both sides)
+        if (su < 0 || su >= sr->image_size || sv < 0 || sv >= sr->image_size) continue;
+        if (SilhouetteAt(sr, sv, su) != uint8_t(sr->id)) continue;
+      }
       if (occ) {  // IsPointUnoccludedMeasured (:736-776) with the depth offset selected in CalculateBasicPointData
         float radius = p->measured_depth_offset_radius;
         if (p->use_depth_scaling) radius *= depth;
@@ -1043,11 +1219,24 @@ int orc_depth_correspondences(const orc_depth_params* p, const orc_model* model,
         if (!WindowUnoccluded(f, center_u, center_v, diameter, (depth - measured_depth_offset - threshold) / v.depth_scale))
           continue;
       }
+      if (mocc) {  // IsPointUnoccludedModeled (:778-824), depth offset selected in CalculateBasicPointData (:682-693)
+        float radius = p->modeled_depth_offset_radius;
+        if (p->use_depth_scaling) radius *= depth;
+        int id = int(radius / model->stride_depth_offset + 0.5f);
+        if (id >= ORC_N_DEPTH_OFFSETS) id = ORC_N_DEPTH_OFFSETS - 1;
+        float modeled_depth_offset = dp[6 + id];
+        float meter_to_pixel = v.fu * dr->scale;
+        if (!p->use_depth_scaling) meter_to_pixel /= depth;
+        float diameter = 2.0f * p->modeled_occlusion_radius * meter_to_pixel;
+        float threshold = p->modeled_occlusion_threshold;
+        if (p->use_depth_scaling) threshold *= depth;
+        if (!ModeledWindowUnoccluded(dr, center_u, center_v, diameter, depth - modeled_depth_offset - threshold)) continue;
+      }
       if (!FindCorrespondence(p, v, f, cc, center_u, center_v, depth, P.correspondence_center_f_camera)) continue;
       P.valid = 1;
       survivors++;
     }
-    if (!occ || survivors >= p->min_n_unoccluded_points) break;
+    if (!(occ || mocc) || survivors >= p->min_n_unoccluded_points) break;
   }
   return n_points;
 }

@@ -36,7 +36,10 @@ class RegionParams(C.Structure):
                 ("unconsidered_line_length", C.c_float), ("max_considered_line_length", C.c_float),
                 ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
                 ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
-                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32)]
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_lines", C.c_int32),
+                ("model_occlusions", C.c_int32), ("modeled_depth_offset_radius", C.c_float),
+                ("modeled_occlusion_radius", C.c_float), ("modeled_occlusion_threshold", C.c_float),
+                ("use_region_checking", C.c_int32)]
 
 
 class DepthParams(C.Structure):
@@ -46,7 +49,10 @@ class DepthParams(C.Structure):
                 ("n_standard_deviations", C.c_int32), ("standard_deviations", C.c_float * MAX_SCHEDULE),
                 ("measure_occlusions", C.c_int32), ("measured_depth_offset_radius", C.c_float),
                 ("measured_occlusion_radius", C.c_float), ("measured_occlusion_threshold", C.c_float),
-                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32)]
+                ("n_unoccluded_iterations", C.c_int32), ("min_n_unoccluded_points", C.c_int32),
+                ("model_occlusions", C.c_int32), ("modeled_depth_offset_radius", C.c_float),
+                ("modeled_occlusion_radius", C.c_float), ("modeled_occlusion_threshold", C.c_float),
+                ("use_silhouette_checking", C.c_int32)]
 
 
 class RegionLine(C.Structure):
@@ -77,14 +83,35 @@ class Model(C.Structure):
                 ("max_view_scalar", C.c_float)]
 
 
+class Rendering(C.Structure):
+    """orc_rendering: one FocusedRenderer output (focused depth image or focused silhouette image)."""
+    _fields_ = [("image", C.c_void_p), ("image_size", C.c_int32), ("pitch", C.c_size_t), ("corner_u", C.c_float),
+                ("corner_v", C.c_float), ("scale", C.c_float), ("projection_term_a", C.c_float),
+                ("projection_term_b", C.c_float), ("id", C.c_int32), ("visible", C.c_int32)]
+
+
 class ColorFrame(C.Structure):
     _fields_ = [("intrinsics", Intrinsics), ("world2camera", C.c_float * 12), ("bgr", C.c_void_p),
-                ("pitch", C.c_size_t)]
+                ("pitch", C.c_size_t), ("depth_rendering", C.POINTER(Rendering)),
+                ("silhouette_rendering", C.POINTER(Rendering))]
 
 
 class DepthFrame(C.Structure):
     _fields_ = [("intrinsics", Intrinsics), ("world2camera", C.c_float * 12), ("depth", C.c_void_p),
-                ("pitch", C.c_size_t), ("depth_scale", C.c_float)]
+                ("pitch", C.c_size_t), ("depth_scale", C.c_float), ("depth_rendering", C.POINTER(Rendering)),
+                ("silhouette_rendering", C.POINTER(Rendering))]
+
+
+def make_rendering(r) -> Rendering:
+    """r: synth.Rendering (image ndarray [size, size] u16 / u8, corner_u, corner_v, scale, a, b, id, visible)."""
+    o = Rendering()
+    o.image = r.image.ctypes.data
+    o.image_size = r.image.shape[0]
+    o.pitch = r.image.strides[0]
+    o.corner_u, o.corner_v, o.scale = r.corner_u, r.corner_v, r.scale
+    o.projection_term_a, o.projection_term_b = r.projection_term_a, r.projection_term_b
+    o.id, o.visible = int(r.id), int(r.visible)
+    return o
 
 
 class Body(C.Structure):
@@ -214,8 +241,11 @@ def region_params(settings) -> RegionParams:
               "n_global_iterations", "n_histogram_bins", "learning_rate_f", "learning_rate_b",
               "unconsidered_line_length", "max_considered_line_length", "reference_contour_length",
               "measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
-              "n_unoccluded_iterations", "min_n_unoccluded_lines"):
+              "n_unoccluded_iterations", "min_n_unoccluded_lines", "modeled_depth_offset_radius",
+              "modeled_occlusion_radius", "modeled_occlusion_threshold"):
         setattr(p, k, getattr(settings, k))
+    p.model_occlusions = int(settings.model_occlusions)
+    p.use_region_checking = int(settings.use_region_checking)
     p.use_adaptive_coverage = int(settings.use_adaptive_coverage)
     p.measure_occlusions = int(settings.measure_occlusions)
     p.n_scales = len(settings.scales)
@@ -239,8 +269,11 @@ def depth_params(settings) -> DepthParams:
     p.use_depth_scaling = int(settings.use_depth_scaling)
     p.measure_occlusions = int(settings.measure_occlusions)
     for k in ("measured_depth_offset_radius", "measured_occlusion_radius", "measured_occlusion_threshold",
-              "n_unoccluded_iterations", "min_n_unoccluded_points"):
+              "n_unoccluded_iterations", "min_n_unoccluded_points", "modeled_depth_offset_radius",
+              "modeled_occlusion_radius", "modeled_occlusion_threshold"):
         setattr(p, k, getattr(settings, k))
+    p.model_occlusions = int(settings.model_occlusions)
+    p.use_silhouette_checking = int(settings.use_silhouette_checking)
     p.n_considered_distances = len(settings.considered_distances)
     p.n_standard_deviations = len(settings.standard_deviations)
     for i, s in enumerate(settings.considered_distances):
@@ -342,6 +375,15 @@ class OracleTracker:
         self.color_frames = (ColorFrame * nb)()
         self.depth_frames = (DepthFrame * nb)()
         self.occlusion_frames = (DepthFrame * nb)()  # RegionModality::depth_camera_ptr (measure_occlusions)
+        self.renderings = {}  # (body, key) -> Rendering, kept alive with the tracker
+        rend = getattr(wl, "renderings", None) or {}
+
+        def hook(b, key):
+            r = rend.get(b, {}).get(key)
+            if r is None:
+                return None
+            self.renderings[(b, key)] = make_rendering(r)
+            return C.pointer(self.renderings[(b, key)])
         nbins = wl.region.n_histogram_bins if wl.region else 1
         self.hist_f = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
         self.hist_b = np.full((nb, nbins ** 3), 1.0 / nbins ** 3, np.float32)
@@ -355,6 +397,10 @@ class OracleTracker:
                 cf.world2camera[:] = f32(wl.color_world2camera).reshape(12).tolist()
                 cf.bgr = wl.color_frames[b].ctypes.data
                 cf.pitch = wl.color_frames[b].strides[0]
+                for key, field in (("region_depth", "depth_rendering"), ("region_silhouette", "silhouette_rendering")):
+                    ptr_ = hook(b, key)
+                    if ptr_ is not None:
+                        setattr(cf, field, ptr_)
                 B.region = C.pointer(self.rp)
                 B.region_model = C.pointer(self.rm)
                 B.color = C.pointer(cf)
@@ -376,6 +422,10 @@ class OracleTracker:
                 df.depth = wl.depth_frames[b].ctypes.data
                 df.pitch = wl.depth_frames[b].strides[0]
                 df.depth_scale = wl.depth_scale
+                for key, field in (("depth_depth", "depth_rendering"), ("depth_silhouette", "silhouette_rendering")):
+                    ptr_ = hook(b, key)
+                    if ptr_ is not None:
+                        setattr(df, field, ptr_)
                 B.depth = C.pointer(self.dp)
                 B.depth_model = C.pointer(self.dm)
                 B.depth_frame = C.pointer(df)

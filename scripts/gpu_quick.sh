@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 python scripts/phase_timing2.py c4 > gpurun_out/phase2_c4.txt 2>&1
-python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e > gpurun_out/bench_c4_quick.json 2> gpurun_out/bench_c4_quick.err
+python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-e2e --no-secondary > gpurun_out/bench_c4_quick.json 2> gpurun_out/bench_c4_quick.err
 head -14 gpurun_out/phase2_c4.txt; sed -n 14,24p gpurun_out/phase2_c4.txt
 python - <<PY
 import json
