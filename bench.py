@@ -165,6 +165,30 @@ def parity_check(ctx, wl, n_sample=4):
             "pose_change_of_the_step_m": float(moved.min())}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Pin this rank's host threads (and therefore, by first touch, the pinned frame buffers it allocates next) to the
+    NUMA node its GPU hangs off. Unbound, the 8 ranks' zero-copy frame reads cross the socket interconnect for half of
+    the GPUs (GPUs 0-3 on node 0, 4-7 on node 1 on the 8-GPU boxes) and the end-to-end step time rose from 0.71 to
+    0.99 ms at N = 8 (SCALE_r01). Returns a description for the JSON line."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return {"numa_node": None, "note": "single NUMA node / not reported"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"numa_node": node, "note": "no allowed CPU on that node"}
+        os.sched_setaffinity(0, cpus)
+        return {"numa_node": node, "cpus": len(cpus), "pci": bdf}
+    except Exception as e:  # no sysfs, no permission: run unbound
+        return {"numa_node": None, "note": f"unbound ({type(e).__name__})"}
+
+
 def secondary_measurements(args, torch, dev, stream, flush):
     """Device-resident step time of the OTHER BASELINE.json configurations (configs[1], configs[2], the per-GPU shards of
     configs[4] in both joint formulations), measured exactly like `value` (CUDA events per step, L2 flushed in between),
