@@ -809,18 +809,30 @@ __device__ __forceinline__ void DepthPoint(const DepthIter& it, const DepthParam
   if (inside) {
     const uint16_t* trow = tile_px + (v_min - tile.y0) * tile.pitch - tile.x0;
     const int row_step = stride * tile.pitch;
+    // The reference's tests, restated so that most samples cost a handful of instructions (results unchanged):
+    //  * depth > min && depth < max on the raw integer sample (a u16 is exact in float: raw > m <=> raw >= floor(m) + 1);
+    //  * dz * dz >= best: the exact early-out (d2 >= dz * dz under round-to-nearest);
+    //  * a SCREEN with reciprocal multiplies instead of the two divisions: its squared distance differs from the exact
+    //    one by < 1e-7 m^2 (|tx|, |ty| < 1 m, relative error of x * (1 / f) against x / f < 2e-7), so a sample whose
+    //    screened value exceeds best by more than 1e-6 m^2 cannot pass the strict test d2 < best; everything else is
+    //    evaluated with the reference's expression, and only those values are ever stored.
+    const int raw_lo = int(floorf(fmaxf(min_depth_value, -2.0f))) + 1;
+    const int raw_hi = int(ceilf(fminf(max_depth_value, 70000.0f))) - 1;
+    const float rfu = 1.0f / it.fu, rfv = 1.0f / it.fv;
     for (int v = v_min; v <= v_max; v += stride, trow += row_step) {
       const float vy = float(v) - it.ppv;
 #pragma unroll 4
       for (int u = u_min; u <= u_max; u += stride) {
-        float depth = float(trow[u]);
-        if (depth > min_depth_value && depth < max_depth_value) {
-          depth *= it.depth_scale;
-          // exact early-out: d2 = (dx*dx + dy*dy) + dz*dz >= dz*dz under round-to-nearest, so dz*dz >= best means
-          // the strict test d2 < best below cannot succeed; skips the two divisions for most non-surface samples
+        const int raw = trow[u];
+        if (raw >= raw_lo && raw <= raw_hi) {
+          const float depth = float(raw) * it.depth_scale;
           const float dz0 = depth - z;
-          if (dz0 * dz0 >= best) continue;
-          float tx = (float(u) - it.ppu) * depth / it.fu;
+          const float dz2 = dz0 * dz0;
+          if (dz2 >= best) continue;
+          const float ux = float(u) - it.ppu;
+          const float ax = ux * depth * rfu - x, ay = vy * depth * rfv - y;
+          if (ax * ax + ay * ay + dz2 > best + 1.0e-6f) continue;
+          float tx = ux * depth / it.fu;
           float ty = vy * depth / it.fv;
           float dx = tx - x, dy = ty - y, dz = depth - z;
           float d2 = dx * dx + dy * dy + dz * dz;

@@ -528,8 +528,33 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   constexpr int kW = T / 32;
   const int body_id = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const BodyDev& body = args.bodies[body_id];
-  if (!body.set) return;
+  const BodyDev& gbody = args.bodies[body_id];
+  if (!gbody.set) return;
+  // Per-body parameters, cameras and model headers are read all over the iteration loops. With 225 KB of the SM's
+  // 228 KB configured as shared memory the L1 cache is ~3 KB, so from global memory each of those reads is an L2 round
+  // trip (long-scoreboard stalls: 2.6 cycles per issue in the r02 capture); one copy into shared memory instead.
+  __shared__ BodyDev s_body;
+  __shared__ CameraDev s_cams[2];
+  __shared__ ModelDev s_models[2];
+  {
+    const int* src = reinterpret_cast<const int*>(&gbody);
+    int* dst = reinterpret_cast<int*>(&s_body);
+    for (int k = tid; k < int(sizeof(BodyDev) / 4); k += T) dst[k] = __ldg(src + k);
+    if (gbody.has_region) {
+      const int* c = reinterpret_cast<const int*>(&args.color_cams[gbody.color_camera]);
+      const int* m = reinterpret_cast<const int*>(&args.region_models[gbody.region_model]);
+      for (int k = tid; k < int(sizeof(CameraDev) / 4); k += T) reinterpret_cast<int*>(&s_cams[0])[k] = __ldg(c + k);
+      for (int k = tid; k < int(sizeof(ModelDev) / 4); k += T) reinterpret_cast<int*>(&s_models[0])[k] = __ldg(m + k);
+    }
+    if (gbody.has_depth) {
+      const int* c = reinterpret_cast<const int*>(&args.depth_cams[gbody.depth_camera]);
+      const int* m = reinterpret_cast<const int*>(&args.depth_models[gbody.depth_model]);
+      for (int k = tid; k < int(sizeof(CameraDev) / 4); k += T) reinterpret_cast<int*>(&s_cams[1])[k] = __ldg(c + k);
+      for (int k = tid; k < int(sizeof(ModelDev) / 4); k += T) reinterpret_cast<int*>(&s_models[1])[k] = __ldg(m + k);
+    }
+  }
+  __syncthreads();
+  const BodyDev& body = s_body;
   const bool has_region = body.has_region, has_depth = body.has_depth;
   const int item = tid & (kGroup - 1);
   // Warp priority: an SM sub-partition issues from its highest-numbered eligible warp first. The lines are the critical
@@ -556,10 +581,10 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
   M3TB_STAMP2(stamp_base);
 
   // ---- prologue: pose, LUT bulk copy, ROI tiles (as in k_track) -----------------------------------------
-  const CameraDev* ccam = has_region ? &args.color_cams[body.color_camera] : nullptr;
-  const CameraDev* dcam = has_depth ? &args.depth_cams[body.depth_camera] : nullptr;
-  const ModelDev* rmodel = has_region ? &args.region_models[body.region_model] : nullptr;
-  const ModelDev* dmodel = has_depth ? &args.depth_models[body.depth_model] : nullptr;
+  const CameraDev* ccam = has_region ? &s_cams[0] : nullptr;
+  const CameraDev* dcam = has_depth ? &s_cams[1] : nullptr;
+  const ModelDev* rmodel = has_region ? &s_models[0] : nullptr;
+  const ModelDev* dmodel = has_depth ? &s_models[1] : nullptr;
   const bool do_rcorr = has_region && (args.phases & PH_REGION_CORR);
   const bool do_dcorr = has_depth && (args.phases & PH_DEPTH_CORR);
   const bool do_rgh = has_region && (args.phases & PH_REGION_GH);
@@ -640,12 +665,14 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       if (ct.w > 0) {
         const CUtensorMap* map = (args.tma_mode == 2 ? args.tmaps_global : args.bin_maps) + ((ct.w - 64) >> 5);
         MbarExpectTx(&sh.ctile_bar, unsigned(ct.w * ct.h * 2));
+#pragma unroll 1
         for (int r = 0; r < ct.h; r += kTileBoxRows)
           TensorCopyG2S(dyn + ct.offset + size_t(r) * ct.w * 2, map, ct.x0, ct.y0 + r, body.color_camera, &sh.ctile_bar);
       }
       if (dt.w > 0) {
         const CUtensorMap* map = (args.tma_mode == 2 ? args.tmaps_global + kTileWidths : args.depth_maps) + ((dt.w - 64) >> 5);
         MbarExpectTx(&sh.depth_bar, unsigned(dt.w * dt.h * 2));
+#pragma unroll 1
         for (int r = 0; r < dt.h; r += kTileBoxRows)
           TensorCopyG2S(dyn + dt.offset + size_t(r) * dt.w * 2, map, dt.x0, dt.y0 + r, body.depth_camera, &sh.depth_bar);
       }
