@@ -902,10 +902,21 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
         *p2 = val;
         __syncwarp();
         M3TB_STAMP2(stamp_base);  // cross-warp sum + normal equations
-        SolveAndUpdateSerial(sh, ccam != nullptr, dcam != nullptr);
+        // with two warp groups the depth camera's pose products are left to the point group's leader (below): they are
+        // off the critical path there, and the serial section every warp waits for gets ~700 cycles shorter
+        SolveAndUpdateSerial(sh, ccam != nullptr, dcam != nullptr && T == kGroup);
         M3TB_STAMP2(stamp_base);  // solve + pose update + pose products
       }
       __syncthreads();
+      if (T > kGroup && dcam != nullptr && point_group) {
+        if (group_leader) {
+          float pose[12];
+#pragma unroll
+          for (int i = 0; i < 12; ++i) pose[i] = sh.pose[i];
+          PublishPoseProducts(pose, false, true, false, sh);
+        }
+        GroupBarrier<T>(1);
+      }
       M3TB_STAMP2(stamp_base);  // released
     }
   }

@@ -189,28 +189,34 @@ def bind_to_gpu_numa_node(torch, local_rank):
         return {"numa_node": None, "note": f"unbound ({type(e).__name__})"}
 
 
-def secondary_measurements(args, torch, dev, stream, flush):
-    """Device-resident step time of the OTHER BASELINE.json configurations (configs[1], configs[2], the per-GPU shards of
-    configs[4] in both joint formulations), measured exactly like `value` (CUDA events per step, L2 flushed in between),
-    so that the driver's record carries them next to the headline workload. Short runs: 10 steps each."""
+def secondary_measurements(args, torch, dist, dev, stream, flush, rank, world):
+    """Device-resident step time of the OTHER BASELINE.json configurations, measured exactly like `value` (CUDA events per
+    step, L2 flushed in between, max over ranks), so that the driver's record carries them next to the headline workload.
+    One GPU: configs[1], configs[2] and the per-GPU shard of configs[4] in both joint formulations. N GPUs: configs[4]
+    weak-scaled like the headline (32 chains x 8 links per GPU; at N = 8 that is BASELINE's "256 instances sharded
+    8 x B200"; whole chains per rank, no collective on the data path). Short runs: 10 steps each. Called by ALL ranks."""
     import copy
     pkg = importlib.import_module("3dobjecttracking_b200")
     capi = importlib.import_module("3dobjecttracking_b200.capi")
     out = {}
-    for key, wname, variant in (("configs[1]", "c2", None), ("configs[2]", "c3", None),
-                                ("configs[4] projected", "c5", "projected"), ("configs[4] constrained", "c5", "constrained")):
+    todo = (("configs[4] projected", "c5", "projected"), ("configs[4] constrained", "c5", "constrained"))
+    if world == 1:
+        todo = (("configs[1]", "c2", None), ("configs[2]", "c3", None)) + todo
+    for key, wname, variant in todo:
         a = copy.copy(args)
         a.workload, a.bodies = wname, None
         if variant:
             a.variant = variant
         try:
-            _, wl = build_workload(a, 0)
+            _, wl = build_workload(a, rank)
             ctx = capi.context_from_workload(wl, device=dev.index, stream=stream.cuda_stream)
             ctx.start_modalities(0)
             poses = np.ascontiguousarray(wl.start_body2world.reshape(wl.n_bodies, 12))
             for _ in range(3):
                 ctx.set_poses(poses); ctx.reset_joint_poses(); ctx.tracking_step(0, wl.n_corr_iterations, wl.n_update_iterations)
             torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier(device_ids=[dev.index])
             l0, evs = ctx.launch_count, []
             for _ in range(10):
                 flush.zero_()
@@ -222,15 +228,21 @@ def secondary_measurements(args, torch, dev, stream, flush):
                 evs.append((e0, e1))
             torch.cuda.synchronize(dev)
             ms = sum(x.elapsed_time(y) for x, y in evs) / len(evs)
+            if world > 1:
+                t = torch.tensor([ms], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
             total_b = pkg.roofline.algorithmic_bytes_per_step(wl)[0]
             peak, _ = measured_peak_gbs()
-            out[key] = {"workload": workload_description(wl, a), "ms_per_step": ms,
-                        "value": wl.n_bodies * wl.n_corr_iterations / (ms * 1e-3), "unit": UNIT,
+            out[key] = {"workload": workload_description(wl, a), "n_gpus": world, "ms_per_step": ms,
+                        "value": world * wl.n_bodies * wl.n_corr_iterations / (ms * 1e-3), "unit": UNIT,
                         "launches_per_step": (ctx.launch_count - l0) // 10,
                         "roofline_frac": total_b / (ms * 1e-3) / 1e9 / peak}
             ctx.close()
         except Exception as e:  # a secondary line must never take the headline down
             out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            if world > 1:
+                raise  # ... except that ranks must not diverge inside collectives
     return out
 
 
@@ -565,6 +577,10 @@ def run_b200(args):
     clocks = sampler.stop()
     clocks["note"] = "sampled every 100 ms from before the timed region to the end of a 1.5 s repeat of the timed step"
 
+    secondary = None
+    if args.workload == "c4" and not args.bodies and not args.no_secondary:
+        secondary = secondary_measurements(args, torch, dist, dev, stream, flush, rank, world)  # every rank takes part
+
     if rank == 0:
         total_b, region_b, depth_b, line_evals, point_evals = pkg.roofline.algorithmic_bytes_per_step(wl)
         peak, peak_src = measured_peak_gbs()
@@ -603,8 +619,8 @@ def run_b200(args):
             out["e2e"] = e2e
         if not args.no_parity_check:
             out["parity_check"] = parity_check(ctx, wl)
-        if world == 1 and args.workload == "c4" and not args.bodies and not args.no_secondary:
-            out["secondary"] = secondary_measurements(args, torch, dev, stream, flush)
+        if secondary is not None:
+            out["secondary"] = secondary
         if world == 1 and not args.no_cpu_baseline:
             n_cpu_steps = max(3, min(50, int(0.5 / max(1e-4, ms_per_step * 1e-3 * 20))))  # ~0.5 s of sustained CPU work
             r = cpu_reference_run(args, wl, steps=n_cpu_steps, warmup=1)
