@@ -69,7 +69,7 @@ class Link(C.Structure):
     """m3tb_link (m3t::Link, link.h:150-156)."""
     _fields_ = [("body", C.c_int32), ("parent", C.c_int32), ("body2joint", C.c_float * 12),
                 ("joint2parent", C.c_float * 12), ("link2world", C.c_float * 12), ("free_directions", C.c_int32 * 6),
-                ("fixed_body2joint_pose", C.c_int32)]
+                ("fixed_body2joint_pose", C.c_int32), ("n_extra_bodies", C.c_int32), ("extra_bodies", C.c_int32 * 3)]
 
 
 class Constraint(C.Structure):
@@ -414,6 +414,10 @@ class Context:
             K.link2world[:] = np.asarray(l2w, np.float32).reshape(12).tolist()
             K.free_directions[:] = [int(bool(d)) for d in l.free_directions]
             K.fixed_body2joint_pose = int(l.fixed_body2joint_pose)
+            extra = tuple(getattr(l, "extra_bodies", ()) or ())
+            K.n_extra_bodies = len(extra)
+            for k, e in enumerate(extra):
+                K.extra_bodies[k] = int(e) - body_offset
         nc = len(spec.constraints)
         cons = (Constraint * max(nc, 1))()
         for i, c in enumerate(spec.constraints):
@@ -517,11 +521,13 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
     op = OptimizerParams(wl.tikhonov_rotation, wl.tikhonov_translation)
     # the depth camera serves the depth modality and RegionModality::MeasureOcclusions
     need_depth_camera = bool(wl.depth) or bool(wl.region and wl.region.measure_occlusions and wl.depth_frames is not None)
+    cw = getattr(wl, "color_world2camera_per_body", None)
+    dw = getattr(wl, "depth_world2camera_per_body", None)
     for b in range(count):
         if wl.region:
-            ctx.set_color_camera(b, wl.color_intrinsics, wl.color_world2camera)
+            ctx.set_color_camera(b, wl.color_intrinsics, wl.color_world2camera if cw is None else cw[first + b])
         if need_depth_camera:
-            ctx.set_depth_camera(b, wl.depth_intrinsics, wl.depth_world2camera, wl.depth_scale)
+            ctx.set_depth_camera(b, wl.depth_intrinsics, wl.depth_world2camera if dw is None else dw[first + b], wl.depth_scale)
     if upload_frames:
         if wl.region:
             ctx.upload_color_batch(0, wl.color_frames[first:first + count])
@@ -537,7 +543,7 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
     if getattr(wl, "structures", None):  # structures whose bodies all lie inside [first, first+count)
         k = 0
         for sp in wl.structures:
-            ids = [l.body for l in sp.links if l.body >= 0]
+            ids = [l.body for l in sp.links if l.body >= 0] + [e for l in sp.links for e in (getattr(l, "extra_bodies", ()) or ())]
             if ids and (min(ids) < first or max(ids) >= first + count):
                 continue
             ctx.set_structure(k, sp, body_offset=first)

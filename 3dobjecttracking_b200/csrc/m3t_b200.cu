@@ -55,6 +55,7 @@ struct PoolMaps {
 // One m3t::Optimizer with more than a single free root link (host image; flattened into the device tables on demand)
 struct StructureHost {
   std::vector<LinkDev> links;
+  std::vector<LinkDev> default_links;  // Link::default_body2joint_pose_ / default_joint2parent_pose_: as handed to m3tb_set_structure
   std::vector<ConstraintDev> constraints;
   float tikhonov_rotation = 1000.0f, tikhonov_translation = 30000.0f;
   bool set = false;
@@ -672,6 +673,11 @@ int SyncStructures(m3tb_ctx* ctx) {
         if (used[l.body]) return Fail(ctx, M3TB_ERR_INVALID, "body " + std::to_string(l.body) + " is referenced by two links");
         used[l.body] = 1;
       }
+      for (int x = 0; x < l.n_extra; ++x) {
+        if (l.extra[x] < 0 || l.extra[x] >= ctx->n_bodies) return Fail(ctx, M3TB_ERR_NOT_SET_UP, "structure references a body that is not set");
+        if (used[l.extra[x]]) return Fail(ctx, M3TB_ERR_INVALID, "body " + std::to_string(l.extra[x]) + " is referenced twice");
+        used[l.extra[x]] = 1;
+      }
     }
     push(s.links, s.constraints, s.tikhonov_rotation, s.tikhonov_translation);
   }
@@ -708,16 +714,20 @@ int SyncStructures(m3tb_ctx* ctx) {
   CU(cudaMemsetAsync(ctx->d_struct_status, 0, sizeof(int) * ns, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_structures, sts.data(), sizeof(StructureDev) * ns, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(ctx->d_links, links.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
-  if (!ctx->defaults_valid) {  // the first upload after m3tb_set_structure defines the defaults
-    CU(cudaMemcpyAsync(ctx->d_links_default, links.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->h_links_default = links;
-    ctx->defaults_valid = true;
-  } else if (int(ctx->h_links_default.size()) != nl) {  // the body table grew: implicit links were appended
+  {
+    // Defaults are per link and change only through that link's own setters (link.cpp:131-139): the default table is the
+    // concatenation of what each m3tb_set_structure call was given (implicit one-link structures: identity joints), NOT
+    // the current - possibly already tracked - joint poses of the other structures.
     std::vector<LinkDev> d = links;
-    for (size_t k = 0; k < std::min(d.size(), ctx->h_links_default.size()); ++k) d[k] = ctx->h_links_default[k];
+    size_t o = 0;
+    for (const StructureHost& sh : ctx->structures) {
+      for (size_t k = 0; k < sh.default_links.size() && o + k < d.size(); ++k) d[o + k] = sh.default_links[k];
+      o += sh.links.size();
+    }
     CU(cudaMemcpyAsync(ctx->d_links_default, d.data(), sizeof(LinkDev) * nl, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->h_links_default = d;
+    ctx->defaults_valid = true;
   }
   ctx->n_links_total = nl;
   if (!cons.empty())
@@ -768,6 +778,9 @@ int ClusterLinks(m3tb_ctx* ctx) {
     if (d.n_links != nl) return 0;
     for (int l = 0; l < nl; ++l)
       if (ctx->h_link_bodies[d.first_link + l] != si * nl + l) return 0;
+    if (si < int(ctx->structures.size()))
+      for (const auto& lk : ctx->structures[si].links)
+        if (lk.n_extra > 0) return 0;
   }
   for (int b = 0; b < ctx->n_bodies; ++b) {
     const BodyDev& B = ctx->h_bodies[b];
@@ -1585,6 +1598,13 @@ int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int
     std::memcpy(l.body2joint, in.body2joint, sizeof(l.body2joint));
     std::memcpy(l.joint2parent, in.joint2parent, sizeof(l.joint2parent));
     std::memcpy(l.link2world, in.link2world, sizeof(l.link2world));
+    if (in.n_extra_bodies < 0 || in.n_extra_bodies > M3TB_MAX_EXTRA_BODIES || (in.n_extra_bodies > 0 && in.body < 0))
+      return Fail(ctx, M3TB_ERR_INVALID, "a link has 0..3 extra bodies, and only next to a primary body");
+    l.n_extra = in.n_extra_bodies;
+    for (int x = 0; x < l.n_extra; ++x) {
+      if (in.extra_bodies[x] < 0 || in.extra_bodies[x] >= ctx->max_bodies) return Fail(ctx, M3TB_ERR_INVALID, "extra body index out of range");
+      l.extra[x] = in.extra_bodies[x];
+    }
     h.links.push_back(l);
   }
   for (int c = 0; c < n_constraints; ++c) {
@@ -1621,6 +1641,7 @@ int m3tb_set_structure(m3tb_ctx* ctx, int structure, const m3tb_link* links, int
   h.set = true;
   int rc = PullLinks(ctx);
   if (rc) return rc;
+  h.default_links = h.links;
   if (structure == int(ctx->structures.size())) ctx->structures.push_back(h);
   else ctx->structures[structure] = h;
   ctx->structures_dirty = true;

@@ -35,6 +35,7 @@ struct LinkDev {
   int level;                 // depth in the tree (root 0)
   float body2joint[12], joint2parent[12];
   float link2world[12];      // links without a body
+  int n_extra, extra[3];     // further modality sets (bodies) of the same physical body: summed into the link, poses written back
 };
 
 struct ConstraintDev {
@@ -617,6 +618,10 @@ __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs a
       }
       v = args.gh_link ? args.gh_link[27 * body + src]
                        : 0.0f + args.gh_region[27 * body + src] + args.gh_depth[27 * body + src];
+      for (int x = 0; x < links[l].n_extra; ++x) {  // Link::CalculateGradientAndHessian over all modalities (link.cpp:184-193)
+        const int eb = links[l].extra[x];
+        v += args.gh_link ? args.gh_link[27 * eb + src] : 0.0f + args.gh_region[27 * eb + src] + args.gh_depth[27 * eb + src];
+      }
     }
     if (k < 6) s.g[6 * l + k] = v; else s.H[36 * l + k - 6] = v;
   }
@@ -634,7 +639,10 @@ __global__ void __launch_bounds__(kStructThreads) k_structure(const StructArgs a
   for (int e = tid; e < nl * 12; e += T) {
     const int l = e / 12, k = e - 12 * l;
     const int body = links[l].body;
-    if (body >= 0) args.poses[12 * body + k] = s.l2w[e];
+    if (body >= 0) {
+      args.poses[12 * body + k] = s.l2w[e];
+      for (int x = 0; x < links[l].n_extra; ++x) args.poses[12 * links[l].extra[x] + k] = s.l2w[e];
+    }
   }
 }
 

@@ -248,6 +248,8 @@ class Workload:
     seed: int = 0
     notes: dict = field(default_factory=dict)
     structures: list | None = None          # [StructureSpec] (kinematic structures, config 5); None = rigid bodies
+    color_world2camera_per_body: np.ndarray | None = None   # [nb,3,4]: multi-camera rigs (default: one pose for all)
+    depth_world2camera_per_body: np.ndarray | None = None
     renderings: dict | None = None          # {body: {"region_depth" | "region_silhouette" | "depth_depth" | "depth_silhouette": Rendering}}
 
     @property
@@ -270,6 +272,7 @@ class LinkSpec:
     free_directions: tuple = (1, 1, 1, 1, 1, 1)
     fixed_body2joint_pose: bool = True
     link2world: np.ndarray = None           # [3,4], links without a body only
+    extra_bodies: tuple = ()                # further modality sets (bodies) of the same physical body (link.h:151)
 
 
 @dataclass
@@ -526,6 +529,39 @@ def make_chain_workload(n_chains=2, n_links=8, n_lines=300, n_points=300, varian
                     gt_body2world=gt, start_body2world=start, seed=seed,
                     notes=dict(n_divides=n_divides, variant=variant, n_links=n_links, n_chains=n_chains, soft=soft,
                                first_body=first_chain * n_links), structures=structures)
+
+
+def make_multi_camera_workload(n_objects=3, n_lines=200, n_points=200, n_divides=3, seed=0, rot_deg=3.0, trans_m=0.005):
+    """n_objects rigid bodies, each observed by TWO colour + depth camera pairs (a stereo-like rig: the second pair is
+    the first one moved by 12 cm / 8 degrees). Object i is body i (camera pair A) and body n_objects + i (camera pair
+    B) - two modality sets of one physical body, i.e. one m3t::Link with four modalities; structure i is the one-link
+    Optimizer that sums them (Link::CalculateGradientAndHessian, link.cpp:184-193)."""
+    wl = make_workload("c2", n_bodies=n_objects, n_lines=n_lines, n_points=n_points, n_divides=n_divides, seed=seed,
+                       rot_deg=rot_deg, trans_m=trans_m)
+    n = n_objects
+    ci, di = wl.color_intrinsics, wl.depth_intrinsics
+    rig = np.zeros((3, 4), np.float32)
+    rig[:, :3] = _rot((0.1, 1.0, 0.05), 8.0)
+    rig[:, 3] = (-0.12, 0.01, 0.015)
+    c2 = pose_mul(rig, wl.color_world2camera)
+    d2 = pose_mul(rig, wl.depth_world2camera)
+    color = np.concatenate([wl.color_frames, np.zeros_like(wl.color_frames)])
+    depth = np.concatenate([wl.depth_frames, np.zeros_like(wl.depth_frames)])
+    for i in range(n):
+        render_color(ci, pose_mul(c2, wl.gt_body2world[i]), seed * 1000003 + 700000 + i, out=color[n + i])
+        render_depth(di, pose_mul(d2, wl.gt_body2world[i]), seed * 1000003 + 700000 + i, depth_scale=wl.depth_scale, out=depth[n + i])
+    wl.n_bodies = 2 * n
+    wl.color_frames, wl.depth_frames = color, depth
+    wl.gt_body2world = np.concatenate([wl.gt_body2world, wl.gt_body2world])
+    wl.start_body2world = np.concatenate([wl.start_body2world, wl.start_body2world])
+    wl.color_world2camera_per_body = np.stack([wl.color_world2camera] * n + [c2] * n)
+    wl.depth_world2camera_per_body = np.stack([wl.depth_world2camera] * n + [d2] * n)
+    wl.structures = [StructureSpec(links=[LinkSpec(body=i, parent=-1, body2joint=identity_pose(), joint2parent=identity_pose(),
+                                                   extra_bodies=(n + i,))],
+                                   tikhonov_rotation=wl.tikhonov_rotation, tikhonov_translation=wl.tikhonov_translation)
+                     for i in range(n)]
+    wl.name = "multi_camera"
+    return wl
 
 
 def make_workload(name="c2", n_bodies=None, n_lines=None, n_points=None, n_divides=4, seed=0, rot_deg=3.0,

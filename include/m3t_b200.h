@@ -132,7 +132,14 @@ typedef struct m3tb_link {
   float link2world[12];          /* Link::link2world_pose_ of a link without body (ignored when body >= 0) */
   int32_t free_directions[6];    /* Link::free_directions(): rot x,y,z, trans x,y,z */
   int32_t fixed_body2joint_pose; /* Link::fixed_body2joint_pose(), default 1 */
+  /* Further modality sets of the SAME physical body (Link::modality_ptrs() holds an arbitrary list, link.h:151;
+   * Link::CalculateGradientAndHessian sums it, link.cpp:184-193): e.g. a second colour + depth camera pair looking at the
+   * body. Each set is an m3tb body of its own (own cameras, models, parameters, histograms); their gradients / Hessians
+   * are added to the link's in list order and every pose update is written to all of them. */
+  int32_t n_extra_bodies;        /* 0 .. M3TB_MAX_EXTRA_BODIES */
+  int32_t extra_bodies[3];
 } m3tb_link;
+#define M3TB_MAX_EXTRA_BODIES 3
 
 /* m3t::Constraint (M3T/include/m3t/constraint.h:109-112) or, with soft != 0, m3t::SoftConstraint
  * (M3T/include/m3t/soft_constraint.h:128-136). link1 / link2 index the structure's link list. */

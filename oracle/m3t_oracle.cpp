@@ -1817,26 +1817,31 @@ void orc_tracking_step_structures(orc_body* bodies, orc_structure* structures, i
         const int bi = s->links[l].body;
         float* dst = bi >= 0 ? bodies[bi].body2world : bodyless_link2world + (size_t(si) * max_links + l) * 12;
         std::memcpy(dst, &l2w[12 * l], 12 * sizeof(float));
+        for (int x = 0; x < s->links[l].n_extra_bodies; ++x)  // one physical body, several modality sets
+          std::memcpy(bodies[s->links[l].extra_bodies[x]].body2world, &l2w[12 * l], 12 * sizeof(float));
       }
     };
+    // the modality sets of link l: its body, then the extra bodies (Link::modality_ptrs() order)
+    auto n_sets = [&](int l) { return s->links[l].body < 0 ? 0 : 1 + s->links[l].n_extra_bodies; };
+    auto set_body = [&](int l, int k) { return k == 0 ? s->links[l].body : s->links[l].extra_bodies[k - 1]; };
     for (int corr = corr_begin; corr < corr_end; ++corr) {
-      for (int l = 0; l < nl; ++l) {
-        if (s->links[l].body < 0) continue;
-        orc_body* b = &bodies[s->links[l].body];
-        if (b->region)
-          b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, b->region_occlusion_frame,
-                                                  b->histogram_f, b->histogram_b, b->body2world, iteration,
-                                                  b->first_iteration, corr, rotation_mode, b->lines, &b->region_view);
-        if (b->depth)
-          b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
-                                                  b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);
-      }
+      for (int l = 0; l < nl; ++l)
+        for (int k = 0; k < n_sets(l); ++k) {
+          orc_body* b = &bodies[set_body(l, k)];
+          if (b->region)
+            b->n_lines = orc_region_correspondences(b->region, b->region_model, b->color, b->region_occlusion_frame,
+                                                    b->histogram_f, b->histogram_b, b->body2world, iteration,
+                                                    b->first_iteration, corr, rotation_mode, b->lines, &b->region_view);
+          if (b->depth)
+            b->n_points = orc_depth_correspondences(b->depth, b->depth_model, b->depth_frame, b->body2world, iteration,
+                                                    b->first_iteration, corr, rotation_mode, b->points, &b->depth_view);
+        }
       for (int upd = 0; upd < n_update; ++upd) {
         std::fill(g.begin(), g.end(), 0.0f);
         std::fill(H.begin(), H.end(), 0.0f);
-        for (int l = 0; l < nl; ++l) {
-          if (s->links[l].body < 0) continue;
-          orc_body* b = &bodies[s->links[l].body];
+        for (int l = 0; l < nl; ++l)
+          for (int k = 0; k < n_sets(l); ++k) {
+          orc_body* b = &bodies[set_body(l, k)];
           float gm[6], Hm[36];
           if (b->region) {
             orc_region_gradient_hessian(b->region, b->color, b->body2world, b->lines, b->n_lines, corr, upd,

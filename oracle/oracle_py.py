@@ -127,7 +127,7 @@ class Body(C.Structure):
 class Link(C.Structure):
     _fields_ = [("body", C.c_int32), ("parent", C.c_int32), ("body2joint", C.c_float * 12),
                 ("joint2parent", C.c_float * 12), ("free_directions", C.c_int32 * 6),
-                ("fixed_body2joint_pose", C.c_int32)]
+                ("fixed_body2joint_pose", C.c_int32), ("n_extra_bodies", C.c_int32), ("extra_bodies", C.c_int32 * 3)]
 
 
 class Constraint(C.Structure):
@@ -314,6 +314,10 @@ class OracleStructure:
             L_.joint2parent[:] = f32(l.joint2parent).reshape(12).tolist()
             L_.free_directions[:] = [int(bool(d)) for d in l.free_directions]
             L_.fixed_body2joint_pose = int(l.fixed_body2joint_pose)
+            extra = tuple(getattr(l, "extra_bodies", ()) or ())
+            L_.n_extra_bodies = len(extra)
+            for k, e in enumerate(extra):
+                L_.extra_bodies[k] = int(e)
         for arr, items in ((self.constraints, hard), (self.soft, soft)):
             for i, c in enumerate(items):
                 K = arr[i]
@@ -394,7 +398,8 @@ class OracleTracker:
             if wl.region:
                 cf = self.color_frames[b]
                 cf.intrinsics = _intr(wl.color_intrinsics)
-                cf.world2camera[:] = f32(wl.color_world2camera).reshape(12).tolist()
+                cf.world2camera[:] = f32(wl.color_world2camera if getattr(wl, "color_world2camera_per_body", None) is None
+                                         else wl.color_world2camera_per_body[b]).reshape(12).tolist()
                 cf.bgr = wl.color_frames[b].ctypes.data
                 cf.pitch = wl.color_frames[b].strides[0]
                 for key, field in (("region_depth", "depth_rendering"), ("region_silhouette", "silhouette_rendering")):
@@ -418,7 +423,8 @@ class OracleTracker:
             if wl.depth:
                 df = self.depth_frames[b]
                 df.intrinsics = _intr(wl.depth_intrinsics)
-                df.world2camera[:] = f32(wl.depth_world2camera).reshape(12).tolist()
+                df.world2camera[:] = f32(wl.depth_world2camera if getattr(wl, "depth_world2camera_per_body", None) is None
+                                         else wl.depth_world2camera_per_body[b]).reshape(12).tolist()
                 df.depth = wl.depth_frames[b].ctypes.data
                 df.pitch = wl.depth_frames[b].strides[0]
                 df.depth_scale = wl.depth_scale

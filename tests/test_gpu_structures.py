@@ -276,3 +276,20 @@ def test_cluster_fused_path_matches_multi_launch_path(capi, synth, variant, monk
     assert np.median(dt) < 5e-4 and np.median(dr) < 1e-2, (dt, dr)
     ctx_a.close()
     ctx_b.close()
+
+
+def test_reset_joint_poses_keeps_other_structures_defaults(capi, synth):
+    """Link::ResetJointPoses restores each link's OWN defaults (link.cpp:243-246): re-declaring structure 1 after
+    tracking must not turn structure 0's tracked joint poses into its defaults."""
+    wl = synth.make_chain_workload(n_chains=2, n_links=4, n_lines=100, n_points=100, n_divides=2, seed=3)
+    ctx = capi.context_from_workload(wl)
+    ctx.start_modalities(0)
+    _, j2p_default, _ = ctx.get_link_poses(0, 4)
+    ctx.tracking_step(0, 2, 2)
+    _, j2p_tracked, _ = ctx.get_link_poses(0, 4)
+    assert np.abs(j2p_tracked - j2p_default).max() > 1e-6          # the joints moved
+    ctx.set_structure(1, wl.structures[1])                          # touch the OTHER structure
+    ctx.reset_joint_poses()
+    _, j2p_reset, _ = ctx.get_link_poses(0, 4)
+    assert np.array_equal(j2p_reset.view(np.uint32), j2p_default.view(np.uint32))
+    ctx.close()

@@ -303,3 +303,32 @@ def test_chain_tracking_converges(oracle):
                 assert np.linalg.norm(rel[:3, 3] - (0.01, 0, 0)) < 2e-4
                 rv = Rotation.from_matrix(rel[:3, :3]).as_rotvec()
                 assert abs(rv[1]) < 2e-3 and abs(rv[2]) < 2e-3
+
+
+def test_link_with_two_modality_sets_sums_them(oracle, synth):
+    """Link::CalculateGradientAndHessian adds up all modalities of a link (link.cpp:184-193): a one-link structure whose
+    link carries a second body (the same physical body seen by a second camera pair) must take exactly the step of a
+    rigid-body optimisation fed with the sum of the four modalities' gradients / Hessians, and both bodies end up with
+    the same pose."""
+    n = 2
+    wl = synth.make_multi_camera_workload(n_objects=n, n_divides=3, seed=8)
+    trk = oracle.OracleTracker(wl, rotation_mode=oracle.ROTATION_LINEAR, exp_mode=oracle.EXP_RODRIGUES)
+    ref = oracle.OracleTracker(wl, rotation_mode=oracle.ROTATION_LINEAR, exp_mode=oracle.EXP_RODRIGUES)
+    trk.start_modalities(0)
+    ref.start_modalities(0)
+    trk.tracking_step(0, n_corr=1, n_update=1)
+    for i in range(n):
+        g = np.zeros(6, np.float32)
+        H = np.zeros((6, 6), np.float32)
+        for b in (i, n + i):                      # modality list order: set A (region, depth), set B (region, depth)
+            ref.region_correspondences(b, 0, 0)
+            gr, Hr = ref.region_gradient_hessian(b, 0, 0)
+            g, H = g + gr, H + Hr
+            ref.depth_correspondences(b, 0, 0)
+            gd, Hd = ref.depth_gradient_hessian(b, 0)
+            g, H = g + gd, H + Hd
+        ok, _ = ref.optimize(i, g, H)
+        assert ok
+    got, want = trk.get_poses(), ref.get_poses()
+    assert np.array_equal(got[:n].view(np.uint32), got[n:].view(np.uint32))
+    assert np.abs(got[:n] - want[:n]).max() < 2e-6
