@@ -609,7 +609,7 @@ def run_b200(args):
             "config": config_dict(wl, args, world, nb),
             "line_evals_per_s": world * line_evals / kernel_s,
             "depth_point_evals_per_s": world * point_evals / kernel_s,
-            "roofline": {"bound": "hbm", "kernel": "k_track", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_track2<1024, true> (one fused launch per step; k_track serves what k_track2 does not take)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": total_b, "region_bytes": region_b, "depth_bytes": depth_b,
                          "launch_ms": ms_per_step},

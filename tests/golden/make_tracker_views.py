@@ -17,19 +17,24 @@ import oracle_py as oracle   # noqa: E402
 from replay import ReferenceReplay  # noqa: E402
 
 
+NEAR = 2e-4
+
+
 def main():
     base = np.load(os.path.join(HERE, "triangle_test_view.npz"))
     views = {"region": {int(base["region_view"]): (base["region_points"], float(base["region_scalar"]))},
              "depth": {int(base["depth_view"]): (base["depth_points"], float(base["depth_scalar"]))}}
     pts = rr.geodesic_points()
-    for scenario in ("tracker", "refiner"):
+    # the reference's arithmetic first, then the mirror arithmetic of the CUDA path with the near-tie neighbours of every
+    # view on its way (NEAR: dot-product margin; neighbouring views are about 6e-3 apart at their closest)
+    for scenario, mirror, near in (("tracker", False, 0.0), ("refiner", False, 0.0), ("tracker", True, NEAR), ("refiner", True, NEAR)):
         while True:
             rep = ReferenceReplay(oracle, views)
-            missing = rep.run(scenario)
+            missing = rep.run(scenario, mirror, near)
             if not missing:
                 break
             for kind, v in missing:
-                print(f"{scenario}: generating {kind} view {v}", flush=True)
+                print(f"{scenario} mirror={mirror}: generating {kind} view {v}", flush=True)
                 c2b = rr.camera2body_from_point(pts[v])
                 p, s = (rr.region_view_points if kind == "region" else rr.depth_view_points)(c2b)
                 views[kind][v] = (p, float(s))

@@ -19,6 +19,7 @@ class ReferenceReplay:
         ori = np.ascontiguousarray((-rr.geodesic_points()).astype(np.float32))
         nv = ori.shape[0]
         self.available = {k: set(v) for k, v in views.items()}
+        self.near = 0.0
         self.keep = []
 
         def model(kind, fl):
@@ -68,21 +69,32 @@ class ReferenceReplay:
         return m
 
     def _closest(self):
-        """The two views GetClosestView would select for the current pose."""
+        """The views GetClosestView would select for the current pose, plus every view whose orientation dot product
+        is within self.near of the winner's (a free-running replay on another arithmetic may take the runner-up)."""
         b2w = np.eye(4); b2w[:3] = self.pose()[:3]
         out = []
+        ori = -self.rr.geodesic_points()
         for kind, w2c in (("region", self.rig["color_w2c"]), ("depth", self.rig["depth_w2c"])):
-            v, _, _, _ = self.rr.closest_view_pose(w2c @ b2w)
-            out.append((kind, v))
+            b2c = w2c @ b2w
+            t = b2c[:3, 3]
+            dots = ori @ (b2c[:3, :3].T @ (t / np.linalg.norm(t)))
+            best = int(np.argmax(dots))
+            out.append((kind, best))
+            for v in np.nonzero(dots >= dots[best] - self.near)[0]:
+                if int(v) != best:
+                    out.append((kind, int(v)))
         return out
 
     def _missing(self):
         return [(k, v) for k, v in self._closest() if v not in self.available[k]]
 
-    def run(self, scenario):
-        """Returns the list of (kind, view) that were needed but not available (empty: the replay is complete)."""
+    def run(self, scenario, mirror=False, near=0.0):
+        """Returns the list of (kind, view) that were needed but not available (empty: the replay is complete).
+        mirror: the oracle's LINEAR / RODRIGUES arithmetic (what the CUDA path computes) instead of the reference's
+        POLAR / PADE; near: also ask for the views within this dot-product margin of each selected view."""
         L, o = self.L, self.oracle
-        mode, exp = o.ROTATION_POLAR, o.EXP_PADE
+        self.near = near
+        mode, exp = (o.ROTATION_LINEAR, o.EXP_RODRIGUES) if mirror else (o.ROTATION_POLAR, o.EXP_PADE)
         if scenario == "tracker":   # StartModalities(0); ExecuteTrackingStep(0): 7 x 2 (tracker_test.cpp:164-179)
             miss = self._missing()
             if miss:
