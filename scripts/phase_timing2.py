@@ -20,7 +20,7 @@ nc, nu = wl.n_corr_iterations, wl.n_update_iterations
 tot, first, last = [], [], []
 for b in range(wl.n_bodies):
     c = ctx.phase_clocks(b, 256)
-    a = c[:128][c[:128] > 0]
+    a = c[:112][c[:112] > 0]
     tot.append(int(a[-1] - a[0])); first.append(int(a[0])); last.append(int(a[-1]))
 tot = np.array(tot)
 w2c = np.asarray(wl.color_world2camera, np.float64)
@@ -33,9 +33,13 @@ slow = int(order[-1])
 both = bool(wl.region and wl.depth)
 for body in (0, slow):
     c = ctx.phase_clocks(body, 256)
-    a = c[:128][c[:128] > 0]
+    a = c[:112][c[:112] > 0]
     d = np.diff(a)
     print(f"{name} body {body}: warp 0 total {a[-1]-a[0]} cycles; prologue {d[0]}")
+    det = {k: int(c[k] - a[0]) for k in (120, 121, 122, 124, 125, 126, 118, 119) if c[k] > 0}
+    print("   prologue detail (cycles after the first stamp): parameters in shared memory %s, staging + mbarriers %s, pose products %s; "
+          "tile thread: start %s, tiles sized %s, TMA issued %s; first iteration: before the LUT / tile waits %s, after %s"
+          % tuple(det.get(k, "-") for k in (120, 121, 122, 124, 125, 126, 118, 119)))
     per_corr = 2 * (1 if both else (int(bool(wl.region)) + int(bool(wl.depth)))) + 5 * nu
     rows = d[1:1 + nc * per_corr].reshape(nc, per_corr)
     labels = (["view", "lines"] if wl.region else []) + (["view_d", "points"] if (wl.depth and not both) else [])
