@@ -116,6 +116,8 @@ def lib():
         return _lib
     if os.environ.get("M3TB_LIB"):  # A/B experiments: another build of the same library
         LIB_PATH = os.environ["M3TB_LIB"]
+        if not os.path.exists(LIB_PATH):
+            raise M3TBError(f"M3TB_LIB names a library that does not exist: {LIB_PATH}")
     if not os.path.exists(LIB_PATH):
         _build.build_cuda()
     elif _build._stale(LIB_PATH, _build.cuda_sources()):

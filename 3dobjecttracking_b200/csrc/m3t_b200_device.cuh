@@ -23,6 +23,14 @@ constexpr int kTileWidths = 7;    // tile widths 64, 96, .. 256 pixels (tensor-m
 constexpr int kTileBoxRows = 16;  // rows per TMA box
 __host__ __device__ constexpr int TileWidth(int i) { return 64 + 32 * i; }
 constexpr int kPhaseSlots = 256;
+
+// Where bin `idx` of the colour histograms lives in the posterior lookup table (float2 per bin). A table entry is 8
+// bytes, so its shared-memory bank pair is the slot's low four bits - in index order the RED bin alone, and the 32 lanes
+// of a warp, looking at two colour blobs a few bins wide, land on three or four bank pairs (measured: 7.9 wavefronts
+// per LDS.64 of the table, 4.9 M of the kernel's 10.7 M shared-memory wavefronts). XOR-ing the green and blue bins into
+// the low bits spreads neighbouring colours over the banks. A bijection on [0, n_bins^3) for 16 and 32 bins (bits >= 4
+// are untouched); every writer and reader of the table goes through it, and the bin-index images store slots.
+__host__ __device__ __forceinline__ unsigned LutSlot(unsigned idx) { return idx ^ ((idx >> 4) & 15u) ^ ((idx >> 8) & 15u); }
 constexpr int kBlockThreads = 256;
 constexpr int kWarps = kBlockThreads / 32;
 

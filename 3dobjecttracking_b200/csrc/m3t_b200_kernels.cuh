@@ -237,7 +237,7 @@ __device__ __forceinline__ int PixelBin(const Tile& t, const uint16_t* tile, con
   if (tx < unsigned(t.w) && ty < unsigned(t.h)) return tile[ty * unsigned(t.pitch) + tx];
   const uint8_t* px = FramePtr(f, x, y, 3u);
   // ColorHistograms::GetProbabilities index (color_histograms.cpp:97-99), BGR memory order
-  return (int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs);
+  return int(LutSlot(unsigned((int(__ldg(px)) >> bs) * nb * nb + (int(__ldg(px + 1)) >> bs) * nb + (int(__ldg(px + 2)) >> bs))));
 }
 
 __device__ __forceinline__ unsigned DepthAt(const Tile& t, const uint16_t* tile, const FrameView& f, int x, int y) {
@@ -1234,7 +1234,7 @@ __global__ void __launch_bounds__(T, 512 / T) k_track(const __grid_constant__ Tr
     const int bs = body.rp.bitshift, nb = body.rp.n_bins;
     uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
     auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
-      return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
+      return LutSlot(((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs));
     };
     for (int g0 = tid; g0 < n_groups; g0 += 4 * T) {  // 12 independent word loads in flight per thread
       unsigned w[4][3];
@@ -1619,7 +1619,7 @@ __device__ __forceinline__ float2 NormaliseBin(float pf, float pb) {
 __global__ void k_lut(const float* hist_f, const float* hist_b, float2* lut, int n, size_t stride, int first_body) {
   const int body = first_body + blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) lut[size_t(body) * stride + i] = NormaliseBin(hist_f[size_t(body) * stride + i], hist_b[size_t(body) * stride + i]);
+  if (i < n) lut[size_t(body) * stride + LutSlot(unsigned(i))] = NormaliseBin(hist_f[size_t(body) * stride + i], hist_b[size_t(body) * stride + i]);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1706,8 +1706,8 @@ __device__ __forceinline__ void IngestRect(const CameraDev& cam, const Tile& t, 
   if (threadIdx.x == 0) atomicAdd(bytes, static_cast<unsigned long long>(row_bytes) * t.h);
 }
 
-__device__ __forceinline__ unsigned BinOf(unsigned b, unsigned g, unsigned r, int bs, unsigned nb) {
-  return ((b >> bs) * nb + (g >> bs)) * nb + (r >> bs);  // color_histograms.cpp:97-99, BGR memory order
+__device__ __forceinline__ unsigned BinOf(unsigned b, unsigned g, unsigned r, int bs, unsigned nb) {  // -> lookup-table slot
+  return LutSlot(((b >> bs) * nb + (g >> bs)) * nb + (r >> bs));  // color_histograms.cpp:97-99, BGR memory order
 }
 // 16 pixels = 48 bytes (three 16-byte words) -> 16 bin indices (two 16-byte words)
 __device__ __forceinline__ void Bins16(const uint4 (&w)[3], int bs, unsigned nb, uint4& lo, uint4& hi) {
@@ -2111,7 +2111,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     }
     hist_f[k] = hf;
     hist_b[k] = hb;
-    lut[k] = NormaliseBin(hf, hb);
+    lut[LutSlot(unsigned(k))] = NormaliseBin(hf, hb);
   }
 }
 

@@ -64,6 +64,12 @@ struct LineRegs {  // RegionModality::DataLine without the distribution (shared 
     if (stamp_ptr && lane == 0 && stamp_i < kPhaseSlots / 2) stamp_ptr[(base) + stamp_i++] = clock64();     \
   } while (0)
 
+// prologue detail (profiling aid): fixed slots past the ones M3TB_STAMP2 fills
+#define M3TB_STAMP_AT(slot, cond)                                                                  \
+  do {                                                                                             \
+    if (args.phase_clock && (cond)) args.phase_clock[size_t(body_id) * kPhaseSlots + (slot)] = clock64(); \
+  } while (0)
+
 // ---------------------------------------------------------------------------------------------
 // One correspondence line, streaming form. Walks the 19 segments of the line in pixel order; after segment w >= 7 the
 // distribution entry that has just become computable is finished from the 8-segment window:
@@ -158,7 +164,7 @@ __device__ __noinline__ void WalkSlow(int scale, int bs, int nb, bool horizontal
         idx = __ldg(reinterpret_cast<const uint16_t*>(reinterpret_cast<const uint8_t*>(bins.px) + size_t(unsigned(y)) * bins.pitch) + x);
       } else {
         const uint8_t* p = FramePtr(frame, x, y, 3u);
-        idx = (int(__ldg(p)) >> bs) * nb * nb + (int(__ldg(p + 1)) >> bs) * nb + (int(__ldg(p + 2)) >> bs);
+        idx = int(LutSlot(unsigned((int(__ldg(p)) >> bs) * nb * nb + (int(__ldg(p + 1)) >> bs) * nb + (int(__ldg(p + 2)) >> bs))));
       }
       const float2 l = LutFetch<LUT_SMEM>(lut_g, lut_s, idx);
       pf *= l.x;
@@ -554,6 +560,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     }
   }
   __syncthreads();
+  M3TB_STAMP_AT(120, tid == T - 32);
   const BodyDev& body = s_body;
   const bool has_region = body.has_region, has_depth = body.has_depth;
   const int item = tid & (kGroup - 1);
@@ -615,11 +622,13 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     MbarInit(&sh.ctile_bar, 1);
   }
   __syncthreads();
+  M3TB_STAMP_AT(121, tid == T - 32);
   if (warp == kW - 1) {
     float pose[12];
 #pragma unroll
     for (int i = 0; i < 12; ++i) pose[i] = sh.pose[i];
     PublishPoseProducts(pose, ccam != nullptr, dcam != nullptr, false, sh);
+    M3TB_STAMP_AT(122, lane == 0);
   }
   if (need_lut && tid == 0) {
     const unsigned bytes = unsigned(body.rp.n_bins * body.rp.n_bins * body.rp.n_bins) * sizeof(float2);
@@ -632,6 +641,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
     // colour tile comes from the camera's BIN-INDEX image (u16 per pixel, written once per frame by k_bin / k_ingest),
     // the depth tile from the raw U16 frame; boxes of kTileBoxRows rows x the tile width, stacked -> row-major tile.
     if (tid == 32 % T) {
+      M3TB_STAMP_AT(124, true);
       Tile ct, dt;
       ct.x0 = ct.y0 = ct.w = ct.h = ct.pitch = 0; ct.offset = lut_bytes + kFixedDynBytes;
       dt = ct;
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       }
       sh.ctile = ct;
       sh.dtile = dt;
+      M3TB_STAMP_AT(125, true);
       if (ct.w > 0) {
         const CUtensorMap* map = (args.tma_mode == 2 ? args.tmaps_global : args.bin_maps) + ((ct.w - 64) >> 5);
         MbarExpectTx(&sh.ctile_bar, unsigned(ct.w * ct.h * 2));
@@ -676,6 +687,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
         for (int r = 0; r < dt.h; r += kTileBoxRows)
           TensorCopyG2S(dyn + dt.offset + size_t(r) * dt.w * 2, map, dt.x0, dt.y0 + r, body.depth_camera, &sh.depth_bar);
       }
+      M3TB_STAMP_AT(126, true);
     }
   } else {  // legacy staging (tma_mode 0): depth rows by 1-D bulk copies, colour bins converted from the BGR frame
     if (tid == 32 % T) {
@@ -736,7 +748,7 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
       const int bs = body.rp.bitshift, nb = body.rp.n_bins;
       uint2* out = reinterpret_cast<uint2*>(dyn + ctile.offset);
       auto bin = [&](unsigned b, unsigned gch, unsigned rch) {
-        return ((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs);
+        return LutSlot(((b >> bs) * unsigned(nb) + (gch >> bs)) * unsigned(nb) + (rch >> bs));
       };
       for (int g0 = tid; g0 < n_groups; g0 += 4 * T) {
         unsigned w[4][3];
@@ -811,8 +823,9 @@ __global__ void __launch_bounds__(T, 1) k_track2(const __grid_constant__ TrackAr
                               body.rp.use_adaptive_coverage ? __ldg(rmodel->view_scalars + view_r) : 0.0f,
                               rmodel->max_view_scalar, rmodel->n_points);
       n_lines = min(n_lines, min(lcap, kGroup));
+      M3TB_STAMP_AT(118, tid == T - 32 && !ctile_ready);
       if (!lut_ready) { MbarWait(&sh.lut_bar, 0); lut_ready = true; }
-      if (!ctile_ready) { MbarWait(&sh.ctile_bar, 0); ctile_ready = true; }
+      if (!ctile_ready) { MbarWait(&sh.ctile_bar, 0); ctile_ready = true; M3TB_STAMP_AT(119, tid == T - 32); }
       L.valid = false;
       if (item < n_lines) {
         RegionLine2<LUT_SMEM>(rit, body.rp, p0, p1, cframe, ctile, ctile_px, bin_image, lut_g, lut_s, lf, lb, dist_col, L);
