@@ -103,15 +103,22 @@ struct m3tb_ctx {
   float *d_gh_region = nullptr, *d_gh_depth = nullptr;
   size_t max_dyn_smem = 0;
   RoiRecord* d_roi = nullptr;             // [max_bodies][2]
-  unsigned long long* d_ingest_bytes = nullptr;
+  unsigned long long* d_ingest_bytes = nullptr;  // [2]: one counter per ingest launch in flight
+  int ingest_bytes_slot = 0;              // the counter of the last ingest launch
+  int sm_count = 148;
   bool ingest_pending = false;            // a pinned frame was handed over since the last k_ingest launch
   // frame prefetch (m3tb_prefetch_frames): second set of image pools / camera tables / ROI records, side stream
   ImagePool color_pool_alt, depth_pool_alt;
   CameraDev *d_ccams_alt = nullptr, *d_dcams_alt = nullptr;
   RoiRecord* d_roi_alt = nullptr;
-  float* d_poses_snap = nullptr;          // poses at the start of the last tracking launch (what the prefetch projects with)
+  float* d_poses_snap[2] = {nullptr, nullptr};  // poses at the start of the last two tracking launches; [snap_parity] is
+  int snap_parity = 0;                    //   what the next prefetch projects with, the other one may still be read by the ingest in flight
   cudaStream_t ingest_stream = nullptr;
-  cudaEvent_t ev_ingest_done = nullptr, ev_poses_snap = nullptr;
+  cudaStream_t table_stream = nullptr;    // camera tables + counter reset of a prefetch: beside the ingest in flight, not behind it
+  CameraDev* h_cam_stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // pinned staging [parity][colour | depth]
+  int stage_parity = 0;
+  cudaEvent_t ev_ingest_done = nullptr, ev_poses_snap = nullptr, ev_tables = nullptr;
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};  // the table copies out of h_cam_stage[parity] have run
   bool prefetch_enabled = false;          // set by the first m3tb_prefetch_frames
   bool prefetched = false;                // the next consumer launch has to wait for ev_ingest_done
   bool poses_snap_valid = false;
@@ -308,8 +315,10 @@ int LaunchIngestIfPending(m3tb_ctx* ctx) {
   a.region_models = ctx->d_rmodels;
   a.depth_models = ctx->d_dmodels;
   a.roi = ctx->d_roi;
-  a.bytes = ctx->d_ingest_bytes;
-  CU(cudaMemsetAsync(ctx->d_ingest_bytes, 0, sizeof(unsigned long long), ctx->stream));
+  ctx->ingest_bytes_slot ^= 1;
+  a.bytes = ctx->d_ingest_bytes + ctx->ingest_bytes_slot;
+  a.n_bodies = ctx->n_bodies;
+  CU(cudaMemsetAsync(a.bytes, 0, sizeof(unsigned long long), ctx->stream));
   k_ingest<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
@@ -452,15 +461,20 @@ int LaunchTrack(m3tb_ctx* ctx, int iteration, int corr_begin, int corr_end, int 
   if (rc) return rc;
   rc = SyncTables(ctx);
   if (rc) return rc;
-  rc = LaunchIngestIfPending(ctx);
-  if (rc) return rc;
   if (ctx->prefetch_enabled && (phases & (PH_REGION_CORR | PH_DEPTH_CORR))) {
-    // what the next prefetch projects the ROIs with: the poses this launch starts from (the side stream must not
-    // read d_poses while this launch writes them)
-    CU(cudaMemcpyAsync(ctx->d_poses_snap, ctx->d_poses, sizeof(float) * 12 * ctx->n_bodies, cudaMemcpyDeviceToDevice, ctx->stream));
+    // What the next prefetch projects the ROIs with: the poses this launch starts from (the side stream must not read
+    // d_poses while this launch writes them). Taken BEFORE this launch is ordered behind the ingest of its own frames,
+    // so the next ingest never waits for it; two buffers, because the ingest in flight may still be reading the
+    // snapshot of the launch before (it is finished before this buffer's turn comes again: the launch in between
+    // waits for it).
+    ctx->snap_parity ^= 1;
+    CU(cudaMemcpyAsync(ctx->d_poses_snap[ctx->snap_parity], ctx->d_poses, sizeof(float) * 12 * ctx->n_bodies,
+                       cudaMemcpyDeviceToDevice, ctx->stream));
     CU(cudaEventRecord(ctx->ev_poses_snap, ctx->stream));
     ctx->poses_snap_valid = true;
   }
+  rc = LaunchIngestIfPending(ctx);
+  if (rc) return rc;
   TrackArgs a = {};
   a.bodies = ctx->d_bodies;
   a.poses = ctx->d_poses;
@@ -1135,6 +1149,7 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
   if (prop.major != 10) return M3TB_ERR_CUDA;  // sm_100a cubin only: no other architecture can run it
   m3tb_ctx* ctx = new m3tb_ctx();
   ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
   ctx->max_bodies = max_bodies;
   ctx->max_cameras = max_cameras;
   ctx->max_models = max_models;
@@ -1181,8 +1196,8 @@ int m3tb_create(int device, int max_bodies, int max_cameras, int max_models, m3t
     CU(cudaMemset(ctx->d_roi, 0xff, sizeof(RoiRecord) * 2 * max_bodies));  // generation -1: nothing ingested yet
     CU(cudaMalloc(&ctx->d_bin_ids, sizeof(int) * max_cameras));
     CU(cudaMalloc(&ctx->d_tmaps, sizeof(CUtensorMap) * 2 * kTileWidths));
-    CU(cudaMalloc(&ctx->d_ingest_bytes, sizeof(unsigned long long)));
-    CU(cudaMemset(ctx->d_ingest_bytes, 0, sizeof(unsigned long long)));
+    CU(cudaMalloc(&ctx->d_ingest_bytes, 2 * sizeof(unsigned long long)));
+    CU(cudaMemset(ctx->d_ingest_bytes, 0, 2 * sizeof(unsigned long long)));
     if (want_timing) {
       CU(cudaMalloc(&ctx->d_phase_clock, sizeof(long long) * kPhaseSlots * max_bodies));
       CU(cudaMemset(ctx->d_phase_clock, 0, sizeof(long long) * kPhaseSlots * max_bodies));
@@ -1219,10 +1234,14 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   cudaFree(ctx->d_mem_b); cudaFree(ctx->d_lut); cudaFree(ctx->d_rstate); cudaFree(ctx->d_dstate);
   cudaFree(ctx->d_phase_clock); cudaFree(ctx->d_roi); cudaFree(ctx->d_ingest_bytes);
   cudaFree(ctx->color_pool_alt.base); cudaFree(ctx->depth_pool_alt.base); cudaFree(ctx->d_ccams_alt);
-  cudaFree(ctx->d_dcams_alt); cudaFree(ctx->d_roi_alt); cudaFree(ctx->d_poses_snap);
+  cudaFree(ctx->d_dcams_alt); cudaFree(ctx->d_roi_alt); cudaFree(ctx->d_poses_snap[0]); cudaFree(ctx->d_poses_snap[1]);
+  if (ctx->table_stream) { cudaStreamSynchronize(ctx->table_stream); cudaStreamDestroy(ctx->table_stream); }
   if (ctx->ingest_stream) { cudaStreamSynchronize(ctx->ingest_stream); cudaStreamDestroy(ctx->ingest_stream); }
+  for (int q = 0; q < 4; ++q) cudaFreeHost(ctx->h_cam_stage[q >> 1][q & 1]);
   if (ctx->ev_ingest_done) cudaEventDestroy(ctx->ev_ingest_done);
   if (ctx->ev_poses_snap) cudaEventDestroy(ctx->ev_poses_snap);
+  if (ctx->ev_tables) cudaEventDestroy(ctx->ev_tables);
+  for (int q = 0; q < 2; ++q) if (ctx->ev_stage[q]) cudaEventDestroy(ctx->ev_stage[q]);
   cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_links_default); cudaFree(ctx->d_constraints);
   cudaFree(ctx->d_gh_link);
   cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
@@ -1814,13 +1833,17 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
   }
   if (!ctx->ingest_stream) {
     CU(cudaStreamCreateWithFlags(&ctx->ingest_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->table_stream, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_ingest_done, cudaEventDisableTiming));
     CU(cudaEventCreateWithFlags(&ctx->ev_poses_snap, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&ctx->ev_tables, cudaEventDisableTiming));
+    for (int q = 0; q < 2; ++q) CU(cudaEventCreateWithFlags(&ctx->ev_stage[q], cudaEventDisableTiming));
+    for (int q = 0; q < 4; ++q) CU(cudaMallocHost(&ctx->h_cam_stage[q >> 1][q & 1], sizeof(CameraDev) * ctx->max_cameras));
     CU(cudaMalloc(&ctx->d_ccams_alt, sizeof(CameraDev) * ctx->max_cameras));
     CU(cudaMalloc(&ctx->d_dcams_alt, sizeof(CameraDev) * ctx->max_cameras));
     CU(cudaMalloc(&ctx->d_roi_alt, sizeof(RoiRecord) * 2 * ctx->max_bodies));
     CU(cudaMemset(ctx->d_roi_alt, 0xff, sizeof(RoiRecord) * 2 * ctx->max_bodies));
-    CU(cudaMalloc(&ctx->d_poses_snap, sizeof(float) * 12 * ctx->max_bodies));
+    for (int q = 0; q < 2; ++q) CU(cudaMalloc(&ctx->d_poses_snap[q], sizeof(float) * 12 * ctx->max_bodies));
   }
   for (int k = 0; k < 2; ++k) {
     ImagePool& pool = k == 0 ? ctx->color_pool : ctx->depth_pool;
@@ -1847,17 +1870,34 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
   std::swap(ctx->d_ccams, ctx->d_ccams_alt);
   std::swap(ctx->d_dcams, ctx->d_dcams_alt);
   std::swap(ctx->d_roi, ctx->d_roi_alt);
-  cudaStream_t is = ctx->ingest_stream;
-  CU(cudaMemcpyAsync(ctx->d_ccams, ctx->h_ccams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, is));
-  CU(cudaMemcpyAsync(ctx->d_dcams, ctx->h_dcams.data(), sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, is));
-  ctx->cams_dirty = false;
+  // Stream plan. The ingest stream runs the ingests back to back: anything queued on it in front of k_ingest would sit
+  // between two PCIe-bound kernels (r02: two pageable table copies + a memset + the wait for the pose snapshot were
+  // ~45 us of a 0.53 ms step). So the set-up goes to a third stream, beside the ingest in flight: wait for the pose
+  // snapshot of the last tracking launch (which also orders it behind every reader of the buffers swapped in above: they
+  // precede that launch on the main stream), camera tables from pinned staging, counter reset; the ingest stream then
+  // waits for one event that is normally long past.
+  cudaStream_t is = ctx->ingest_stream, ts = ctx->table_stream;
   const float* poses = ctx->d_poses;
   if (ctx->poses_snap_valid) {
-    CU(cudaStreamWaitEvent(is, ctx->ev_poses_snap, 0));
-    poses = ctx->d_poses_snap;
+    CU(cudaStreamWaitEvent(ts, ctx->ev_poses_snap, 0));
+    poses = ctx->d_poses_snap[ctx->snap_parity];
   } else {
     CU(cudaStreamSynchronize(ctx->stream));  // first frame: nothing in flight that could be writing the poses
   }
+  ctx->stage_parity ^= 1;  // the staging of the prefetch before this one may still be in flight; the one before that
+  CU(cudaEventSynchronize(ctx->ev_stage[ctx->stage_parity]));  // normally is not (a host that never waits could be ahead)
+  CameraDev* stage_c = ctx->h_cam_stage[ctx->stage_parity][0];
+  CameraDev* stage_d = ctx->h_cam_stage[ctx->stage_parity][1];
+  std::memcpy(stage_c, ctx->h_ccams.data(), sizeof(CameraDev) * ctx->max_cameras);
+  std::memcpy(stage_d, ctx->h_dcams.data(), sizeof(CameraDev) * ctx->max_cameras);
+  CU(cudaMemcpyAsync(ctx->d_ccams, stage_c, sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, ts));
+  CU(cudaMemcpyAsync(ctx->d_dcams, stage_d, sizeof(CameraDev) * ctx->max_cameras, cudaMemcpyHostToDevice, ts));
+  CU(cudaEventRecord(ctx->ev_stage[ctx->stage_parity], ts));
+  ctx->cams_dirty = false;
+  ctx->ingest_bytes_slot ^= 1;
+  CU(cudaMemsetAsync(ctx->d_ingest_bytes + ctx->ingest_bytes_slot, 0, sizeof(unsigned long long), ts));
+  CU(cudaEventRecord(ctx->ev_tables, ts));
+  CU(cudaStreamWaitEvent(is, ctx->ev_tables, 0));
   IngestArgs a;
   a.bodies = ctx->d_bodies;
   a.poses = poses;
@@ -1866,9 +1906,20 @@ int m3tb_prefetch_frames(m3tb_ctx* ctx) {
   a.region_models = ctx->d_rmodels;
   a.depth_models = ctx->d_dmodels;
   a.roi = ctx->d_roi;
-  a.bytes = ctx->d_ingest_bytes;
-  CU(cudaMemsetAsync(ctx->d_ingest_bytes, 0, sizeof(unsigned long long), is));
-  k_ingest<<<ctx->n_bodies, kBlockThreads, 0, is>>>(a);
+  a.bytes = ctx->d_ingest_bytes + ctx->ingest_bytes_slot;
+  a.n_bodies = ctx->n_bodies;
+  // Grid of the prefetch ingest: a quarter of the SMs, CTAs looping over the bodies. k_track2 takes a whole SM per body
+  // (1024 threads x 64 registers), so an ingest CTA that sits on an SM keeps a body waiting for as long as the ingest
+  // lasts (~0.5 ms), and whichever kernel is dispatched first wins: with one CTA per body the end-to-end step alternated
+  // between 0.36 and 0.92 ms once both kernels became ready at the same moment. The link does not need more: ~80 KB in
+  // flight saturate it (scripts/probes/pcie_probe.cu), one CTA keeps 16 KB in flight. Measured on the bench workload
+  // (128 bodies, ms per end-to-end step): 12 CTAs 0.65, 20 0.585, 24 0.567, 32 0.518, 37 0.517, 40 0.526, 48 0.546,
+  // 64 0.532, 80 0.546, 128 0.541 - 0.575 (M3TB_INGEST_CTAS overrides).
+  static const int forced_ctas = [] { const char* e = std::getenv("M3TB_INGEST_CTAS"); return e ? std::atoi(e) : 0; }();
+  int ingest_ctas = std::max(16, ctx->sm_count / 4);
+  if (forced_ctas > 0) ingest_ctas = forced_ctas;
+  ingest_ctas = std::min(ingest_ctas, ctx->n_bodies);
+  k_ingest<<<ingest_ctas, kBlockThreads, 0, is>>>(a);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev_ingest_done, is));
   ctx->launches++;
@@ -1953,7 +2004,7 @@ int m3tb_detach_frames(m3tb_ctx* ctx) {
 int m3tb_last_ingest_bytes(m3tb_ctx* ctx, unsigned long long* bytes) {
   CHECK_CTX();
   if (!bytes) return Fail(ctx, M3TB_ERR_INVALID, "null output");
-  CU(cudaMemcpyAsync(bytes, ctx->d_ingest_bytes, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(bytes, ctx->d_ingest_bytes + ctx->ingest_bytes_slot, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return M3TB_OK;
 }

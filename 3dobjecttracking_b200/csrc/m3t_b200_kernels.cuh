@@ -1666,6 +1666,7 @@ struct IngestArgs {
   const ModelDev* depth_models;
   RoiRecord* roi;
   unsigned long long* bytes;  // total bytes fetched by this launch
+  int n_bodies;               // the grid may be smaller: CTAs loop over the bodies (see m3tb_prefetch_frames)
 };
 
 __device__ __forceinline__ void IngestRect(const CameraDev& cam, const Tile& t, unsigned bpp, unsigned long long* bytes) {
@@ -1866,14 +1867,10 @@ __device__ __forceinline__ void BoxRect(const float (&box)[4], float reach_px, i
   t.x0 = x0; t.y0 = y0; t.w = x1 - x0; t.h = y1 - y0; t.pitch = t.w;
 }
 
-__global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
-  const int body_id = blockIdx.x;
+__device__ __forceinline__ void IngestBody(const IngestArgs& args, int body_id, Tile (&rect)[2], int (&todo)[2], float* s_red,
+                                           int& s_view) {
   const BodyDev& body = args.bodies[body_id];
-  if (!body.set) return;
-  __shared__ Tile rect[2];
-  __shared__ int todo[2];
-  __shared__ float s_red[5 * (kBlockThreads / 32)];
-  __shared__ int s_view;
+  if (!body.set) return;  // block-uniform
   float pose[12];
   for (int i = 0; i < 12; ++i) pose[i] = args.poses[12 * body_id + i];
   const bool region_occ = body.has_region && body.rp.measure_occlusions;
@@ -1938,6 +1935,17 @@ __global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
     else IngestRect(cc, rect[0], 3u, args.bytes);
   }
   if (todo[1]) IngestRect(args.depth_cams[body.depth_camera], rect[1], 2u, args.bytes);
+}
+
+__global__ void __launch_bounds__(kBlockThreads) k_ingest(IngestArgs args) {
+  __shared__ Tile rect[2];
+  __shared__ int todo[2];
+  __shared__ float s_red[5 * (kBlockThreads / 32)];
+  __shared__ int s_view;
+  for (int body_id = blockIdx.x; body_id < args.n_bodies; body_id += gridDim.x) {
+    IngestBody(args, body_id, rect, todo, s_red, s_view);
+    __syncthreads();  // rect / todo belong to the next body now
+  }
 }
 
 __device__ __forceinline__ float sgnf_dev(float v) { return v < 0.0f ? -1.0f : (v > 0.0f ? 1.0f : 0.0f); }
