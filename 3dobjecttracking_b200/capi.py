@@ -102,6 +102,7 @@ SYMBOLS = [
     "m3tb_n_structures", "m3tb_calculate_consistent_poses", "m3tb_get_link_poses", "m3tb_get_structure_theta",
     "m3tb_set_gradient_hessian", "m3tb_reset_joint_poses", "m3tb_prefetch_frames", "m3tb_detach_frames",
     "m3tb_debug_closest_view", "m3tb_upload_depth_rendering", "m3tb_upload_silhouette_rendering",
+    "m3tb_share_color_histograms",
 ]
 
 _lib = None
@@ -155,6 +156,7 @@ def lib():
     L.m3tb_get_poses.argtypes = [vp, ci, ci, fp]
     L.m3tb_set_histograms.argtypes = [vp, ci, fp, fp]
     L.m3tb_get_histograms.argtypes = [vp, ci, fp, fp]
+    L.m3tb_share_color_histograms.argtypes = [vp, ci, ci]
     L.m3tb_tracking_step.argtypes = [vp, ci, ci, ci]
     L.m3tb_corr_iteration.argtypes = [vp, ci, ci, ci]
     L.m3tb_start_modalities.argtypes = [vp, ci]
@@ -356,6 +358,10 @@ class Context:
         self._ck(self.L.m3tb_get_poses(self.h, first, count, _p(out)))
         return out.reshape(count, 3, 4)
 
+    def share_color_histograms(self, body, owner_body):
+        """RegionModality::UseSharedColorHistograms: `body` uses the ColorHistograms object of `owner_body` (-1: its own again)."""
+        self._ck(self.L.m3tb_share_color_histograms(self.h, body, owner_body))
+
     def set_histograms(self, body, hf, hb):
         hf, hb = _f32(hf), _f32(hb)
         self._ck(self.L.m3tb_set_histograms(self.h, body, _p(hf), _p(hb)))
@@ -537,6 +543,11 @@ def context_from_workload(wl: Workload, device=0, stream=None, upload_frames=Tru
             ctx.upload_depth_batch(0, wl.depth_frames[first:first + count])
     for b in range(count):
         ctx.set_body(b, rp, dp, op, 0, 0, b, b)
+    if getattr(wl, "histogram_owner", None) is not None:
+        for b in range(count):
+            o = int(wl.histogram_owner[first + b])
+            if o >= 0:
+                ctx.share_color_histograms(b, o - first)
     for b, per in (getattr(wl, "renderings", None) or {}).items():  # FocusedRenderer outputs, where the workload has them
         if first <= b < first + count:
             for key, r in per.items():

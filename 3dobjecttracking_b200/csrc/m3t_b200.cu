@@ -136,6 +136,13 @@ struct m3tb_ctx {
   const void* d_tmaps_bases[2] = {nullptr, nullptr};  // the pools d_tmaps currently describes
 
   // kinematic structures (empty: every body is its own rigid-body optimiser inside k_track)
+  // shared ColorHistograms objects (m3tb_share_color_histograms): per body the owner of the object it uses, -1 = its own
+  std::vector<int> hist_owner;
+  std::vector<int> hist_table_uploaded;  // what d_hist_owner / d_hist_groups hold
+  int n_hist_groups = 0;
+  int* d_hist_owner = nullptr;     // [max_bodies]
+  int* d_hist_groups = nullptr;    // group_owner[n] | group_first[n + 1] | members[...]
+  int hist_groups_capacity = 0;
   std::vector<StructureHost> structures;
   bool structures_dirty = false;
   int n_struct_launch = 0;                 // user structures + one implicit structure per unreferenced body
@@ -865,9 +872,68 @@ int LaunchHistogram(m3tb_ctx* ctx, int mode, int iteration) {
   a.roi = ctx->d_roi;
   a.depth_cams = ctx->d_dcams;
   a.iteration = iteration;
+  a.shared_owner = nullptr;
+  // shared ColorHistograms objects: group tables (owner first), checked against the bodies as they are now
+  std::vector<int> group_owner, group_first, members;
+  bool any_shared = false;
+  for (int b = 0; b < ctx->n_bodies && b < int(ctx->hist_owner.size()); ++b) any_shared = any_shared || ctx->hist_owner[b] >= 0;
+  if (any_shared) {
+    for (int o = 0; o < ctx->n_bodies; ++o) {
+      if (ctx->hist_owner[o] != o) continue;
+      group_owner.push_back(o);
+      group_first.push_back(int(members.size()));
+      members.push_back(o);
+      for (int b = 0; b < ctx->n_bodies; ++b)
+        if (b != o && ctx->hist_owner[b] == o) members.push_back(b);
+    }
+    group_first.push_back(int(members.size()));
+    for (int b = 0; b < ctx->n_bodies; ++b) {
+      const int o = ctx->hist_owner[b];
+      if (o < 0) continue;
+      const BodyDev &B = ctx->h_bodies[b], &O = ctx->h_bodies[o];
+      if (o >= ctx->n_bodies || ctx->hist_owner[o] != o || !B.set || !O.set || !B.has_region || !O.has_region ||
+          B.rp.n_bins != O.rp.n_bins)
+        return Fail(ctx, M3TB_ERR_NOT_SET_UP, "shared colour histograms: owner and member need region modalities with the same number of bins");
+    }
+    const int n_groups = int(group_owner.size());
+    std::vector<int> table(group_owner);
+    table.insert(table.end(), group_first.begin(), group_first.end());
+    table.insert(table.end(), members.begin(), members.end());
+    if (!ctx->d_hist_owner) CU(cudaMalloc(&ctx->d_hist_owner, sizeof(int) * ctx->max_bodies));
+    if (int(table.size()) > ctx->hist_groups_capacity) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->d_hist_groups);
+      ctx->d_hist_groups = nullptr;
+      CU(cudaMalloc(&ctx->d_hist_groups, sizeof(int) * table.size()));
+      ctx->hist_groups_capacity = int(table.size());
+    }
+    std::vector<int> key(table);  // groups + the per-body owners of the bodies that exist now
+    key.insert(key.end(), ctx->hist_owner.begin(), ctx->hist_owner.begin() + ctx->n_bodies);
+    if (key != ctx->hist_table_uploaded) {
+      CU(cudaStreamSynchronize(ctx->stream));  // the tables may still be read by the launch before; they change rarely
+      CU(cudaMemcpy(ctx->d_hist_owner, ctx->hist_owner.data(), sizeof(int) * ctx->n_bodies, cudaMemcpyHostToDevice));
+      CU(cudaMemcpy(ctx->d_hist_groups, table.data(), sizeof(int) * table.size(), cudaMemcpyHostToDevice));
+      ctx->hist_table_uploaded = key;
+      ctx->n_hist_groups = n_groups;
+    }
+    a.shared_owner = ctx->d_hist_owner;
+  }
   k_histogram<<<ctx->n_bodies, kBlockThreads, 0, ctx->stream>>>(a);
   CU(cudaGetLastError());
   ctx->launches++;
+  if (any_shared) {
+    SharedHistArgs s;
+    s.bodies = ctx->d_bodies;
+    s.hist_f = ctx->d_hist_f; s.hist_b = ctx->d_hist_b; s.mem_f = ctx->d_mem_f; s.mem_b = ctx->d_mem_b; s.lut = ctx->d_lut;
+    s.stride = ctx->hist_stride;
+    s.mode = mode;
+    s.group_owner = ctx->d_hist_groups;
+    s.group_first = ctx->d_hist_groups + ctx->n_hist_groups;
+    s.members = ctx->d_hist_groups + 2 * ctx->n_hist_groups + 1;
+    k_histogram_shared<<<ctx->n_hist_groups, kBlockThreads, 0, ctx->stream>>>(s);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
   return M3TB_OK;
 }
 
@@ -1244,7 +1310,7 @@ int m3tb_destroy(m3tb_ctx* ctx) {
   for (int q = 0; q < 2; ++q) if (ctx->ev_stage[q]) cudaEventDestroy(ctx->ev_stage[q]);
   cudaFree(ctx->d_structures); cudaFree(ctx->d_links); cudaFree(ctx->d_links_default); cudaFree(ctx->d_constraints);
   cudaFree(ctx->d_gh_link);
-  cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status);
+  cudaFree(ctx->d_theta); cudaFree(ctx->d_struct_status); cudaFree(ctx->d_hist_owner); cudaFree(ctx->d_hist_groups);
   delete ctx;
   return M3TB_OK;
 }
@@ -1482,14 +1548,40 @@ int m3tb_set_histograms(m3tb_ctx* ctx, int body, const float* histogram_f, const
     return Fail(ctx, M3TB_ERR_INVALID, "body has no region modality");
   const int nb = ctx->h_bodies[body].rp.n_bins;
   const int n3 = nb * nb * nb;
-  CU(cudaMemcpyAsync(ctx->d_hist_f + size_t(body) * ctx->hist_stride, histogram_f, n3 * sizeof(float),
-                     cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaMemcpyAsync(ctx->d_hist_b + size_t(body) * ctx->hist_stride, histogram_b, n3 * sizeof(float),
-                     cudaMemcpyHostToDevice, ctx->stream));
-  dim3 grid((n3 + 255) / 256, 1);
-  k_lut<<<grid, 256, 0, ctx->stream>>>(ctx->d_hist_f, ctx->d_hist_b, ctx->d_lut, n3, ctx->hist_stride, body);
-  CU(cudaGetLastError());
-  ctx->launches++;
+  const int owner = (body < int(ctx->hist_owner.size())) ? ctx->hist_owner[body] : -1;
+  for (int b = 0; b < ctx->n_bodies; ++b) {  // a shared object: every body that uses it keeps a copy
+    if (b != body && (owner < 0 || ctx->hist_owner[b] != owner)) continue;
+    if (!ctx->h_bodies[b].has_region || ctx->h_bodies[b].rp.n_bins != nb) continue;
+    CU(cudaMemcpyAsync(ctx->d_hist_f + size_t(b) * ctx->hist_stride, histogram_f, n3 * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->d_hist_b + size_t(b) * ctx->hist_stride, histogram_b, n3 * sizeof(float),
+                       cudaMemcpyHostToDevice, ctx->stream));
+    dim3 grid((n3 + 255) / 256, 1);
+    k_lut<<<grid, 256, 0, ctx->stream>>>(ctx->d_hist_f, ctx->d_hist_b, ctx->d_lut, n3, ctx->hist_stride, b);
+    CU(cudaGetLastError());
+    ctx->launches++;
+  }
+  return M3TB_OK;
+}
+
+int m3tb_share_color_histograms(m3tb_ctx* ctx, int body, int owner_body) {
+  CHECK_CTX();
+  if (body < 0 || body >= ctx->max_bodies || owner_body < -1 || owner_body >= ctx->max_bodies)
+    return Fail(ctx, M3TB_ERR_INVALID, "body index out of range");
+  if (ctx->hist_owner.empty()) ctx->hist_owner.assign(ctx->max_bodies, -1);
+  if (owner_body < 0) {  // DoNotUseSharedColorHistograms: a body that owns a shared object cannot leave it to its members
+    for (int b = 0; b < ctx->max_bodies; ++b)
+      if (b != body && ctx->hist_owner[b] == body) return Fail(ctx, M3TB_ERR_INVALID, "body owns a shared object that others still use");
+    ctx->hist_owner[body] = -1;
+  } else {
+    if (ctx->hist_owner[owner_body] >= 0 && ctx->hist_owner[owner_body] != owner_body)
+      return Fail(ctx, M3TB_ERR_INVALID, "the owner uses another body's shared object itself");
+    for (int b = 0; b < ctx->max_bodies; ++b)
+      if (b != body && body != owner_body && ctx->hist_owner[b] == body)
+        return Fail(ctx, M3TB_ERR_INVALID, "body owns a shared object that others still use");
+    ctx->hist_owner[owner_body] = owner_body;
+    ctx->hist_owner[body] = owner_body;
+  }
   return M3TB_OK;
 }
 

@@ -1644,6 +1644,24 @@ struct HistArgs {
   const RoiRecord* roi;
   const CameraDev* depth_cams;  // measured occlusion handling
   int iteration;
+  const int* shared_owner;      // per body: -1 = its own ColorHistograms, else the owner of the shared one (or null: none shared)
+};
+
+// RegionModality::UseSharedColorHistograms (region_modality.cpp:168-179): the members of a group only ADD their line
+// pixels (k_histogram, into their own count arrays); the tracker then runs InitializeHistograms / UpdateHistograms once on
+// the shared object (tracker.cpp:435-443, 507-515) - k_histogram_shared, one CTA per group.
+struct SharedHistArgs {
+  const BodyDev* bodies;
+  float* hist_f;
+  float* hist_b;
+  float* mem_f;
+  float* mem_b;
+  float2* lut;
+  size_t stride;
+  int mode;
+  const int* group_owner;   // [n_groups]
+  const int* group_first;   // [n_groups + 1] into members
+  const int* members;       // body indices, owner first
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -2082,6 +2100,7 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
   }
   __threadfence();
   __syncthreads();
+  if (args.shared_owner && args.shared_owner[body_id] >= 0) return;  // shared ColorHistograms: k_histogram_shared finishes
   // CalculateHistogram (color_histograms.cpp:174-214)
   float sf = 0.0f, sb = 0.0f;
   for (int k = tid; k < nbins3; k += kBlockThreads) { sf += mem_f[k]; sb += mem_b[k]; }
@@ -2120,6 +2139,77 @@ __global__ void __launch_bounds__(kBlockThreads) k_histogram(HistArgs args) {
     hist_f[k] = hf;
     hist_b[k] = hb;
     lut[LutSlot(unsigned(k))] = NormaliseBin(hf, hb);
+  }
+}
+
+// One CTA per shared ColorHistograms object. The members' counts are whole numbers, so their sum (and the sum over the
+// bins) is exact in any order as long as it stays below 2^24 - the same value the reference gets by adding pixel after
+// pixel into one array. Then CalculateHistogram with the OWNER's learning rates, and the result goes to every member's
+// copy of the histograms and of the lookup table (the tracking kernels keep reading per-body tables).
+__global__ void __launch_bounds__(kBlockThreads) k_histogram_shared(SharedHistArgs args) {
+  __shared__ float s_sum[2][kWarps];
+  const int g = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int owner = args.group_owner[g];
+  const int first = args.group_first[g], last = args.group_first[g + 1];
+  const RegionParamsDev& rp = args.bodies[owner].rp;
+  const int nbins3 = rp.n_bins * rp.n_bins * rp.n_bins;
+  float* mem_f = args.mem_f + size_t(owner) * args.stride;
+  float* mem_b = args.mem_b + size_t(owner) * args.stride;
+  float* hist_f = args.hist_f + size_t(owner) * args.stride;
+  float* hist_b = args.hist_b + size_t(owner) * args.stride;
+  float sf = 0.0f, sb = 0.0f;
+  for (int k = tid; k < nbins3; k += kBlockThreads) {
+    float mf = 0.0f, mb = 0.0f;
+    for (int q = first; q < last; ++q) {
+      const size_t off = size_t(args.members[q]) * args.stride + k;
+      mf += args.mem_f[off];
+      mb += args.mem_b[off];
+    }
+    mem_f[k] = mf;  // the owner is members[first]: its own counts were read above, by this thread
+    mem_b[k] = mb;
+    sf += mf;
+    sb += mb;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sf += __shfl_down_sync(0xffffffffu, sf, off);
+    sb += __shfl_down_sync(0xffffffffu, sb, off);
+  }
+  if (lane == 0) { s_sum[0][warp] = sf; s_sum[1][warp] = sb; }
+  __syncthreads();
+  float sum_f = 0.0f, sum_b = 0.0f;
+  for (int w = 0; w < kWarps; ++w) { sum_f += s_sum[0][w]; sum_b += s_sum[1][w]; }
+  const float lr_f = args.mode == 0 ? 1.0f : rp.learning_rate_f;
+  const float lr_b = args.mode == 0 ? 1.0f : rp.learning_rate_b;
+  const float uniform = 1.0f / float(nbins3);
+  const float cf = 1.0f - lr_f, cb = 1.0f - lr_b;
+  const float rf = lr_f / sum_f, rb = lr_b / sum_b;
+  for (int k = tid; k < nbins3; k += kBlockThreads) {  // each thread revisits the bins it summed
+    float hf = hist_f[k], hb = hist_b[k];
+    if (sum_f == 0.0f) {
+      if (lr_f == 1.0f) hf = uniform;
+    } else if (cf == 0.0f) {
+      hf = mem_f[k] * rf;
+    } else {
+      hf *= cf;
+      hf += mem_f[k] * rf;
+    }
+    if (sum_b == 0.0f) {
+      if (lr_b == 1.0f) hb = uniform;
+    } else if (cb == 0.0f) {
+      hb = mem_b[k] * rb;
+    } else {
+      hb *= cb;
+      hb += mem_b[k] * rb;
+    }
+    const float2 l = NormaliseBin(hf, hb);
+    for (int q = first; q < last; ++q) {
+      const size_t base = size_t(args.members[q]) * args.stride;
+      args.hist_f[base + k] = hf;
+      args.hist_b[base + k] = hb;
+      args.lut[base + LutSlot(unsigned(k))] = l;
+    }
   }
 }
 

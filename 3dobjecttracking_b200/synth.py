@@ -250,6 +250,7 @@ class Workload:
     structures: list | None = None          # [StructureSpec] (kinematic structures, config 5); None = rigid bodies
     color_world2camera_per_body: np.ndarray | None = None   # [nb,3,4]: multi-camera rigs (default: one pose for all)
     depth_world2camera_per_body: np.ndarray | None = None
+    histogram_owner: np.ndarray | None = None   # [nb] int: body whose ColorHistograms object this body uses (-1: its own)
     renderings: dict | None = None          # {body: {"region_depth" | "region_silhouette" | "depth_depth" | "depth_silhouette": Rendering}}
 
     @property

@@ -284,6 +284,15 @@ int m3tb_get_poses(m3tb_ctx* ctx, int first, int count, float* body2world);
 int m3tb_set_histograms(m3tb_ctx* ctx, int body, const float* histogram_f, const float* histogram_b);
 int m3tb_get_histograms(m3tb_ctx* ctx, int body, float* histogram_f, float* histogram_b);
 
+/* RegionModality::UseSharedColorHistograms / DoNotUseSharedColorHistograms (region_modality.cpp:168-179): `body` uses
+ * the ColorHistograms object of `owner_body` (owner_body == -1: its own again). Members of a shared object only add their
+ * line pixels in m3tb_start_modalities / m3tb_calculate_results; the object is initialised / updated ONCE from the sum of
+ * all members' pixels (tracker.cpp:435-443, 507-515) with the owner's n_histogram_bins and learning rates (the shared
+ * object's own parameters, color_histograms.h). The owner must not use another body's object itself; owner and members
+ * need the same n_histogram_bins (checked at the next launch). m3tb_get_histograms of a member returns the shared
+ * values, m3tb_set_histograms on any user sets them for all users. */
+int m3tb_share_color_histograms(m3tb_ctx* ctx, int body, int owner_body);
+
 /* ---- the hot path, fused: Tracker::ExecuteTrackingStep without CalculateResults (tracker.cpp:344-361)
  * for every body of the context: for corr in [0,n_corr): CalculateCorrespondences; for upd in
  * [0,n_update): CalculateGradientAndHessian + Optimizer::CalculateOptimization. One kernel launch. */

@@ -1325,7 +1325,46 @@ static void StartOne(orc_body* b, int iteration, int rotation_mode) {
   orc_hist_calculate(nb, 1.0f, mb.data(), b->histogram_b);
 }
 
+// RegionModality::UseSharedColorHistograms (region_modality.cpp:168-179): bodies whose histogram_f pointers are equal use
+// ONE ColorHistograms object. Their modalities only add their line pixels (StartModality :382-386, CalculateResults
+// :575-582 skip ClearMemory / Initialize / Update); the tracker clears the object before and initialises / updates it
+// once after all modalities (tracker.cpp:435-443, 507-515). The object's own learning rates (color_histograms.h) are
+// taken from the first body of the group. Returns false if no body shares anything (the per-body path then runs).
+static bool SharedHistogramPass(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, bool start) {
+  std::vector<int> leader(n_bodies);
+  bool any = false;
+  for (int i = 0; i < n_bodies; ++i) {
+    leader[i] = i;
+    if (!bodies[i].region) continue;
+    for (int j = 0; j < i; ++j)
+      if (bodies[j].region && bodies[j].histogram_f == bodies[i].histogram_f) { leader[i] = j; any = true; break; }
+  }
+  if (!any) return false;
+  for (int l = 0; l < n_bodies; ++l) {
+    if (leader[l] != l) continue;
+    orc_body* L = &bodies[l];
+    if (start) L->first_iteration = iteration;
+    if (!L->region) continue;
+    int nb = L->region->n_histogram_bins;
+    size_t n = size_t(nb) * nb * nb;
+    std::vector<float> mf(n, 0.0f), mb(n, 0.0f);  // ClearMemory
+    for (int i = l; i < n_bodies; ++i) {
+      if (leader[i] != l) continue;
+      orc_body* b = &bodies[i];
+      if (start) b->first_iteration = iteration;
+      const bool handle_occlusions = start ? b->region->n_unoccluded_iterations == 0
+                                           : (iteration - b->first_iteration) >= b->region->n_unoccluded_iterations;
+      orc_region_add_line_pixels_occ(b->region, b->region_model, b->color, b->region_occlusion_frame, handle_occlusions,
+                                     b->body2world, rotation_mode, mf.data(), mb.data());
+    }
+    orc_hist_calculate(nb, start ? 1.0f : L->region->learning_rate_f, mf.data(), L->histogram_f);
+    orc_hist_calculate(nb, start ? 1.0f : L->region->learning_rate_b, mb.data(), L->histogram_b);
+  }
+  return true;
+}
+
 void orc_start_modalities(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads) {
+  if (SharedHistogramPass(bodies, n_bodies, iteration, rotation_mode, true)) return;
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
   for (int i = 0; i < n_bodies; ++i) StartOne(&bodies[i], iteration, rotation_mode);
 }
@@ -1344,6 +1383,7 @@ static void ResultsOne(orc_body* b, int iteration, int rotation_mode) {
 }
 
 void orc_calculate_results(orc_body* bodies, int n_bodies, int iteration, int rotation_mode, int n_threads) {
+  if (SharedHistogramPass(bodies, n_bodies, iteration, rotation_mode, false)) return;
 #pragma omp parallel for schedule(dynamic) num_threads(n_threads > 0 ? n_threads : 1)
   for (int i = 0; i < n_bodies; ++i) ResultsOne(&bodies[i], iteration, rotation_mode);
 }

@@ -409,8 +409,10 @@ class OracleTracker:
                 B.region = C.pointer(self.rp)
                 B.region_model = C.pointer(self.rm)
                 B.color = C.pointer(cf)
-                B.histogram_f = ptr(self.hist_f[b])
-                B.histogram_b = ptr(self.hist_b[b])
+                # shared ColorHistograms (UseSharedColorHistograms): the members point at the owner's arrays
+                own = b if getattr(wl, "histogram_owner", None) is None or wl.histogram_owner[b] < 0 else int(wl.histogram_owner[b])
+                B.histogram_f = ptr(self.hist_f[own])
+                B.histogram_b = ptr(self.hist_b[own])
                 B.lines = self.lines[b].ctypes.data_as(C.POINTER(RegionLine))
                 if wl.region.measure_occlusions and wl.depth_frames is not None:
                     of = self.occlusion_frames[b]
@@ -464,8 +466,18 @@ class OracleTracker:
     def get_poses(self):
         return np.array([list(self.bodies[b].body2world) for b in range(self.wl.n_bodies)], np.float32).reshape(-1, 3, 4)
 
+    def _mirror_shared_histograms(self):
+        """hist_f[b] / hist_b[b] of a member of a shared object show the owner's values (the C side only writes the owner's)."""
+        owner = getattr(self.wl, "histogram_owner", None)
+        if owner is not None:
+            for b, o in enumerate(owner):
+                if o >= 0 and o != b:
+                    self.hist_f[b] = self.hist_f[o]
+                    self.hist_b[b] = self.hist_b[o]
+
     def start_modalities(self, iteration=0):
         self.L.orc_start_modalities(self.bodies, self.wl.n_bodies, iteration, self.rotation_mode, self.n_threads)
+        self._mirror_shared_histograms()
 
     def tracking_step(self, iteration=0, n_corr=None, n_update=None, first=None, count=None, corr_begin=0):
         """Runs corr iterations [corr_begin, n_corr) for bodies [first, first+count).
@@ -487,6 +499,7 @@ class OracleTracker:
 
     def calculate_results(self, iteration=0):
         self.L.orc_calculate_results(self.bodies, self.wl.n_bodies, iteration, self.rotation_mode, self.n_threads)
+        self._mirror_shared_histograms()
 
     # fine-grained, one body
     def region_correspondences(self, b, iteration, corr):
