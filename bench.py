@@ -419,7 +419,7 @@ def run_reference(args):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
 
 
 def run_b200(args):
@@ -629,14 +629,34 @@ def run_b200(args):
                                    "sample": f"{n_cpu_steps} full steps of the same workload ({nb} bodies x {n_corr} corr iterations), OpenMP over bodies, thread count chosen by sustained rate",
                                    "best_step_value": r["best_step_value"], "single_thread_value": r1["value"],
                                    "phase_split_cpu_seconds": r["phase_split_cpu_seconds"]}
-        print(json.dumps(out))
+        emit(json.dumps(out))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the result. Libraries write there too (NCCL prints its version banner on stdout at
+    every debug level but NONE, OpenMP runtimes their warnings): keep a private handle on the real stdout for the result
+    and point file descriptor 1 at stderr for everything else, in this process and its children."""
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(line + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
