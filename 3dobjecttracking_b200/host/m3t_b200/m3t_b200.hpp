@@ -323,6 +323,33 @@ class Modality {
 };
 
 // ---- region_modality.h --------------------------------------------------------------------------------------------
+// ---- color_histograms.h: only what a SHARED object needs (a modality's own histograms live with its body) ---------------
+// The object's n_bins and learning rates (color_histograms.h:38-45) stand for those of every modality that uses it; on
+// the device they are the parameters of the owner, the body of the first modality the object was given to.
+class ColorHistograms {
+ public:
+  explicit ColorHistograms(const std::string& name, int n_bins = 16, float learning_rate_f = 0.2f, float learning_rate_b = 0.2f)
+      : name_(name), n_bins_(n_bins), learning_rate_f_(learning_rate_f), learning_rate_b_(learning_rate_b) {}
+  const std::string& name() const { return name_; }
+  void set_n_bins(int v) { n_bins_ = v; }
+  void set_learning_rate_f(float v) { learning_rate_f_ = v; }
+  void set_learning_rate_b(float v) { learning_rate_b_ = v; }
+  int n_bins() const { return n_bins_; }
+  float learning_rate_f() const { return learning_rate_f_; }
+  float learning_rate_b() const { return learning_rate_b_; }
+  bool SetUp() { set_up_ = true; return true; }
+  bool set_up() const { return set_up_; }
+  int owner_body() const { return owner_body_; }
+  void claim_owner(int body) { if (owner_body_ < 0) owner_body_ = body; }
+
+ private:
+  std::string name_;
+  int n_bins_;
+  float learning_rate_f_, learning_rate_b_;
+  bool set_up_ = false;
+  int owner_body_ = -1;
+};
+
 class RegionModality : public Modality {
  public:
   RegionModality(const std::string& name, const std::shared_ptr<Batch>& batch, const std::shared_ptr<Body>& body_ptr,
@@ -347,16 +374,44 @@ class RegionModality : public Modality {
     for (size_t i = 0; i < v.size() && i < M3TB_MAX_SCHEDULE; ++i) params_.standard_deviations[i] = v[i];
     set_up_ = false;
   }
-  void set_n_histogram_bins(int v) { params_.n_histogram_bins = v; set_up_ = false; }
-  void set_learning_rate_f(float v) { params_.learning_rate_f = v; set_up_ = false; }
-  void set_learning_rate_b(float v) { params_.learning_rate_b = v; set_up_ = false; }
+  // region_modality.cpp:168-203: with a shared ColorHistograms object the three histogram parameters are the object's
+  void UseSharedColorHistograms(const std::shared_ptr<ColorHistograms>& color_histograms_ptr) {
+    color_histograms_ptr_ = color_histograms_ptr;
+    set_up_ = false;
+  }
+  void DoNotUseSharedColorHistograms() { color_histograms_ptr_ = nullptr; set_up_ = false; }
+  const std::shared_ptr<ColorHistograms>& color_histograms_ptr() const { return color_histograms_ptr_; }
+  bool set_n_histogram_bins(int v) {
+    if (color_histograms_ptr_) { std::cerr << "Modality " << name_ << " uses shared color histograms" << std::endl; return false; }
+    params_.n_histogram_bins = v; set_up_ = false; return true;
+  }
+  bool set_learning_rate_f(float v) {
+    if (color_histograms_ptr_) { std::cerr << "Modality " << name_ << " uses shared color histograms" << std::endl; return false; }
+    params_.learning_rate_f = v; set_up_ = false; return true;
+  }
+  bool set_learning_rate_b(float v) {
+    if (color_histograms_ptr_) { std::cerr << "Modality " << name_ << " uses shared color histograms" << std::endl; return false; }
+    params_.learning_rate_b = v; set_up_ = false; return true;
+  }
   void set_unconsidered_line_length(float v) { params_.unconsidered_line_length = v; set_up_ = false; }
   void set_max_considered_line_length(float v) { params_.max_considered_line_length = v; set_up_ = false; }
   const m3tb_region_params& params() const { return params_; }
   const std::shared_ptr<ColorCamera>& color_camera_ptr() const { return color_camera_ptr_; }
   const std::shared_ptr<RegionModel>& region_model_ptr() const { return region_model_ptr_; }
 
-  bool SetUp() override { set_up_ = true; return true; }  // the body's device record is written by Optimizer::SetUp
+  bool SetUp() override {  // the body's device record is written by Optimizer::SetUp
+    if (color_histograms_ptr_) {
+      if (!color_histograms_ptr_->set_up()) {
+        std::cerr << "Color histograms " << color_histograms_ptr_->name() << " was not set up" << std::endl;
+        return false;
+      }
+      params_.n_histogram_bins = color_histograms_ptr_->n_bins();
+      params_.learning_rate_f = color_histograms_ptr_->learning_rate_f();
+      params_.learning_rate_b = color_histograms_ptr_->learning_rate_b();
+    }
+    set_up_ = true;
+    return true;
+  }
   bool StartModality(int iteration, int corr_iteration) override {
     if (!IsSetup()) return false;
     (void)corr_iteration;
@@ -393,6 +448,7 @@ class RegionModality : public Modality {
   m3tb_region_params params_;
   std::shared_ptr<ColorCamera> color_camera_ptr_;
   std::shared_ptr<RegionModel> region_model_ptr_;
+  std::shared_ptr<ColorHistograms> color_histograms_ptr_;  // null: the modality's own histograms
 };
 
 // ---- depth_modality.h ----------------------------------------------------------------------------------------------
@@ -728,6 +784,7 @@ class Optimizer {
     const m3tb_region_params* rp = nullptr;
     const m3tb_depth_params* dp = nullptr;
     int rmodel = 0, dmodel = 0, ccam = 0, dcam = 0;
+    std::shared_ptr<ColorHistograms> shared;
     for (auto& m : link.modality_ptrs()) {
       if (!m->set_up()) {
         std::cerr << "Modality " << m->name() << " was not set up" << std::endl;
@@ -737,14 +794,31 @@ class Optimizer {
         rp = &r->params();
         rmodel = r->region_model_ptr()->index();
         ccam = r->color_camera_ptr()->index();
+        shared = r->color_histograms_ptr();
       } else if (auto d = std::dynamic_pointer_cast<DepthModality>(m)) {
         dp = &d->params();
         dmodel = d->depth_model_ptr()->index();
         dcam = d->depth_camera_ptr()->index();
       }
     }
-    return Check(batch_->ctx(), m3tb_set_body(batch_->ctx(), link.body_ptr()->index(), rp, dp, &params_, rmodel, dmodel, ccam, dcam),
-                 "Optimizer::SetUp");
+    const int body = link.body_ptr()->index();
+    if (!Check(batch_->ctx(), m3tb_set_body(batch_->ctx(), body, rp, dp, &params_, rmodel, dmodel, ccam, dcam), "Optimizer::SetUp"))
+      return false;
+    if (rp && shared) {  // UseSharedColorHistograms: the first body the object was given to owns it on the device
+      shared->claim_owner(body);
+      if (!Check(batch_->ctx(), m3tb_share_color_histograms(batch_->ctx(), body, shared->owner_body()),
+                 "RegionModality::UseSharedColorHistograms"))
+        return false;
+      if (std::find(shared_bodies_.begin(), shared_bodies_.end(), body) == shared_bodies_.end()) shared_bodies_.push_back(body);
+    } else {
+      auto it = std::find(shared_bodies_.begin(), shared_bodies_.end(), body);
+      if (it != shared_bodies_.end()) {  // DoNotUseSharedColorHistograms since the last SetUp
+        if (!Check(batch_->ctx(), m3tb_share_color_histograms(batch_->ctx(), body, -1), "RegionModality::DoNotUseSharedColorHistograms"))
+          return false;
+        shared_bodies_.erase(it);
+      }
+    }
+    return true;
   }
   bool SetUpStructure(const std::vector<std::shared_ptr<Link>>& links) {
     auto index_of = [&](const std::shared_ptr<Link>& l) {
@@ -804,6 +878,7 @@ class Optimizer {
   std::vector<std::shared_ptr<Constraint>> constraint_ptrs_;
   std::vector<std::shared_ptr<SoftConstraint>> soft_constraint_ptrs_;
   m3tb_optimizer_params params_{};
+  std::vector<int> shared_bodies_;  // bodies whose region modality was set up with a shared ColorHistograms object
   int structure_index_ = -1;
   bool set_up_ = false;
 };

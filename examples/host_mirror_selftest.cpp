@@ -60,6 +60,26 @@ int main() {
   EXPECT(soft->standard_deviation_rotation() == 0.01f && soft->standard_deviation_translation() == 0.001f);
   EXPECT(soft->max_distance_rotation() == 0.0f);
 
+  // Shared colour histograms (region_modality.cpp:168-203): the object's parameters replace the modality's, the modality's
+  // own setters refuse while it is shared, and SetUp needs the object set up first
+  {
+    Intrinsics intr{600.0f, 600.0f, 320.0f, 240.0f, 640, 480};
+    auto camera = std::make_shared<ColorCamera>("camera_h", batch, intr, Transform3fA::Identity());
+    auto model = std::make_shared<RegionModel>("model_h", batch);
+    auto modality = std::make_shared<RegionModality>("region_h", batch, body, camera, model);
+    auto histograms = std::make_shared<ColorHistograms>("histograms", 32, 0.3f, 0.1f);
+    EXPECT(modality->set_n_histogram_bins(16));
+    modality->UseSharedColorHistograms(histograms);
+    EXPECT(!modality->set_n_histogram_bins(8) && !modality->set_learning_rate_f(0.5f) && !modality->set_learning_rate_b(0.5f));
+    EXPECT(!modality->SetUp());                        // "Color histograms histograms was not set up"
+    EXPECT(histograms->SetUp() && modality->SetUp());
+    EXPECT(modality->params().n_histogram_bins == 32 && modality->params().learning_rate_f == 0.3f &&
+           modality->params().learning_rate_b == 0.1f);
+    EXPECT(histograms->owner_body() == -1);            // claimed by the first Optimizer::SetUp that sees it
+    modality->DoNotUseSharedColorHistograms();
+    EXPECT(!modality->set_up() && modality->set_n_histogram_bins(16) && modality->SetUp());
+  }
+
   // Tracker refuses to run before SetUp (tracker.cpp:224-228)
   Tracker tracker("tracker", batch);
   EXPECT(!tracker.ExecuteTrackingStep(0));
